@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of MMRec on B200, measured per BASELINE.json.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
+
+Workload (N=1): BASELINE.json configs[1] -- FREEDOM on the synthetic baby-shaped graph (20k users, 7k items,
+160k train edges, d=64, 3 UI layers + 1 item-graph layer), then full-catalog scoring + mask + top-50 for every
+user in batches of 4096 (`eval_batch_size`, src/configs/overall.yaml:45).  One step =
+    [A] propagation   forward(norm_adj): 1 SpMM on mm_adj (fused `+h`) + 3 SpMMs on A_hat (fused layer mean)
+    [B] projection    image/text Linear(4096->64) over the whole feature table (the calculate_loss form)
+    [C] scoring       U x I scores + train-positive mask + top-50, all users
+`value` = graph-prop edges/s = sum of nnz over the SpMMs of [A] / device time of [A]; the second half of the
+metric (scored-items/s = users x items / device time of [C]) and the projection rate are in `extra`.
+Timing: CUDA events on the launch stream around each section, L2 flushed (512 MiB write) before every step,
+max over ranks.  `e2e` repeats [A] and [C] through the same public API with HOST buffers (pinned), copies inside
+the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mmrec_b200.utils import synth  # noqa: E402
+
+TOPK = 50
+EVAL_BATCH = 4096
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, name, n_layers=3, seed=0, items_scale=1):
+        self.name = name
+        U, I, E, d, F = synth.SHAPES[name]
+        self.g = synth.make_graph(U, I * items_scale, E * items_scale, seed)
+        self.U, self.I, self.d, self.F = U, I * items_scale, d, F
+        self.n_layers = n_layers
+        self.tr_u, self.tr_i = self.g.train
+        rng = np.random.default_rng(7)
+        bound = np.sqrt(6.0 / (self.U + d))                       # xavier_uniform, freedom.py:51-52
+        self.user_emb = rng.uniform(-bound, bound, (self.U, d)).astype(np.float32)
+        bound = np.sqrt(6.0 / (self.I + d))
+        self.item_emb = rng.uniform(-bound, bound, (self.I, d)).astype(np.float32)
+
+    def features(self, rows=None):
+        rng = np.random.default_rng(11)
+        n = self.I if rows is None else rows
+        return rng.standard_normal((n, self.F), dtype=np.float32), rng.standard_normal((n, self.F), dtype=np.float32)
+
+    def knn_coo(self, k=10, seed=3):
+        """Synthetic stand-in for FREEDOM's mm_adj structure at bench scale when the dense I x I similarity is
+        skipped: k random neighbours per item from each modality, 0.1/0.9 weights (freedom.py:74)."""
+        rng = np.random.default_rng(seed)
+        rows = np.repeat(np.arange(self.I), k)
+        c1, c2 = rng.integers(0, self.I, self.I * k), rng.integers(0, self.I, self.I * k)
+        w = np.float32(np.float32(1.0 / np.sqrt(np.float32(k))) ** 2)
+        return (np.concatenate([rows, rows]), np.concatenate([c1, c2]),
+                np.concatenate([np.full(self.I * k, 0.1 * w, np.float32), np.full(self.I * k, 0.9 * w, np.float32)]))
+
+    def eval_mask(self, lo, hi):
+        m = (self.tr_u >= lo) & (self.tr_u < hi)
+        order = np.argsort(self.tr_u[m], kind="stable")
+        return np.stack([self.tr_u[m][order] - lo, self.tr_i[m][order]])
+
+
+# ------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from mmrec_b200 import graph, ops
+    from mmrec_b200.ops import CSR
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from mmrec_b200 import sharded
+        return sharded.bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler)
+
+    wl = Workload(args.workload, n_layers=3)
+    U, I, d = wl.U, wl.I, wl.d
+    n = U + I
+    adj = graph.build_norm_adj((wl.tr_u, wl.tr_i), U, I, dev)
+    kr, kc, kv = wl.knn_coo()
+    mm = CSR.from_coo(torch.from_numpy(kr).to(dev), torch.from_numpy(kc).to(dev), torch.from_numpy(kv).to(dev), I, I)
+    ego_h = torch.from_numpy(np.concatenate([wl.user_emb, wl.item_emb])).pin_memory()
+    ego = ego_h.to(dev)
+    vf, tf = wl.features()
+    vf, tf = torch.from_numpy(vf).to(dev), torch.from_numpy(tf).to(dev)
+    rng = np.random.default_rng(5)
+    Wv = torch.from_numpy((rng.standard_normal((d, wl.F)) / np.sqrt(wl.F)).astype(np.float32)).to(dev)
+    Wt = torch.from_numpy((rng.standard_normal((d, wl.F)) / np.sqrt(wl.F)).astype(np.float32)).to(dev)
+    bv, bt = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    batches = []
+    for lo in range(0, U, EVAL_BATCH):
+        hi = min(U, lo + EVAL_BATCH)
+        m = torch.from_numpy(wl.eval_mask(lo, hi))
+        batches.append((torch.arange(lo, hi), m, m.pin_memory()))
+    batches_dev = [(u.to(dev), m.to(dev)) for u, m, _ in batches]
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    item_ego = ego[U:]
+
+    def propagate():
+        all_emb = ops.propagate_mean(adj, ego, wl.n_layers)
+        i_out = ops.spmm(mm, item_ego, base=all_emb[U:])
+        return all_emb[:U], i_out
+
+    edges = wl.n_layers * adj.nnz + mm.nnz
+    spmm_bytes = wl.n_layers * adj.algorithmic_bytes(d) + mm.algorithmic_bytes(d)
+    proj_bytes = 2 * (4 * I * wl.F + 4 * d * wl.F + 4 * I * d)
+    proj_flops = 2 * 2 * I * wl.F * d
+    score_items = U * I
+    score_flops = 2 * U * I * d
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    tA = tB = tC = 0.0
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    launches0 = 0
+    with torch.no_grad():
+        for step in range(args.warmup + args.steps):
+            if step == args.warmup:
+                torch.cuda.synchronize()
+                sampler.start()
+                launches0 = ops.LAUNCHES
+                wall0 = time.perf_counter()
+            flush.zero_()                                            # evict L2 (126 MB) between steps
+            e = [ev() for _ in range(6)]
+            e[0].record()
+            u_g, i_g = propagate()
+            e[1].record()
+            e[2].record()
+            pv = ops.project(vf, Wv, bv)
+            pt = ops.project(tf, Wt, bt)
+            e[3].record()
+            e[4].record()
+            outs = [ops.score_topk(u_g, i_g, users, mask, TOPK) for users, mask in batches_dev]
+            e[5].record()
+            torch.cuda.synchronize()
+            if step >= args.warmup:
+                tA += e[0].elapsed_time(e[1]); tB += e[2].elapsed_time(e[3]); tC += e[4].elapsed_time(e[5])
+    wall = time.perf_counter() - wall0
+    launches = ops.LAUNCHES - launches0
+    clocks = sampler.stop()
+    K = args.steps
+    msA, msB, msC = tA / K, tB / K, tC / K
+
+    # ---- e2e: same public API, HOST buffers, copies inside the timed region
+    e2e_A = e2e_C = 0.0
+    h2d = d2h = 0
+    out_u = torch.empty(U, d).pin_memory(); out_i = torch.empty(I, d).pin_memory()
+    out_idx = [torch.empty(b[0].numel(), TOPK, dtype=torch.int64).pin_memory() for b in batches]
+    users_h = [b[0].pin_memory() for b in batches]
+    with torch.no_grad():
+        for step in range(args.warmup + args.steps):
+            flush.zero_()
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            ego_d = ego_h.to(dev, non_blocking=True)
+            all_emb = ops.propagate_mean(adj, ego_d, wl.n_layers)
+            i_out = ops.spmm(mm, ego_d[U:], base=all_emb[U:])
+            out_u.copy_(all_emb[:U], non_blocking=True); out_i.copy_(i_out, non_blocking=True)
+            e[1].record()
+            e[2].record()
+            for (u, m, mp), uh, oh in zip(batches, users_h, out_idx):
+                ud, md = uh.to(dev, non_blocking=True), mp.to(dev, non_blocking=True)
+                _, idx = ops.score_topk(all_emb[:U], i_out, ud, md, TOPK)
+                oh.copy_(idx, non_blocking=True)
+            e[3].record()
+            torch.cuda.synchronize()
+            if step >= args.warmup:
+                e2e_A += e[0].elapsed_time(e[1]); e2e_C += e[2].elapsed_time(e[3])
+    h2d = ego_h.numel() * 4 + sum(uh.numel() * 8 + b[2].numel() * 8 for uh, b in zip(users_h, batches))
+    d2h = (out_u.numel() + out_i.numel()) * 4 + sum(o.numel() * 8 for o in out_idx)
+    e2e_msA, e2e_msC = e2e_A / K, e2e_C / K
+
+    pk = peaks()
+    ui_bytes = adj.algorithmic_bytes(d)
+    res = {
+        "metric": "graph-prop edges/sec (+ full-catalog scored-items/sec in extra) @ d=64",
+        "value": edges / (msA * 1e-3), "unit": "edges/s", "n_gpus": 1, "steps": K, "warmup": args.warmup,
+        "ms_per_step": msA + msB + msC, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"FREEDOM synthetic {wl.name}: {U} users, {I} items, {len(wl.tr_u)} train edges, d={d}, "
+                               f"{wl.n_layers} UI layers + 1 mm layer, top-{TOPK} over all users, eval batch {EVAL_BATCH}",
+                   "l2": "flushed (512 MiB write) before every step", "parallelism": "1 GPU"},
+        "extra": {"prop_ms": msA, "proj_ms": msB, "score_topk_ms": msC,
+                  "scored_items_per_sec": score_items / (msC * 1e-3),
+                  "projected_rows_per_sec": 2 * I / (msB * 1e-3),
+                  "edges_per_step": edges, "scored_items_per_step": score_items,
+                  "wall_s_timed_region": wall, "score_path": os.environ.get("MMREC_SCORE_PATH", "tc")},
+        "roofline": {"kernel": "spmm_vec_kernel<64> (4 launches: 3 x A_hat + mm_adj)", "bound": "hbm",
+                     "achieved": spmm_bytes / (msA * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": spmm_bytes / (msA * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
+                     "algorithmic_bytes_per_launch_ui": ui_bytes},
+        "roofline_projection": {"kernel": "gemm_nt_kernel<32,64,2,4> (2 launches)", "bound": "hbm",
+                                "achieved": proj_bytes / (msB * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                "frac": proj_bytes / (msB * 1e-3) / 1e9 / pk["hbm_gbs"], "tflops": proj_flops / (msB * 1e-3) / 1e12},
+        "roofline_scoring": {"kernel": "score + mask + topk_rows", "bound": "tensor",
+                             "achieved": score_flops / (msC * 1e-3) / 1e12, "peak": pk["bf16_tflops"] / 2, "unit": "TFLOP/s",
+                             "frac": score_flops / (msC * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
+                             "note": "peak = measured bf16 dense / 2 (TF32 rate); useful flops 2*B*I*d"},
+        "e2e": {"value": edges / (e2e_msA * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "prop_ms": e2e_msA, "score_topk_ms": e2e_msC, "scored_items_per_sec": score_items / (e2e_msC * 1e-3)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline(wl, kr, kc, kv, steps=3)
+    print(json.dumps(res))
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port: same torch CPU ops in the same order as the reference)
+# ------------------------------------------------------------------------------------------------------
+def cpu_setup(wl, kr, kc, kv):
+    from oracle import mmrec_oracle as O
+    adj = O.norm_adj_coo(wl.tr_u, wl.tr_i, wl.U, wl.I)
+    mm = torch.sparse_coo_tensor(torch.from_numpy(np.stack([kr, kc])), torch.from_numpy(kv), (wl.I, wl.I), check_invariants=False)
+    return O, adj, mm, torch.from_numpy(wl.user_emb), torch.from_numpy(wl.item_emb)
+
+
+def cpu_step(O, wl, adj, mm, ue, ie, n_eval_batches=1):
+    t0 = time.perf_counter()
+    u_g, i_g = O.freedom_forward(adj, mm, ue, ie, 1, wl.n_layers)          # freedom.py:164-178
+    t1 = time.perf_counter()
+    scored = 0
+    for b in range(n_eval_batches):
+        lo = (b * EVAL_BATCH) % wl.U
+        hi = min(wl.U, lo + EVAL_BATCH)
+        users = torch.arange(lo, hi)
+        mask = torch.from_numpy(wl.eval_mask(lo, hi))
+        s = O.full_sort_scores(u_g, i_g, users)                             # freedom.py:216-220
+        O.mask_topk(s, mask, TOPK)                                          # trainer.py:304-309
+        scored += (hi - lo) * wl.I
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, scored
+
+
+def cpu_baseline(wl, kr, kc, kv, steps=3):
+    O, adj, mm, ue, ie = cpu_setup(wl, kr, kc, kv)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with torch.no_grad():
+        cpu_step(O, wl, adj, mm, ue, ie)
+        ta = tc = 0.0
+        sc = 0
+        for _ in range(steps):
+            a, c, s = cpu_step(O, wl, adj, mm, ue, ie)
+            ta += a; tc += c; sc += s
+    edges = wl.n_layers * adj._nnz() + mm._nnz()
+    return {"value": edges * steps / ta, "unit": "edges/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} x (FREEDOM forward on the full graph + 1 eval batch of {EVAL_BATCH} users), torch CPU fp32, "
+                      "same ops/order as the reference (oracle/mmrec_oracle.py)",
+            "scored_items_per_sec": sc / tc}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = Workload(args.workload, n_layers=3)
+    kr, kc, kv = wl.knn_coo()
+    O, adj, mm, ue, ie = cpu_setup(wl, kr, kc, kv)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    edges = wl.n_layers * adj._nnz() + mm._nnz()
+    ta = tc = 0.0
+    sc = 0
+    with torch.no_grad():
+        for step in range(args.warmup + args.steps):
+            a, c, s = cpu_step(O, wl, adj, mm, ue, ie)
+            if step >= args.warmup:
+                ta += a; tc += c; sc += s
+    K = args.steps
+    value = edges * K / ta
+    sample = (f"each step: FREEDOM forward on the full graph + score/mask/top-{TOPK} of ONE batch of {EVAL_BATCH} users "
+              f"(bounded sample of the {wl.U}-user pass), torch CPU fp32 with {threads} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": "graph-prop edges/sec (+ full-catalog scored-items/sec in extra) @ d=64",
+        "value": value, "unit": "edges/s", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+        "ms_per_step": (ta + tc) / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"FREEDOM synthetic {wl.name}: {wl.U} users, {wl.I} items, {len(wl.tr_u)} train edges, d={wl.d}, "
+                               f"{wl.n_layers} UI layers + 1 mm layer", "parallelism": f"CPU, {threads} threads"},
+        "extra": {"prop_ms": ta / K * 1e3, "score_topk_ms_per_batch": tc / K * 1e3, "scored_items_per_sec": sc / tc},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "scored_items_per_sec": sc / tc},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="baby", choices=list(synth.SHAPES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/* mmrec_b200 -- C ABI of the B200-native hot path of MMRec.
+ *
+ * The reference (enoche/MMRec, /root/reference) is pure Python on PyTorch; it has no FFI of
+ * its own.  Its "plugin boundary" is the model class contract of
+ * src/common/abstract_recommender.py:10-52,71-103, and the hot path below that boundary is the
+ * set of PyTorch library calls listed next to each entry point.  This header is what a
+ * maintainer binds (ctypes stub in INTEGRATION.md) to replace exactly those calls.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (normally a torch tensor); the
+ *    library never allocates or frees device memory: scratch is passed in as `ws`, sized by the
+ *    matching *_workspace_bytes() call;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*; 0 = legacy default);
+ *  - return value 0 = ok, negative = MMREC_E* below; mmrec_last_error() gives the message
+ *    (thread-local);
+ *  - all matrices are row-major; floating point is fp32 (the reference computes in fp32),
+ *    CSR indices are int32, COO indices / gather indices / result indices are int64 as in the
+ *    reference's tensors.
+ */
+#ifndef MMREC_B200_H
+#define MMREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMREC_OK 0
+#define MMREC_EINVAL (-1)      /* bad argument (null pointer, negative size, unsupported d or k) */
+#define MMREC_EWORKSPACE (-2)  /* ws_bytes smaller than *_workspace_bytes() */
+#define MMREC_ECUDA (-3)       /* a CUDA runtime call failed; see mmrec_last_error() */
+#define MMREC_EUNSUPPORTED (-4)/* device is not sm_100 (the library carries sm_100a code only) */
+
+#define MMREC_ABI_VERSION 1
+
+int mmrec_abi_version(void);
+const char* mmrec_last_error(void);
+/* 0 if the current device can run this library (compute capability 10.x), else MMREC_EUNSUPPORTED */
+int mmrec_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1c  COO -> CSR.   Replaces the per-call `coalesce()` + COO->CSR conversion hidden inside every
+ * `torch.sparse.mm(adj, x)` on the path (src/models/freedom.py:167,172; bm3.py:90;
+ * mgcn.py:162,172,176,180,184; layergcn.py:131; lightgcn.py:120; common/encoders.py:99,122).
+ * The reference's matrices arrive un-coalesced and, for FREEDOM's mm_adj, with duplicate
+ * coordinates that must add (freedom.py:74): duplicates are summed in input order (stable sort),
+ * which is what coalesce() does.  Output rows are sorted by column.
+ *   row/col  int64[nnz]; val fp32[nnz] or NULL (= all ones)
+ *   rowptr   int32[n_rows+1]; colidx int32[nnz]; vals fp32[nnz]  (first nnz_out[0] entries valid)
+ *   nnz_out  int64[1] on the device: number of entries after merging duplicates
+ * ------------------------------------------------------------------------------------------- */
+size_t mmrec_csr_from_coo_workspace_bytes(int64_t nnz, int64_t n_rows);
+int mmrec_csr_from_coo(int64_t nnz, const int64_t* row, const int64_t* col, const float* val,
+                       int64_t n_rows, int64_t n_cols, int sum_duplicates,
+                       int32_t* rowptr, int32_t* colidx, float* vals, int64_t* nnz_out,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* Work plan for mmrec_spmm_f32: rows longer than `seg` non-zeros are split into segments so that
+ * the power-law item rows do not serialise on one warp.
+ *   tasks      int32[4 * max_tasks]  {row, begin, end, split_id(-1 = whole row)}
+ *   split_rows int32[4 * max_split]  {first_slot, n_seg, row_begin, seg}
+ *   counts     int64[4] on the device: {n_tasks, n_split_rows, n_slots, longest_row}
+ * max_tasks = n_rows + nnz / seg + 1 and max_split = nnz / seg + 1 are always enough. */
+size_t mmrec_spmm_plan_workspace_bytes(int64_t n_rows);
+int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg,
+                    int32_t* tasks, int32_t* split_rows, int64_t* counts,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* Per-edge symmetric normalisation of a bipartite edge list, fp32, computed like
+ * src/models/freedom.py:145-154 (`_normalize_adj_m`): deg counted exactly, then
+ * val[e] = rsqrt(deg_u[u] + eps) * rsqrt(deg_i[i] + eps) with IEEE sqrt and divide.
+ *   ws: int32[n_users + n_items] */
+size_t mmrec_bipartite_norm_workspace_bytes(int64_t n_users, int64_t n_items);
+int mmrec_bipartite_norm_f32(int64_t n_edges, const int64_t* users, const int64_t* items,
+                             int64_t n_users, int64_t n_items, float eps, float* vals,
+                             void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  CSR SpMM with fused layer-combination epilogue.   Replaces `torch.sparse.mm(adj, x)` and the
+ * `stack(...).mean(dim=1)` / `+ h` that follow it (src/models/freedom.py:164-178, bm3.py:84-95,
+ * lightgcn.py:115-128, mgcn.py:157-185, layergcn.py:125-138); its backward is the same call on the
+ * transposed CSR (autograd of torch.sparse.mm, triggered at src/common/trainer.py:185).
+ *
+ *   y[r,:]   = sum_j vals[j] * X[colidx[j], :]           j in rowptr[r] .. rowptr[r+1]
+ *   if gate_ref: y[r,:] *= cos(y[r,:], gate_ref[r,:])    (LayerGCN, layergcn.py:132-133)
+ *   if Y:        Y[r,:] = y[r,:]
+ *   if acc_out:  acc_out[r,:] = ((acc_in ? acc_in[r,:] : 0) + y[r,:]) / acc_div
+ *
+ * acc_in may alias acc_out.  d in {32, 64, 128, 256} runs the vectorised kernel, any other d >= 1
+ * the generic one.  tasks/n_tasks/split_rows/counters/partial come from mmrec_spmm_plan
+ * (counters: int32[n_split_rows], zero on entry and zero again on exit; partial:
+ * fp32[n_slots * d]); tasks == NULL selects one warp per row.  Summation order is fixed, so the
+ * result is bit-reproducible run to run.
+ * ------------------------------------------------------------------------------------------- */
+int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d,
+                   const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                   const int32_t* tasks, int64_t n_tasks, const int32_t* split_rows,
+                   int32_t* counters, float* partial,
+                   const float* X, int64_t ldx,
+                   float* Y, int64_t ldy,
+                   const float* acc_in, float* acc_out, int64_t ldacc, float acc_div,
+                   const float* gate_ref, int64_t ldgate,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  fused gather -> linear(+bias) -> optional row L2-normalise.   Replaces
+ * `self.image_trs(self.image_embedding.weight)[items]` (src/models/freedom.py:205-209,
+ * bm3.py:102-104, mgcn.py:148-150) and `F.normalize(MLP(features))` (mmgcn.py:165-168).
+ *   Y[n,:] = table[idx ? idx[n] : n, :] @ W^T + bias      table [n_table, F], W [d, F], bias [d]|NULL
+ *   l2_normalize: Y[n,:] /= max(||Y[n,:]||_2, 1e-12)
+ * ------------------------------------------------------------------------------------------- */
+int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int64_t n_table, int64_t F,
+                      const float* W, const float* bias, int d, int l2_normalize,
+                      float* Y, int64_t ldy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  full-catalog scoring, train-positive mask and per-user top-k.   Replaces
+ * `torch.matmul(u_embeddings, restore_item_e.transpose(0, 1))` (src/models/freedom.py:219,
+ * bm3.py:153, mgcn.py:262, layergcn.py:185, lightgcn.py:162, mmgcn.py:104) and
+ * `scores[mask[0], mask[1]] = -1e10; torch.topk(scores, k)` (src/common/trainer.py:304-309).
+ *
+ * mmrec_score_f32:    S[b, i] = <Ue[users ? users[b] : b, :], Ie[i, :]>            S [B, ldS]
+ * mmrec_mask_f32:     S[mask_rows[j], mask_cols[j] - item_offset] = -1e10 for columns inside
+ *                     [item_offset, item_offset + n_items)
+ * mmrec_topk_rows_f32: out_idx/out_val [B, k], descending value, ties -> lower index, index
+ *                     reported as column + item_offset.  1 <= k <= 1024, k <= n_items.
+ * mmrec_score_topk_f32: all three fused, scores never materialised in HBM.
+ *                     ws from mmrec_score_topk_workspace_bytes.
+ * mmrec_topk_merge:   merge `parts` sorted lists per user ([parts, B, k] values + indices) into
+ *                     one (the per-user top-k reduction across item shards).
+ * ------------------------------------------------------------------------------------------- */
+/* arithmetic path of mmrec_score_f32 / mmrec_score_topk_f32: 1 = tcgen05 3xTF32 where the shape fits
+ * (default; env MMREC_SCORE_PATH=simt|tc sets the initial value), 0 = exact fp32 on CUDA cores. */
+int mmrec_score_set_path(int tensor_core);
+int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu,
+                    int64_t n_items, const float* Ie, int64_t ldi, int d,
+                    float* S, int64_t ldS, void* stream);
+int mmrec_mask_f32(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols,
+                   int64_t B, int64_t n_items, int64_t item_offset, float* S, int64_t ldS, void* stream);
+int mmrec_topk_rows_f32(int64_t B, int64_t n_items, const float* S, int64_t ldS, int k,
+                        int64_t item_offset, int64_t* out_idx, float* out_val, void* stream);
+size_t mmrec_score_topk_workspace_bytes(int64_t B, int64_t n_items, int d, int k);
+int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu,
+                         int64_t n_items, const float* Ie, int64_t ldi, int d,
+                         int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols,
+                         int k, int64_t item_offset, int64_t* out_idx, float* out_val,
+                         void* ws, size_t ws_bytes, void* stream);
+int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, const int64_t* idx,
+                     int64_t* out_idx, float* out_val, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMREC_B200_H */

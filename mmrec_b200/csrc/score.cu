@@ -1,0 +1,96 @@
+// K3: full-catalog scoring  S = U[users] I^T  (src/models/freedom.py:216-220) and its fusion with the
+// trainer's mask + top-k (src/common/trainer.py:304-309).
+//
+// Two arithmetic paths share the entry points:
+//   * exact fp32 on CUDA cores (gemm_simt.cuh): one fmaf chain per score, k ascending -- bit-faithful;
+//   * tcgen05 tensor cores with the 3xTF32 split (score_tc.cu) when the shape fits its tiles; selected by
+//     mmrec_score_set_path() / env MMREC_SCORE_PATH = "simt" | "tc" (default: tc where supported).
+// mmrec_score_topk_f32 processes the users in row blocks whose score block stays L2-resident
+// (B_blk x n_items x 4 B <= 64 MiB), so the B x n_items matrix the reference materialises in HBM
+// (115 MB per 4096 users at 7k items, 16 GB at 1M items) never exists.
+#include <stdlib.h>
+#include <string.h>
+
+#include "gemm_simt.cuh"
+
+namespace mmrec {
+// implemented in score_tc.cu; returns 1 if it handled the call, 0 if the shape is unsupported, <0 on error
+int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie,
+             int64_t ldi, int d, float* S, int64_t ldS, cudaStream_t stream);
+
+int mask_apply(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int64_t row0, int64_t B,
+               int64_t n_items, int64_t item_offset, float* S, int64_t ldS, cudaStream_t stream);
+
+static int g_score_path = -1;   // -1 unset, 0 simt, 1 tc
+static int score_path() {
+    if (g_score_path < 0) {
+        const char* e = getenv("MMREC_SCORE_PATH");
+        g_score_path = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    }
+    return g_score_path;
+}
+}  // namespace mmrec
+
+using namespace mmrec;
+
+extern "C" int mmrec_score_set_path(int tc) { g_score_path = tc ? 1 : 0; return MMREC_OK; }
+
+extern "C" int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items,
+                               const float* Ie, int64_t ldi, int d, float* S, int64_t ldS, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(B >= 0 && n_items >= 0 && d >= 1, "score: bad sizes");
+    if (B == 0 || n_items == 0) return MMREC_OK;
+    MMREC_CHECK_ARG(Ue && Ie && S && ldu >= d && ldi >= d && ldS >= n_items, "score: null pointer or bad leading dimension");
+    if (score_path() == 1) {
+        int r = score_tc(B, users, Ue, ldu, n_items, Ie, ldi, d, S, ldS, stream);
+        if (r != 0) return r < 0 ? r : MMREC_OK;
+    }
+    GemmNT p;
+    p.A = Ue; p.lda = ldu; p.a_idx = users; p.M = B;
+    p.B = Ie; p.ldb = ldi; p.N = n_items; p.K = d; p.bias = nullptr; p.C = S; p.ldc = ldS; p.l2_normalize = 0;
+    return launch_gemm_nt<128, 128, 8, 8>(p, stream);
+}
+
+static int64_t score_block_rows(int64_t B, int64_t n_items) {
+    const int64_t budget = 64ll << 20;
+    int64_t rows = budget / (n_items * 4);
+    if (rows < 128) rows = 128;
+    rows = rows / 128 * 128;
+    return rows < B ? rows : B;
+}
+
+extern "C" size_t mmrec_score_topk_workspace_bytes(int64_t B, int64_t n_items, int d, int k) {
+    (void)d; (void)k;
+    if (B <= 0 || n_items <= 0) return 256;
+    return (size_t)score_block_rows(B, n_items) * (size_t)((n_items + 3) / 4 * 4) * sizeof(float) + 256;
+}
+
+extern "C" int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items,
+                                    const float* Ie, int64_t ldi, int d, int64_t mask_nnz, const int64_t* mask_rows,
+                                    const int64_t* mask_cols, int k, int64_t item_offset, int64_t* out_idx,
+                                    float* out_val, void* ws, size_t ws_bytes, void* stream_) {
+    MMREC_CHECK_ARG(B >= 0 && n_items >= 1 && d >= 1 && k >= 1, "score_topk: bad sizes");
+    if (B == 0) return MMREC_OK;
+    const size_t need = mmrec_score_topk_workspace_bytes(B, n_items, d, k);
+    if (!ws || ws_bytes < need) {
+        set_error("score_topk: workspace %zu < %zu", ws_bytes, need);
+        return MMREC_EWORKSPACE;
+    }
+    float* S = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    const int64_t ldS = (n_items + 3) / 4 * 4;
+    const int64_t rows = score_block_rows(B, n_items);
+    for (int64_t r0 = 0; r0 < B; r0 += rows) {
+        const int64_t nb = (B - r0) < rows ? (B - r0) : rows;
+        int rc = mmrec_score_f32(nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_items, Ie, ldi, d, S,
+                                 ldS, stream_);
+        if (rc) return rc;
+        if (mask_nnz > 0) {
+            // mask rows are positions in the whole batch: the kernel shifts by r0 and ignores rows outside [0, nb)
+            rc = mask_apply(mask_nnz, mask_rows, mask_cols, r0, nb, n_items, item_offset, S, ldS, (cudaStream_t)stream_);
+            if (rc) return rc;
+        }
+        rc = mmrec_topk_rows_f32(nb, n_items, S, ldS, k, item_offset, out_idx + r0 * k, out_val + r0 * k, stream_);
+        if (rc) return rc;
+    }
+    return MMREC_OK;
+}

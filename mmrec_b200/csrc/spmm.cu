@@ -1,0 +1,280 @@
+// K1: CSR SpMM  y = A X  with the layer-combination epilogue fused (running sum / mean, "+h", LayerGCN's
+// cosine gate).  HBM/L2-bound gather kernel: no tensor cores (0.25-0.5 flop/byte).
+//
+// Mapping (D = embedding width, a multiple of 32 floats):
+//   * one warp per task; a task is a whole row or, for rows longer than the plan's segment length, one
+//     segment of it (mmrec_spmm_plan) -- the power-law item rows would otherwise serialise on one warp;
+//   * inside a warp a row of X is D*4 bytes = LPR lanes x float4 (LPR = D/4, at most 32): every lane group
+//     issues ONE coalesced 16-byte-per-lane request per non-zero, G = 32/LPR groups work on G non-zeros at a
+//     time, each lane keeps UNR independent loads in flight;
+//   * column indices / values are fetched 32 at a time with one coalesced load per warp and handed round
+//     with shuffles; group partial sums are combined with shuffles at the end of the row;
+//   * split rows: each segment writes its partial sum to scratch, the LAST segment to arrive (per-row
+//     counter) adds the partials in segment order -> the summation order never depends on scheduling, so
+//     results are bit-reproducible.
+// Grid: persistent, (SM count x resident CTAs) CTAs of 8 warps striding over the task list.
+#include "common.cuh"
+
+namespace mmrec {
+
+struct SpmmParams {
+    int64_t n_rows, n_cols;
+    const int32_t* rowptr; const int32_t* colidx; const float* vals;
+    const int4* tasks; int64_t n_tasks; const int4* split_rows; int32_t* counters; float* partial;
+    const float* X; int64_t ldx;
+    float* Y; int64_t ldy;
+    const float* acc_in; float* acc_out; int64_t ldacc; float acc_div;
+    const float* gate_ref; int64_t ldgate;
+    int d;
+};
+
+template <int D>
+struct VecCfg {
+    static constexpr int V = D >= 128 ? D / 128 : 1;   // float4 per lane
+    static constexpr int LPR = D >= 128 ? 32 : D / 4;  // lanes per row
+    static constexpr int G = 32 / LPR;                 // rows of X in flight per shuffle step
+    static constexpr int UNR = (V >= 2) ? 4 : 8;       // independent row loads per lane
+};
+
+template <int D>
+__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, int l, float4 (&y)[VecCfg<D>::V]) {
+    using C = VecCfg<D>;
+    // called by lanes [0, LPR) of the warp, all of which hold the finished row
+    if (p.gate_ref) {
+        float dot = 0.f, ny = 0.f, nr = 0.f;
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) {
+            float4 r = ldg4(p.gate_ref + (int64_t)row * p.ldgate + v * 128 + l * 4);
+            dot += y[v].x * r.x + y[v].y * r.y + y[v].z * r.z + y[v].w * r.w;
+            ny += y[v].x * y[v].x + y[v].y * y[v].y + y[v].z * y[v].z + y[v].w * y[v].w;
+            nr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+        }
+        const unsigned m = C::LPR == 32 ? 0xffffffffu : ((1u << C::LPR) - 1u);
+#pragma unroll
+        for (int o = C::LPR / 2; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(m, dot, o);
+            ny += __shfl_xor_sync(m, ny, o);
+            nr += __shfl_xor_sync(m, nr, o);
+        }
+        // F.cosine_similarity(eps=1e-8): <x/max(|x|,eps), y/max(|y|,eps)>  (layergcn.py:132)
+        float c = dot / (fmaxf(sqrtf(ny), 1e-8f) * fmaxf(sqrtf(nr), 1e-8f));
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) { y[v].x *= c; y[v].y *= c; y[v].z *= c; y[v].w *= c; }
+    }
+    if (p.Y) {
+#pragma unroll
+        for (int v = 0; v < C::V; ++v)
+            *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + v * 128 + l * 4) = y[v];
+    }
+    if (p.acc_out) {
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) {
+            float4 a = y[v];
+            if (p.acc_in) {
+                float4 b = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + v * 128 + l * 4);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (p.acc_div != 1.0f) {
+                a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
+                a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
+            }
+            *reinterpret_cast<float4*>(p.acc_out + (int64_t)row * p.ldacc + v * 128 + l * 4) = a;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
+    using C = VecCfg<D>;
+    const int lane = threadIdx.x & 31;
+    const int g = lane / C::LPR, l = lane % C::LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
+
+    for (int64_t t = warp0; t < n_work; t += nwarps) {
+        int row, b, e, sid;
+        if (p.tasks) {
+            int4 tk = __ldg(p.tasks + t);
+            row = tk.x; b = tk.y; e = tk.z; sid = tk.w;
+        } else {
+            row = (int)t; b = __ldg(p.rowptr + t); e = __ldg(p.rowptr + t + 1); sid = -1;
+        }
+        float4 acc[C::V];
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (int base = b; base < e; base += 32) {
+            const int n = min(32, e - base);
+            int c = 0; float w = 0.f;
+            if (lane < n) { c = __ldg(p.colidx + base + lane); w = __ldg(p.vals + base + lane); }
+            const int iters = (n + C::G - 1) / C::G;
+            for (int j0 = 0; j0 < iters; j0 += C::UNR) {
+                float4 x[C::UNR][C::V];
+                float wj[C::UNR];
+#pragma unroll
+                for (int u = 0; u < C::UNR; ++u) {
+                    const int src = (j0 + u) * C::G + g;
+                    const int cj = __shfl_sync(0xffffffffu, c, src & 31);
+                    wj[u] = __shfl_sync(0xffffffffu, w, src & 31);
+                    const bool ok = src < n;
+                    if (!ok) wj[u] = 0.f;
+#pragma unroll
+                    for (int v = 0; v < C::V; ++v)
+                        x[u][v] = ok ? ldg4(p.X + (int64_t)cj * p.ldx + v * 128 + l * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < C::UNR; ++u) {
+#pragma unroll
+                    for (int v = 0; v < C::V; ++v) {
+                        acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x);
+                        acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);
+                        acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z);
+                        acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);
+                    }
+                }
+            }
+        }
+        // combine the G lane groups (fixed order)
+#pragma unroll
+        for (int o = 16; o >= C::LPR; o >>= 1) {
+#pragma unroll
+            for (int v = 0; v < C::V; ++v) {
+                acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+                acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+                acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+                acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+            }
+        }
+        if (sid < 0) {
+            if (g == 0) spmm_epilogue<D>(p, row, l, acc);
+        } else {
+            const int4 sr = __ldg(p.split_rows + sid);   // {first_slot, n_seg, row_begin, seg_len}
+            const int seg = (b - sr.z) / sr.w;
+            float* slot = p.partial + ((int64_t)sr.x + seg) * D;
+            if (g == 0) {
+#pragma unroll
+                for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(slot + v * 128 + l * 4) = acc[v];
+            }
+            __threadfence();
+            __syncwarp();
+            int old = 0;
+            if (lane == 0) old = atomicAdd(p.counters + sid, 1);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == sr.y - 1) {            // last segment to arrive: reduce in segment order
+                __threadfence();
+                if (g == 0) {
+                    float4 tot[C::V];
+#pragma unroll
+                    for (int v = 0; v < C::V; ++v) tot[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int s = 0; s < sr.y; ++s) {
+                        const float* ps = p.partial + ((int64_t)sr.x + s) * D;
+#pragma unroll
+                        for (int v = 0; v < C::V; ++v) {
+                            float4 q = __ldcg(reinterpret_cast<const float4*>(ps + v * 128 + l * 4));
+                            tot[v].x += q.x; tot[v].y += q.y; tot[v].z += q.z; tot[v].w += q.w;
+                        }
+                    }
+                    spmm_epilogue<D>(p, row, l, tot);
+                }
+                if (lane == 0) p.counters[sid] = 0;   // self-cleaning for the next launch
+            }
+        }
+    }
+}
+
+// Any d: 32 columns at a time, scalar loads.  Correctness path for odd widths, not tuned.
+__global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp0; row < p.n_rows; row += nwarps) {
+        const int b = p.rowptr[row], e = p.rowptr[row + 1];
+        float dot = 0.f, ny = 0.f, nr = 0.f;
+        if (p.gate_ref) {
+            for (int k0 = 0; k0 < p.d; k0 += 32) {
+                const int k = k0 + lane;
+                float acc = 0.f;
+                if (k < p.d)
+                    for (int j = b; j < e; ++j) acc = fmaf(p.vals[j], p.X[(int64_t)p.colidx[j] * p.ldx + k], acc);
+                float r = k < p.d ? p.gate_ref[row * p.ldgate + k] : 0.f;
+                dot += acc * r; ny += acc * acc; nr += r * r;
+            }
+            dot = warp_sum(dot); ny = warp_sum(ny); nr = warp_sum(nr);
+        }
+        const float c = p.gate_ref ? dot / (fmaxf(sqrtf(ny), 1e-8f) * fmaxf(sqrtf(nr), 1e-8f)) : 1.f;
+        for (int k0 = 0; k0 < p.d; k0 += 32) {
+            const int k = k0 + lane;
+            if (k >= p.d) continue;
+            float acc = 0.f;
+            for (int j = b; j < e; ++j) acc = fmaf(p.vals[j], p.X[(int64_t)p.colidx[j] * p.ldx + k], acc);
+            if (p.gate_ref) acc *= c;
+            if (p.Y) p.Y[row * p.ldy + k] = acc;
+            if (p.acc_out) {
+                float a = acc + (p.acc_in ? p.acc_in[row * p.ldacc + k] : 0.f);
+                if (p.acc_div != 1.0f) a = __fdiv_rn(a, p.acc_div);
+                p.acc_out[row * p.ldacc + k] = a;
+            }
+        }
+    }
+}
+
+template <int D>
+static int launch_vec(const SpmmParams& p, cudaStream_t stream) {
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        MMREC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, spmm_vec_kernel<D>, 256, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
+    int64_t grid = (n_work + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    if (grid > cap) grid = cap;
+    if (grid < 1) return MMREC_OK;
+    spmm_vec_kernel<D><<<(unsigned)grid, 256, 0, stream>>>(p);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}
+
+}  // namespace mmrec
+
+using namespace mmrec;
+
+extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32_t* rowptr, const int32_t* colidx,
+                              const float* vals, const int32_t* tasks, int64_t n_tasks, const int32_t* split_rows,
+                              int32_t* counters, float* partial, const float* X, int64_t ldx, float* Y, int64_t ldy,
+                              const float* acc_in, float* acc_out, int64_t ldacc, float acc_div, const float* gate_ref,
+                              int64_t ldgate, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && d >= 1, "spmm: bad sizes");
+    if (n_rows == 0) return MMREC_OK;
+    MMREC_CHECK_ARG(rowptr && X && (Y || acc_out), "spmm: null pointer");
+    MMREC_CHECK_ARG(ldx >= d && (!Y || ldy >= d) && (!acc_out || ldacc >= d) && (!gate_ref || ldgate >= d), "spmm: leading dimension < d");
+    MMREC_CHECK_ARG(acc_div != 0.0f, "spmm: acc_div == 0");
+    MMREC_CHECK_ARG(!tasks || (n_tasks >= 0 && split_rows && counters && partial), "spmm: plan pointers missing");
+    SpmmParams p;
+    p.n_rows = n_rows; p.n_cols = n_cols; p.rowptr = rowptr; p.colidx = colidx; p.vals = vals;
+    p.tasks = (const int4*)tasks; p.n_tasks = n_tasks; p.split_rows = (const int4*)split_rows;
+    p.counters = counters; p.partial = partial; p.X = X; p.ldx = ldx; p.Y = Y; p.ldy = ldy;
+    p.acc_in = acc_in; p.acc_out = acc_out; p.ldacc = ldacc; p.acc_div = acc_div; p.gate_ref = gate_ref;
+    p.ldgate = ldgate; p.d = d;
+    auto al16 = [](const void* q, int64_t ld) { return q == nullptr || ((((uintptr_t)q) & 15) == 0 && (ld & 3) == 0); };
+    const bool vec_ok = al16(X, ldx) && al16(Y, ldy) && al16(acc_in, ldacc) && al16(acc_out, ldacc) &&
+                        al16(gate_ref, ldgate) && al16(partial, 4);
+    if (vec_ok) {
+        switch (d) {
+            case 32: return launch_vec<32>(p, stream);
+            case 64: return launch_vec<64>(p, stream);
+            case 128: return launch_vec<128>(p, stream);
+            case 256: return launch_vec<256>(p, stream);
+            default: break;
+        }
+    }
+    p.tasks = nullptr;   // the generic kernel walks whole rows
+    int64_t grid = (n_rows + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    spmm_generic_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}

@@ -1,0 +1,413 @@
+"""Host-side operators over the C ABI (include/mmrec_b200.h): the three op families of MMRec's hot path.
+
+Each function here replaces a PyTorch library call of the reference (cited per function, paths relative
+to /root/reference) with a call into libmmrec_b200.so on the current CUDA stream.  PyTorch is used for
+device memory, streams and autograd bookkeeping only.  There is no CPU path: tensors must live on a
+sm_100 device, otherwise `MMRecError` is raised.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MMRecError, check
+
+_ws_cache: dict = {}
+SEG = 128          # non-zeros per SpMM task (rows longer than this are split)
+LAUNCHES = 0       # kernels of this library launched so far (bench.py's gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise MMRecError("mmrec_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise MMRecError(f"expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ws(name: str, nbytes: int, device) -> torch.Tensor:
+    key = (name, device.index)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# K1c: CSR container
+# ------------------------------------------------------------------------------------------------
+class CSR:
+    """Row-sorted int32 CSR of a sparse matrix on the device, with the SpMM work plan.
+
+    Stands in for the reference's `torch.sparse` COO tensors (`norm_adj`, `masked_adj`, `mm_adj`, `R`;
+    SURVEY.md 8a a1/a2/a8).  Built once per graph (per epoch for FREEDOM's pruned graph) instead of the
+    coalesce + COO->CSR conversion ATen performs inside every `torch.sparse.mm` call.
+    """
+
+    def __init__(self, n_rows, n_cols, rowptr, colidx, vals, nnz, symmetric=False, seg=SEG):
+        self.n_rows, self.n_cols, self.nnz = int(n_rows), int(n_cols), int(nnz)
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.symmetric = symmetric
+        self.seg = seg
+        self._t: Optional["CSR"] = None
+        self._partial = {}
+        self._plan()
+
+    # -- construction ------------------------------------------------------------------------------
+    @staticmethod
+    def from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int,
+                 sum_duplicates: bool = True, symmetric: bool = False, seg: int = SEG) -> "CSR":
+        _lib.require_device()
+        _need_cuda(row, col, val)
+        lib = _lib.load()
+        row, col = row.to(torch.int64).contiguous(), col.to(torch.int64).contiguous()
+        val = None if val is None else _f32c(val)
+        nnz = row.numel()
+        dev = row.device
+        rowptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+        colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+        vals = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+        nnz_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        nbytes = lib.mmrec_csr_from_coo_workspace_bytes(nnz, n_rows)
+        ws = _ws("csr", nbytes, dev)
+        check(lib.mmrec_csr_from_coo(nnz, _ptr(row), _ptr(col), _ptr(val), n_rows, n_cols, int(sum_duplicates),
+                                     _ptr(rowptr), _ptr(colidx), _ptr(vals), _ptr(nnz_out), _ptr(ws), ws.numel(),
+                                     _stream()), "mmrec_csr_from_coo")
+        _count(6)
+        n = int(nnz_out.item())
+        return CSR(n_rows, n_cols, rowptr, colidx[:max(n, 1)], vals[:max(n, 1)], n, symmetric, seg)
+
+    @staticmethod
+    def from_torch_sparse(t: torch.Tensor, symmetric: bool = False) -> "CSR":
+        """From an (un-coalesced) torch COO tensor as the reference builds them."""
+        idx, val = t._indices(), t._values()
+        return CSR.from_coo(idx[0], idx[1], val.to(torch.float32), t.shape[0], t.shape[1], True, symmetric)
+
+    def _plan(self):
+        lib = _lib.load()
+        dev = self.rowptr.device
+        max_tasks = self.n_rows + self.nnz // self.seg + 1
+        max_split = self.nnz // self.seg + 1
+        tasks = torch.empty(4 * max_tasks, dtype=torch.int32, device=dev)
+        split = torch.empty(4 * max_split, dtype=torch.int32, device=dev)
+        counts = torch.zeros(4, dtype=torch.int64, device=dev)
+        ws = _ws("plan", lib.mmrec_spmm_plan_workspace_bytes(self.n_rows), dev)
+        check(lib.mmrec_spmm_plan(self.n_rows, _ptr(self.rowptr), self.seg, _ptr(tasks), _ptr(split), _ptr(counts),
+                                  _ptr(ws), ws.numel(), _stream()), "mmrec_spmm_plan")
+        _count(5)
+        c = counts.tolist()
+        self.n_tasks, self.n_split, self.n_slots, self.longest_row = int(c[0]), int(c[1]), int(c[2]), int(c[3])
+        self.tasks = tasks[:4 * max(self.n_tasks, 1)]
+        self.split_rows = split[:4 * max(self.n_split, 1)]
+        self.counters = torch.zeros(max(self.n_split, 1), dtype=torch.int32, device=dev)
+
+    def partial(self, d: int) -> torch.Tensor:
+        t = self._partial.get(d)
+        if t is None:
+            t = torch.empty(max(self.n_slots, 1) * d, dtype=torch.float32, device=self.rowptr.device)
+            self._partial[d] = t
+        return t
+
+    # -- views ---------------------------------------------------------------------------------------
+    def coo(self):
+        """(row int64, col int64, val) of the stored entries."""
+        counts = (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64)
+        row = torch.repeat_interleave(torch.arange(self.n_rows, device=self.rowptr.device), counts)
+        return row, self.colidx[:self.nnz].to(torch.int64), self.vals[:self.nnz]
+
+    def t(self) -> "CSR":
+        """Transposed matrix (needed by the backward of directed graphs: mm_adj, R)."""
+        if self.symmetric:
+            return self
+        if self._t is None:
+            r, c, v = self.coo()
+            self._t = CSR.from_coo(c, r, v, self.n_cols, self.n_rows, False, False, self.seg)
+            self._t._t = self
+        return self._t
+
+    def to_dense(self) -> torch.Tensor:
+        r, c, v = self.coo()
+        out = torch.zeros(self.n_rows, self.n_cols, dtype=torch.float32, device=v.device)
+        out.index_put_((r, c), v, accumulate=True)
+        return out
+
+    def algorithmic_bytes(self, d: int) -> int:
+        """4(n_rows+1) + 8 nnz + 4 n_cols d + 4 n_rows d."""
+        return 4 * (self.n_rows + 1) + 8 * self.nnz + 4 * self.n_cols * d + 4 * self.n_rows * d
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: SpMM
+# ------------------------------------------------------------------------------------------------
+def spmm_raw(A: CSR, X: torch.Tensor, Y: Optional[torch.Tensor] = None, acc_in: Optional[torch.Tensor] = None,
+             acc_out: Optional[torch.Tensor] = None, acc_div: float = 1.0, gate_ref: Optional[torch.Tensor] = None,
+             use_plan: bool = True):
+    """y = A X with the fused epilogue of include/mmrec_b200.h (no autograd).  Replaces `torch.sparse.mm`
+    (`src/models/freedom.py:167,172`) plus the stack/mean (`:175-176`) and `+ h` (`:178`) that follow."""
+    _need_cuda(X, Y, acc_in, acc_out, gate_ref)
+    lib = _lib.load()
+    if X.dim() != 2 or X.shape[0] != A.n_cols:
+        raise MMRecError(f"spmm: X is {tuple(X.shape)}, matrix has {A.n_cols} columns")
+    X = _f32c(X)
+    d = X.shape[1]
+    for name, t in (("Y", Y), ("acc_in", acc_in), ("acc_out", acc_out), ("gate_ref", gate_ref)):
+        if t is not None and (t.shape != (A.n_rows, d) or not t.is_contiguous() or t.dtype != torch.float32):
+            raise MMRecError(f"spmm: {name} must be contiguous float32 [{A.n_rows}, {d}]")
+    if Y is None and acc_out is None:
+        raise MMRecError("spmm: nothing to write")
+    plan = use_plan and A.n_tasks > 0
+    check(lib.mmrec_spmm_f32(A.n_rows, A.n_cols, d, _ptr(A.rowptr), _ptr(A.colidx), _ptr(A.vals),
+                             _ptr(A.tasks) if plan else None, A.n_tasks if plan else 0,
+                             _ptr(A.split_rows) if plan else None, _ptr(A.counters) if plan else None,
+                             _ptr(A.partial(d)) if plan else None,
+                             _ptr(X), X.stride(0), _ptr(Y), d, _ptr(acc_in), _ptr(acc_out), d, float(acc_div),
+                             _ptr(gate_ref), d, _stream()), "mmrec_spmm_f32")
+    _count()
+
+
+class _SpmmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, A: CSR, base):
+        ctx.A = A
+        ctx.has_base = base is not None
+        out = torch.empty(A.n_rows, X.shape[1], dtype=torch.float32, device=X.device)
+        if base is None:
+            spmm_raw(A, X, Y=out)
+        else:
+            spmm_raw(A, X, acc_in=_f32c(base), acc_out=out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        At = ctx.A.t()
+        gx = torch.empty(At.n_rows, g.shape[1], dtype=torch.float32, device=g.device)
+        spmm_raw(At, g, Y=gx)                       # dX = A^T dY  (autograd of torch.sparse.mm)
+        return gx, None, (g if ctx.has_base else None)
+
+
+def spmm(A: CSR, X: torch.Tensor, base: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`base + A @ X` (base optional), differentiable w.r.t. X and base."""
+    return _SpmmFn.apply(X, A, base)
+
+
+class _PropagateMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ego, A: CSR, n_layers: int):
+        ctx.A, ctx.L = A, n_layers
+        ego = _f32c(ego)
+        if n_layers == 0:
+            return ego.clone()
+        acc = torch.empty_like(ego)
+        x = ego
+        for l in range(1, n_layers + 1):
+            last = l == n_layers
+            y = None if last else torch.empty_like(ego)
+            spmm_raw(A, x, Y=y, acc_in=ego if l == 1 else acc, acc_out=acc, acc_div=float(n_layers + 1) if last else 1.0)
+            x = y
+        return acc
+
+    @staticmethod
+    def backward(ctx, g):
+        L = ctx.L
+        gm = _f32c(g) / float(L + 1)                # d mean / d E_l, the same for every layer
+        if L == 0:
+            return g, None, None
+        At = ctx.A.t()
+        cur = gm
+        for _ in range(L):                          # g_l = gm + A^T g_{l+1}
+            nxt = torch.empty_like(gm)
+            spmm_raw(At, cur, acc_in=gm, acc_out=nxt)
+            cur = nxt
+        return cur, None, None
+
+
+def propagate_mean(A: CSR, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
+    """mean(E_0 .. E_L), E_{l+1} = A E_l -- the LightGCN propagation every graph model repeats
+    (`src/models/freedom.py:169-176`, `bm3.py:86-92`, `lightgcn.py:116-123`, `mgcn.py:159-166`), with the
+    running sum and the final division fused into the SpMM epilogue (no stack, no extra passes)."""
+    return _PropagateMeanFn.apply(ego, A, n_layers)
+
+
+def propagate_layergcn(A: CSR, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
+    """Inference form of `src/models/layergcn.py:125-138`: E_{l+1} = cos(A E_l, E_0) * A E_l, sum over layers
+    1..L, gate and running sum fused into the SpMM epilogue.  (Training goes through `spmm` + torch ops so
+    that autograd sees the cosine gate.)"""
+    ego = _f32c(ego)
+    acc = torch.empty_like(ego)
+    x = ego
+    for l in range(1, n_layers + 1):
+        y = torch.empty_like(ego)
+        spmm_raw(A, x, Y=y, acc_in=None if l == 1 else acc, acc_out=acc, gate_ref=ego)
+        x = y
+    return acc
+
+
+# ------------------------------------------------------------------------------------------------
+# K2: modality projection
+# ------------------------------------------------------------------------------------------------
+def project_raw(table, weight, bias, idx=None, l2_normalize=False) -> torch.Tensor:
+    _need_cuda(table, weight, bias, idx)
+    lib = _lib.load()
+    table, weight = _f32c(table), _f32c(weight)
+    bias = None if bias is None else _f32c(bias)
+    if idx is not None:
+        idx = idx.to(torch.int64).contiguous()
+    n_out = table.shape[0] if idx is None else idx.numel()
+    d, F = weight.shape
+    if table.shape[1] != F:
+        raise MMRecError(f"project: table has {table.shape[1]} features, weight expects {F}")
+    out = torch.empty(n_out, d, dtype=torch.float32, device=table.device)
+    check(lib.mmrec_project_f32(n_out, _ptr(idx), _ptr(table), table.shape[0], F, _ptr(weight), _ptr(bias), d,
+                                int(l2_normalize), _ptr(out), d, _stream()), "mmrec_project_f32")
+    _count()
+    return out
+
+
+class _ProjectFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, weight, bias, idx):
+        ctx.save_for_backward(table, weight, idx)
+        ctx.has_bias = bias is not None
+        return project_raw(table, weight, bias, idx, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        # Backward of nn.Linear over the (gathered) table: dense GEMMs, left to cuBLAS through torch for now
+        # (the feature-table gradient path is a "next" row, not part of K2's forward).
+        table, weight, idx = ctx.saved_tensors
+        x = table if idx is None else table[idx]
+        gw = g.t().mm(x) if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        gt = None
+        if ctx.needs_input_grad[0]:
+            gx = g.mm(weight)
+            gt = gx if idx is None else torch.zeros_like(table).index_add_(0, idx, gx)
+        return gt, gw, gb, None
+
+
+def project(table, weight, bias=None, idx=None, l2_normalize=False) -> torch.Tensor:
+    """`Linear(table)[idx]` computed only for the gathered rows (`src/models/freedom.py:205-209`,
+    `bm3.py:102-104`, `mgcn.py:148-150`); `l2_normalize` adds `F.normalize` (`mmgcn.py:165-168`)."""
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (table, weight, bias))
+    if not needs_grad:
+        return project_raw(table, weight, bias, idx, l2_normalize)
+    y = _ProjectFn.apply(table, weight, bias, idx)
+    return torch.nn.functional.normalize(y) if l2_normalize else y
+
+
+# ------------------------------------------------------------------------------------------------
+# K3: scoring, mask, top-k
+# ------------------------------------------------------------------------------------------------
+def set_score_path(tensor_core: bool):
+    _lib.load().mmrec_score_set_path(int(bool(tensor_core)))
+
+
+def score(user_e, item_e, users=None) -> torch.Tensor:
+    """S = U[users] I^T, freshly allocated fp32 [B, n_items] owned by the caller (the trainer mutates it):
+    `torch.matmul(u_embeddings, restore_item_e.transpose(0, 1))` (`src/models/freedom.py:216-220`)."""
+    _need_cuda(user_e, item_e, users)
+    lib = _lib.load()
+    user_e, item_e = _f32c(user_e), _f32c(item_e)
+    if users is not None:
+        users = users.to(torch.int64).contiguous()
+    B = user_e.shape[0] if users is None else users.numel()
+    n_items, d = item_e.shape
+    out = torch.empty(B, n_items, dtype=torch.float32, device=item_e.device)
+    check(lib.mmrec_score_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e), item_e.stride(0), d,
+                              _ptr(out), n_items, _stream()), "mmrec_score_f32")
+    _count()
+    return out
+
+
+def mask_topk(scores: torch.Tensor, mask: Optional[torch.Tensor], k: int, item_offset: int = 0):
+    """`scores[mask[0], mask[1]] = -1e10; torch.topk(scores, k)` (`src/common/trainer.py:307-309`), in place on
+    `scores`.  Returns (values, indices); equal scores come out in ascending item index."""
+    _need_cuda(scores, mask)
+    lib = _lib.load()
+    if not (scores.is_contiguous() and scores.dtype == torch.float32 and scores.dim() == 2):
+        raise MMRecError("mask_topk: scores must be contiguous float32 [B, n_items]")
+    B, n_items = scores.shape
+    if mask is not None and mask.numel() > 0:
+        mask = mask.to(torch.int64).contiguous()
+        check(lib.mmrec_mask_f32(mask.shape[1], _ptr(mask[0]), _ptr(mask[1]), B, n_items, item_offset, _ptr(scores),
+                                 n_items, _stream()), "mmrec_mask_f32")
+        _count()
+    idx = torch.empty(B, k, dtype=torch.int64, device=scores.device)
+    val = torch.empty(B, k, dtype=torch.float32, device=scores.device)
+    check(lib.mmrec_topk_rows_f32(B, n_items, _ptr(scores), n_items, k, item_offset, _ptr(idx), _ptr(val), _stream()),
+          "mmrec_topk_rows_f32")
+    _count()
+    return val, idx
+
+
+def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0):
+    """Fused `full_sort_predict` + mask + top-k (`src/models/freedom.py:216-220` + `src/common/trainer.py:304-309`)
+    without materialising the [B, n_items] score matrix in HBM.  Returns (values [B,k], indices int64 [B,k])."""
+    _need_cuda(user_e, item_e, users, mask)
+    lib = _lib.load()
+    user_e, item_e = _f32c(user_e), _f32c(item_e)
+    if users is not None:
+        users = users.to(torch.int64).contiguous()
+    B = user_e.shape[0] if users is None else users.numel()
+    n_items, d = item_e.shape
+    idx = torch.empty(B, k, dtype=torch.int64, device=item_e.device)
+    val = torch.empty(B, k, dtype=torch.float32, device=item_e.device)
+    m0 = m1 = None
+    nnz = 0
+    if mask is not None and mask.numel() > 0:
+        mask = mask.to(torch.int64).contiguous()
+        m0, m1, nnz = mask[0], mask[1], mask.shape[1]
+    nbytes = lib.mmrec_score_topk_workspace_bytes(B, n_items, d, k)
+    ws = _ws("score_topk", nbytes, item_e.device)
+    check(lib.mmrec_score_topk_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e),
+                                   item_e.stride(0), d, nnz, _ptr(m0), _ptr(m1), k, item_offset, _ptr(idx), _ptr(val),
+                                   _ptr(ws), ws.numel(), _stream()), "mmrec_score_topk_f32")
+    _count(3)
+    return val, idx
+
+
+def topk_merge(vals: torch.Tensor, idx: torch.Tensor):
+    """Merge per-shard top-k lists [parts, B, k] into the global top-k [B, k] (SURVEY.md 8e eval collective)."""
+    _need_cuda(vals, idx)
+    lib = _lib.load()
+    vals, idx = _f32c(vals), idx.to(torch.int64).contiguous()
+    parts, B, k = vals.shape
+    out_i = torch.empty(B, k, dtype=torch.int64, device=vals.device)
+    out_v = torch.empty(B, k, dtype=torch.float32, device=vals.device)
+    check(lib.mmrec_topk_merge(parts, B, k, _ptr(vals), _ptr(idx), _ptr(out_i), _ptr(out_v), _stream()), "mmrec_topk_merge")
+    _count()
+    return out_v, out_i
+
+
+def bipartite_norm(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, eps: float = 1e-7) -> torch.Tensor:
+    """fp32 1/sqrt((d_u+eps)(d_i+eps)) per edge, as `_normalize_adj_m` (`src/models/freedom.py:145-154`)."""
+    _need_cuda(users, items)
+    lib = _lib.load()
+    users, items = users.to(torch.int64).contiguous(), items.to(torch.int64).contiguous()
+    vals = torch.empty(users.numel(), dtype=torch.float32, device=users.device)
+    ws = _ws("bnorm", lib.mmrec_bipartite_norm_workspace_bytes(n_users, n_items), users.device)
+    check(lib.mmrec_bipartite_norm_f32(users.numel(), _ptr(users), _ptr(items), n_users, n_items, eps, _ptr(vals), _ptr(ws),
+                                       ws.numel(), _stream()), "mmrec_bipartite_norm_f32")
+    _count(2)
+    return vals

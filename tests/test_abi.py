@@ -1,0 +1,72 @@
+"""The C-ABI shared library loads here (no GPU) and exports every symbol include/mmrec_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "mmrec_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmrec_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_built_and_exports_every_header_symbol():
+    from mmrec_b200 import _lib
+    assert os.path.isfile(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_lib.PROTOTYPES), "python prototypes and header disagree"
+
+
+def test_loader_binds_and_reports_version():
+    from mmrec_b200 import _lib
+    lib = _lib.load()
+    assert lib.mmrec_abi_version() == 1
+    assert lib.mmrec_last_error() is not None
+
+
+def test_argument_errors_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on a CPU box."""
+    from mmrec_b200 import _lib
+    lib = _lib.load()
+    assert lib.mmrec_spmm_f32(-1, 0, 64, None, None, None, None, 0, None, None, None, None, 0, None, 0, None, None, 0,
+                              1.0, None, 0, None) == -1
+    assert b"spmm" in lib.mmrec_last_error()
+    assert lib.mmrec_topk_rows_f32(4, 10, None, 10, 11, 0, None, None, None) == -1     # k > n_items
+    assert lib.mmrec_project_f32(-5, None, None, 0, 0, None, None, 0, 0, None, 0, None) == -1
+    assert lib.mmrec_topk_merge(100, 4, 50, None, None, None, None, None) == -1        # parts * k > 4096
+
+
+def test_product_path_refuses_cpu_tensors():
+    import torch
+    from mmrec_b200 import ops
+    from mmrec_b200._lib import MMRecError
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(MMRecError):
+        ops.score(torch.zeros(4, 64), torch.zeros(8, 64))
+    with pytest.raises(MMRecError):
+        ops.CSR.from_coo(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64), None, 4, 4)
+
+
+def test_product_never_imports_the_oracle():
+    import subprocess, sys
+    out = subprocess.run([sys.executable, "-c",
+                          "import sys; sys.path.insert(0, %r); import mmrec_b200.ops, mmrec_b200.graph, "
+                          "mmrec_b200.models.freedom, mmrec_b200.models.bm3, mmrec_b200.models.mgcn, "
+                          "mmrec_b200.common.trainer, mmrec_b200.utils.quick_start; "
+                          "print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))" % ROOT],
+                         capture_output=True, text=True, check=True)
+    assert out.stdout.strip() == "False"
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mmrec_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert "import oracle" not in open(os.path.join(dirpath, f)).read().replace("mmrec_oracle", "")
+                assert "from oracle" not in open(os.path.join(dirpath, f)).read()

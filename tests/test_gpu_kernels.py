@@ -1,0 +1,318 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle -- kernels in isolation.
+
+Tolerances: embeddings / projections 1e-4 relative (north star); indices bit-exact on identical scores.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import mmrec_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from mmrec_b200 import _lib
+    _lib.require_device()
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rand_coo(n_rows, n_cols, nnz, seed, dup_frac=0.1):
+    g = torch.Generator().manual_seed(seed)
+    r = torch.randint(0, n_rows, (nnz,), generator=g)
+    c = torch.randint(0, n_cols, (nnz,), generator=g)
+    nd = int(nnz * dup_frac)
+    if nd:
+        src = torch.randint(0, nnz, (nd,), generator=g)
+        r = torch.cat([r, r[src]]); c = torch.cat([c, c[src]])
+    v = torch.rand(r.numel(), generator=g) - 0.5
+    p = torch.randperm(r.numel(), generator=g)
+    return r[p], c[p], v[p]
+
+
+# ------------------------------------------------------------------------------------------------ K1c
+@pytest.mark.parametrize("n_rows,n_cols,nnz", [(1, 1, 1), (7, 5, 0), (300, 200, 5000), (2000, 3000, 40000), (5, 100000, 3000)])
+def test_csr_from_coo_coalesce_semantics(dev, n_rows, n_cols, nnz):
+    from mmrec_b200.ops import CSR
+    r, c, v = rand_coo(n_rows, n_cols, nnz, seed=nnz + n_rows)
+    A = CSR.from_coo(r.to(dev), c.to(dev), v.to(dev), n_rows, n_cols)
+    ref = torch.sparse_coo_tensor(torch.stack([r, c]), v, (n_rows, n_cols)).coalesce()
+    assert A.nnz == ref._nnz()
+    rp = A.rowptr.cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == A.nnz and np.all(np.diff(rp) >= 0)
+    if A.nnz:
+        rows, cols, vals = [t.cpu() for t in A.coo()]
+        assert np.array_equal(torch.stack([rows, cols]).numpy(), ref.indices().numpy())       # row-major, sorted cols
+        np.testing.assert_allclose(vals.numpy(), ref.values().numpy(), rtol=1e-6, atol=1e-7)
+    # duplicates kept when asked
+    B = CSR.from_coo(r.to(dev), c.to(dev), None, n_rows, n_cols, sum_duplicates=False)
+    assert B.nnz == r.numel()
+
+
+def test_csr_transpose_and_plan(dev):
+    from mmrec_b200.ops import CSR
+    r, c, v = rand_coo(500, 300, 8000, seed=3, dup_frac=0)
+    # one very long row so that the plan must split it
+    r = torch.cat([r, torch.full((3000,), 7)]); c = torch.cat([c, torch.randint(0, 300, (3000,))]); v = torch.cat([v, torch.rand(3000)])
+    A = CSR.from_coo(r.to(dev), c.to(dev), v.to(dev), 500, 300)
+    assert A.longest_row >= 290 and A.n_split >= 1 and A.n_tasks > 500 and A.n_slots >= 2
+    t = A.tasks.cpu().numpy().reshape(-1, 4)
+    lens = t[:, 2] - t[:, 1]
+    assert lens.max() <= A.seg and lens.sum() == A.nnz
+    At = A.t()
+    np.testing.assert_allclose(At.to_dense().cpu().numpy(), A.to_dense().cpu().numpy().T, rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("d", [32, 64, 128, 256, 48, 5])
+@pytest.mark.parametrize("use_plan", [True, False])
+def test_spmm_matches_oracle(dev, d, use_plan):
+    from mmrec_b200 import ops
+    from mmrec_b200.ops import CSR
+    n_rows, n_cols = 1500, 900
+    r, c, v = rand_coo(n_rows, n_cols, 20000, seed=d)
+    r = torch.cat([r, torch.full((2500,), 11), torch.full((700,), 1499)])
+    c = torch.cat([c, torch.randint(0, n_cols, (3200,))]); v = torch.cat([v, torch.rand(3200) - 0.5])
+    r[r == 5] = 6                                           # an empty row
+    X = torch.randn(n_cols, d, generator=torch.Generator().manual_seed(1))
+    A = CSR.from_coo(r.to(dev), c.to(dev), v.to(dev), n_rows, n_cols)
+    ref = torch.sparse.mm(torch.sparse_coo_tensor(torch.stack([r, c]), v, (n_rows, n_cols)), X)
+    Y = torch.full((n_rows, d), float("nan"), device=dev)
+    ops.spmm_raw(A, X.to(dev), Y=Y, use_plan=use_plan)
+    assert rel(Y, ref) < 1e-5
+    assert torch.all(Y[5] == 0)
+    # bit-reproducible run to run (fixed summation order, also for split rows)
+    Y2 = torch.empty_like(Y)
+    for _ in range(3):
+        ops.spmm_raw(A, X.to(dev), Y=Y2, use_plan=use_plan)
+        assert torch.equal(Y, Y2)
+    assert int(A.counters.abs().sum().item()) == 0          # split-row counters are self-cleaning
+
+
+@pytest.mark.parametrize("d", [64, 128, 40])
+def test_spmm_fused_epilogues(dev, d):
+    from mmrec_b200 import ops
+    from mmrec_b200.ops import CSR
+    n = 800
+    r, c, v = rand_coo(n, n, 9000, seed=9)
+    A = CSR.from_coo(r.to(dev), c.to(dev), v.to(dev), n, n)
+    Ad = A.to_dense().cpu()
+    X = torch.randn(n, d); base = torch.randn(n, d); ref0 = torch.randn(n, d)
+    # acc_out = (acc_in + y) / div, in place
+    acc = base.clone().to(dev)
+    Y = torch.empty(n, d, device=dev)
+    ops.spmm_raw(A, X.to(dev), Y=Y, acc_in=acc, acc_out=acc, acc_div=4.0)
+    y = Ad @ X
+    assert rel(Y, y) < 1e-5 and rel(acc, (base + y) / 4.0) < 1e-5
+    # acc_out only, no acc_in
+    acc2 = torch.empty(n, d, device=dev)
+    ops.spmm_raw(A, X.to(dev), acc_out=acc2)
+    assert rel(acc2, y) < 1e-5
+    # LayerGCN gate (layergcn.py:132-133)
+    Yg = torch.empty(n, d, device=dev)
+    ops.spmm_raw(A, X.to(dev), Y=Yg, gate_ref=ref0.to(dev))
+    w = torch.nn.functional.cosine_similarity(y, ref0, dim=-1)
+    assert rel(Yg, w.unsqueeze(1) * y) < 1e-5
+
+
+def test_propagate_mean_forward_backward_vs_oracle(dev, golden):
+    from mmrec_b200 import graph, ops
+    g = golden("freedom_tiny.npz")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    adj = graph.build_norm_adj((g["inter_row"], g["inter_col"]), U, I, dev)
+    oadj = O.norm_adj_coo(g["inter_row"], g["inter_col"], U, I)
+    ego = torch.cat([torch.from_numpy(g["param0.user_embedding.weight"]), torch.from_numpy(g["param0.item_id_embedding.weight"])])
+    for L in (0, 1, 2, 3, 4):
+        e1 = ego.clone().to(dev).requires_grad_(True)
+        e2 = ego.clone().requires_grad_(True)
+        out = ops.propagate_mean(adj, e1, L)
+        ref = O.propagate_mean(oadj, e2, L)
+        assert rel(out, ref) < 1e-5
+        w = torch.randn_like(ref)
+        (out * w.to(dev)).sum().backward()
+        (ref * w).sum().backward()
+        assert rel(e1.grad, e2.grad) < 1e-5
+    # spmm with base, directed matrix (needs the explicit transpose in backward)
+    mm = torch.sparse_coo_tensor(torch.from_numpy(g["mm_adj_idx"]), torch.from_numpy(g["mm_adj_val"]), (I, I))
+    M = ops.CSR.from_torch_sparse(mm.to(dev))
+    assert M.nnz < g["mm_adj_val"].shape[0]                 # duplicates were summed
+    h1 = ego[U:].clone().to(dev).requires_grad_(True); b1 = torch.randn(I, 64, device=dev, requires_grad=True)
+    h2 = ego[U:].clone().requires_grad_(True); b2 = b1.detach().cpu().requires_grad_(True)
+    o1 = ops.spmm(M, h1, base=b1); o2 = b2 + torch.sparse.mm(mm, h2)
+    assert rel(o1, o2) < 1e-5
+    w = torch.randn(I, 64)
+    (o1 * w.to(dev)).sum().backward(); (o2 * w).sum().backward()
+    assert rel(h1.grad, h2.grad) < 1e-5 and rel(b1.grad, b2.grad) < 1e-6
+
+
+def test_bipartite_norm_and_pruning_vs_reference(dev, golden):
+    from mmrec_b200 import graph
+    g = golden("freedom_tiny.npz")
+    U, I = int(g["n_users"]), int(g["n_items"])
+    pr = graph.EdgePruner((g["inter_row"], g["inter_col"]), U, I, dev)
+    assert np.array_equal(pr.edge_indices.cpu().numpy(), g["edge_indices"])
+    ev = pr.edge_values.cpu().numpy()
+    # 1/sqrt with IEEE sqrt+div: identical bits to torch.pow(x, -0.5) on CPU, or within 1 ulp
+    assert np.max(np.abs(ev.view(np.int32).astype(np.int64) - g["edge_values"].view(np.int32).astype(np.int64))) <= 1
+    A = pr.adj_from_keep(torch.from_numpy(g["prune_keep_idx"]).to(dev))
+    n = U + I
+    ref = torch.sparse_coo_tensor(torch.from_numpy(g["masked_adj_idx"]), torch.from_numpy(g["masked_adj_val"]), (n, n)).to_dense()
+    np.testing.assert_allclose(A.to_dense().cpu().numpy(), ref.numpy(), rtol=2e-7, atol=0)
+    assert A.nnz == g["masked_adj_val"].shape[0]
+    A2, keep = pr.sample(float(g["cfg_dropout"]))
+    assert keep.numel() == g["prune_keep_idx"].shape[0] and len(torch.unique(keep)) == keep.numel()
+    assert A2.nnz == 2 * keep.numel()
+
+
+# ------------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("n,F,d", [(700, 256, 64), (1000, 4096, 64), (333, 130, 64), (257, 384, 32), (300, 512, 128),
+                                   (129, 200, 256), (64, 77, 96), (50, 64, 300)])
+def test_project_matches_oracle(dev, n, F, d):
+    from mmrec_b200 import ops
+    g = torch.Generator().manual_seed(n + F)
+    X = torch.randn(n, F, generator=g); W = torch.randn(d, F, generator=g) / F ** 0.5; b = torch.randn(d, generator=g)
+    idx = torch.randint(0, n, (n // 2 + 3,), generator=g)
+    Xd, Wd, bd = X.to(dev), W.to(dev), b.to(dev)
+    assert rel(ops.project(Xd, Wd, bd), O.project(X, W, b)) < 1e-5
+    assert rel(ops.project(Xd, Wd, None), O.project(X, W, None)) < 1e-5
+    assert rel(ops.project(Xd, Wd, bd, idx=idx.to(dev)), O.project(X, W, b, idx=idx)) < 1e-5
+    assert rel(ops.project(Xd, Wd, bd, l2_normalize=True), O.project(X, W, b, l2_normalize=True)) < 1e-5
+    # autograd (backward of nn.Linear + gather)
+    X1, W1, b1 = Xd.clone().requires_grad_(True), Wd.clone().requires_grad_(True), bd.clone().requires_grad_(True)
+    X2, W2, b2 = X.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    w = torch.randn(idx.numel(), d, generator=g)
+    (ops.project(X1, W1, b1, idx=idx.to(dev)) * w.to(dev)).sum().backward()
+    (O.project(X2, W2, b2, idx=idx) * w).sum().backward()
+    assert rel(X1.grad, X2.grad) < 1e-5 and rel(W1.grad, W2.grad) < 1e-5 and rel(b1.grad, b2.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("B,I,k", [(1, 50, 50), (3, 51, 1), (127, 1000, 50), (300, 7000, 50), (64, 5000, 1024), (4097, 333, 20)])
+def test_topk_exact_on_identical_scores(dev, B, I, k):
+    from mmrec_b200 import ops
+    g = torch.Generator().manual_seed(B * 7 + I)
+    S = torch.randn(B, I, generator=g)
+    S = (S * 8).round() / 8                                                           # many exact ties
+    S[0, :] = 0.25                                                                    # a fully tied row
+    nm = min(B * 5, B * I // 2)
+    mask = torch.stack([torch.randint(0, B, (nm,), generator=g), torch.randint(0, I, (nm,), generator=g)])
+    ref = S.clone()
+    ref[mask[0], mask[1]] = -1e10
+    rv, ri = O.topk_tie_low_index(ref.numpy(), k)
+    Sd = S.clone().to(dev)
+    val, idx = ops.mask_topk(Sd, mask.to(dev), k)
+    assert torch.equal(Sd.cpu(), ref)                       # in-place mask, like the trainer
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert np.array_equal(val.cpu().numpy(), rv)
+    tv, _ = torch.topk(ref, k, dim=-1)                      # values agree with torch.topk exactly
+    assert torch.equal(val.cpu(), tv)
+    v2, i2 = ops.mask_topk(S.clone().to(dev), None, k, item_offset=1000)
+    assert torch.equal(i2.cpu() - 1000, torch.from_numpy(O.topk_tie_low_index(S.numpy(), k)[1]))
+
+
+@pytest.mark.parametrize("B,U,I,d,k", [(128, 500, 700, 64, 50), (4096, 5000, 7000, 64, 50), (1000, 1000, 333, 64, 20),
+                                       (77, 300, 20000, 128, 50), (513, 600, 900, 32, 10), (200, 200, 500, 48, 5)])
+@pytest.mark.parametrize("path", ["simt", "tc"])
+def test_score_and_fused_topk(dev, B, U, I, d, k, path):
+    from mmrec_b200 import ops
+    ops.set_score_path(path == "tc")
+    try:
+        g = torch.Generator().manual_seed(B + I)
+        ue = torch.randn(U, d, generator=g) * 0.1; ie = torch.randn(I, d, generator=g) * 0.1
+        users = torch.randint(0, U, (B,), generator=g)
+        nm = B * 8
+        mask = torch.stack([torch.randint(0, B, (nm,), generator=g), torch.randint(0, I, (nm,), generator=g)])
+        S = ops.score(ue.to(dev), ie.to(dev), users.to(dev))
+        ref = O.full_sort_scores(ue.double(), ie.double(), users)
+        scale = ref.abs().max().item()
+        assert (S.cpu().double() - ref).abs().max().item() < 2e-6 * scale + 1e-9      # fp32-level accuracy
+        assert S.shape == (B, I) and S.is_contiguous()
+        # fused path == the unfused path on the kernel's own scores (identical arithmetic -> identical indices)
+        val, idx = ops.score_topk(ue.to(dev), ie.to(dev), users.to(dev), mask.to(dev), k)
+        Sm = S.clone()
+        v2, i2 = ops.mask_topk(Sm, mask.to(dev), k)
+        assert torch.equal(idx, i2) and torch.equal(val, v2)
+        # against the fp64 re-score: every disagreement must be a near tie, and the SETS must agree up to near ties
+        refm = ref.clone(); refm[mask[0], mask[1]] = -1e10
+        rv, ri = O.topk_tie_low_index(refm.numpy(), k)
+        got = idx.cpu().numpy()
+        bad = np.nonzero((got != ri).any(axis=1))[0]
+        for b in bad:
+            cols = np.nonzero(got[b] != ri[b])[0]
+            gap = np.abs(refm[b, got[b, cols]].numpy() - refm[b, ri[b, cols]].numpy()).max()
+            assert gap < 4e-6 * scale, f"row {b}: non-tie mismatch, gap {gap}"
+        assert len(bad) <= max(2, B // 20)
+    finally:
+        ops.set_score_path(True)
+
+
+def test_score_without_user_index_and_strided_inputs(dev):
+    from mmrec_b200 import ops
+    ue = torch.randn(300, 64, device=dev); ie = torch.randn(411, 64, device=dev)
+    S = ops.score(ue, ie)
+    assert rel(S, ue.cpu() @ ie.cpu().t()) < 1e-5
+    big = torch.randn(300, 128, device=dev)
+    S2 = ops.score(big[:, :64], ie)                         # non-contiguous view is made contiguous
+    assert rel(S2, big[:, :64].cpu() @ ie.cpu().t()) < 1e-5
+
+
+def test_topk_merge_equals_global_topk(dev):
+    from mmrec_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, I, k, parts = 700, 4000, 50, 8
+    S = torch.randn(B, I, generator=g)
+    S[:, 100] = S[:, 3100]                                  # ties across shards
+    shard = I // parts
+    vals, idxs = [], []
+    for p in range(parts):
+        v, i = ops.mask_topk(S[:, p * shard:(p + 1) * shard].contiguous().to(dev), None, k, item_offset=p * shard)
+        vals.append(v); idxs.append(i)
+    mv, mi = ops.topk_merge(torch.stack(vals), torch.stack(idxs))
+    rv, ri = O.topk_tie_low_index(S.numpy(), k)
+    assert np.array_equal(mi.cpu().numpy(), ri) and np.array_equal(mv.cpu().numpy(), rv)
+
+
+# ------------------------------------------------------------------------------------------------ full size
+def test_full_size_properties_baby(dev):
+    """BASELINE.json configs[1] sizes (20k users, 7k items, 160k edges, d=64): size-independent properties."""
+    from mmrec_b200 import graph, ops
+    from mmrec_b200.utils import synth
+    g = synth.named("baby")
+    U, I = g.n_users, g.n_items
+    tu, ti = g.train
+    A = graph.build_norm_adj((tu, ti), U, I, dev)
+    n = U + I
+    assert A.nnz == 2 * len(tu)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 64, generator=gen).to(dev); y = torch.randn(n, 64, generator=gen).to(dev)
+    Ax, Ay, Axy = (torch.empty(n, 64, device=dev) for _ in range(3))
+    ops.spmm_raw(A, x, Y=Ax); ops.spmm_raw(A, y, Y=Ay); ops.spmm_raw(A, x + y, Y=Axy)
+    assert rel(Axy, Ax + Ay) < 1e-6                                           # linearity
+    assert abs(((Ax * y).sum() - (x * Ay).sum()).item()) < 1e-3 * (Ax * y).abs().sum().item()   # symmetry <Ax,y>=<x,Ay>
+    ones = torch.ones(n, 64, device=dev); A1 = torch.empty(n, 64, device=dev)
+    ops.spmm_raw(A, ones, Y=A1)
+    rows, _, vals = A.coo()
+    rs = torch.zeros(n, device=dev, dtype=torch.float64).index_add_(0, rows, vals.double())
+    assert (A1[:, 0].double() - rs).abs().max().item() < 1e-5               # A 1 = row sums
+    emb = ops.propagate_mean(A, x * 0.05, 3)
+    ue, ie = emb[:U].contiguous(), emb[U:].contiguous()
+    users = torch.arange(0, 4096, device=dev)
+    mask = torch.stack([torch.from_numpy(tu[tu < 4096]), torch.from_numpy(ti[tu < 4096])]).to(dev)
+    val, idx = ops.score_topk(ue, ie, users, mask, 50)
+    assert torch.all(val[:, :-1] >= val[:, 1:])                               # sorted
+    assert idx.min() >= 0 and idx.max() < I
+    assert all(len(set(r)) == 50 for r in idx[:64].cpu().tolist())          # no repeats
+    re = (ue[users][:, None, :] * ie[idx]).sum(-1)                            # values are the scores of the indices
+    assert (re - val).abs().max().item() < 1e-5 * val.abs().max().item() + 1e-9
+    hit = torch.zeros(4096, I, dtype=torch.bool, device=dev); hit[mask[0], mask[1]] = True
+    assert not hit.gather(1, idx).any()                                       # masked train positives never returned
+    val2, idx2 = ops.score_topk(ue, ie, users, mask, 50)
+    assert torch.equal(idx, idx2) and torch.equal(val, val2)                  # idempotent / deterministic

@@ -1,0 +1,159 @@
+"""Host-side logic of the drop-in (no GPU): graph builders, config, dataset, dataloaders, evaluator -- against the
+golden vectors recorded from the reference and against the oracle."""
+import os
+import random
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from mmrec_b200 import graph
+from mmrec_b200.utils import synth
+from mmrec_b200.utils.configurator import Config
+from mmrec_b200.utils.dataloader import EvalDataLoader, TrainDataLoader
+from mmrec_b200.utils.dataset import RecDataset
+from mmrec_b200.utils.topk_evaluator import TopKEvaluator, hit_matrix
+from mmrec_b200.utils.utils import early_stopping, get_model
+from oracle import mmrec_oracle as O
+
+
+@pytest.fixture(scope="module")
+def tiny_run():
+    tmp = tempfile.mkdtemp(prefix="mmrec_host_")
+    u, i, e, d, f = synth.SHAPES["tiny"]
+    g = synth.make_graph(u, i, e, seed=0)
+    v, t = synth.make_features(i, f, seed=1)
+    synth.write_dataset(os.path.join(tmp, "data"), "tiny", g, v, t)
+    cfg = Config("FREEDOM", "tiny", {"data_path": os.path.join(tmp, "data") + "/", "use_gpu": False,
+                                     "eval_batch_size": 128, "train_batch_size": 512})
+    ds = RecDataset(cfg)
+    tr, va, te = ds.split()
+    return cfg, g, tr, va, te
+
+
+def test_synth_graph_matches_golden_graph(golden):
+    gg = golden("tiny_graph.npz")
+    g = synth.named("tiny")
+    assert np.array_equal(g.user, gg["user"]) and np.array_equal(g.item, gg["item"]) and np.array_equal(g.label, gg["label"])
+    tu, ti = g.train
+    assert np.bincount(tu, minlength=g.n_users).min() >= 1 and np.bincount(ti, minlength=g.n_items).min() >= 1
+    assert len(np.unique(g.user * g.n_items + g.item)) == len(g.user)
+
+
+@pytest.mark.parametrize("f,attr", [("freedom_tiny.npz", "norm_adj"), ("lightgcn_tiny.npz", "norm_adj_matrix")])
+def test_norm_adj_entries_bit_exact_vs_reference(golden, f, attr):
+    g = golden(f)
+    rows, cols, vals = graph.norm_adj_entries(g["inter_row"], g["inter_col"], int(g["n_users"]), int(g["n_items"]))
+    assert np.array_equal(np.stack([rows, cols]), g[attr + "_idx"])
+    assert np.array_equal(vals.view(np.uint32), g[attr + "_val"].view(np.uint32))
+
+
+def test_mgcn_entries_bit_exact_vs_reference(golden):
+    g = golden("mgcn_tiny.npz")
+    rows, cols, vals = graph.mgcn_norm_adj_entries(g["inter_row"], g["inter_col"], int(g["n_users"]), int(g["n_items"]))
+    assert np.array_equal(np.stack([rows, cols]), g["norm_adj_idx"])
+    assert np.array_equal(vals.view(np.uint32), g["norm_adj_val"].view(np.uint32))
+
+
+def test_config_layers_and_missing_keys(tiny_run):
+    cfg = tiny_run[0]
+    assert cfg["embedding_size"] == 64 and cfg["n_ui_layers"] == 2 and cfg["knn_k"] == 10
+    assert cfg["reg_weight"] == [0.0, 1e-05, 1e-04, 1e-03]           # widened float syntax
+    assert cfg["USER_ID_FIELD"] == "userID" and cfg["no_such_key"] is None
+    assert cfg["hyper_parameters"] == ["seed", "dropout", "reg_weight"] or set(cfg["hyper_parameters"]) == {"seed", "dropout", "reg_weight"}
+    assert cfg["valid_metric_bigger"] is True and cfg["device"].type == "cpu"
+    cfg2 = Config("BM3", "tiny", {"n_layers": [2]})
+    assert cfg2["use_neg_sampling"] is False and cfg2["n_layers"] == [2]
+
+
+def test_dataset_split_and_cold_start_filter(tiny_run):
+    cfg, g, tr, va, te = tiny_run
+    assert len(tr) == int((g.label == 0).sum())
+    train_users = set(tr.df["userID"].tolist())
+    assert set(va.df["userID"]).issubset(train_users) and set(te.df["userID"]).issubset(train_users)
+    assert tr.get_user_num() == g.n_users and tr.get_item_num() == g.n_items
+
+
+def test_train_loader_batches_and_negatives(tiny_run):
+    cfg, g, tr, va, te = tiny_run
+    dl = TrainDataLoader(cfg, tr, batch_size=512, shuffle=True)
+    dl.pretrain_setup()
+    hist = set(zip(tr.df["userID"].tolist(), tr.df["itemID"].tolist()))
+    seen = 0
+    for batch in dl:
+        assert batch.dtype == torch.int64 and batch.shape[0] == 3 and batch.shape[1] <= 512
+        u, p, n = batch.numpy()
+        assert all((a, b) in hist for a, b in zip(u.tolist(), p.tolist()))
+        assert not any((a, b) in hist for a, b in zip(u.tolist(), n.tolist()))
+        seen += batch.shape[1]
+    assert seen == len(tr)
+    m = dl.inter_matrix(form="coo")
+    assert m.shape == (g.n_users, g.n_items) and m.nnz == len(tr)
+    cfg_b = Config("BM3", "tiny", {"data_path": cfg["data_path"], "use_gpu": False})
+    b = next(iter(TrainDataLoader(cfg_b, tr, batch_size=100)))
+    assert b.shape == (2, 100)
+
+
+def test_eval_loader_matches_reference_batches(tiny_run, golden):
+    cfg, g, tr, va, te = tiny_run
+    gold = golden("freedom_tiny.npz")
+    dl = EvalDataLoader(cfg, va, additional_dataset=tr, batch_size=128)
+    first = next(iter(dl))
+    assert np.array_equal(first[0].numpy(), gold["eval_users"])
+    # same mask entries per batch row (the reference keeps per-user order of appearance)
+    assert np.array_equal(first[1].numpy(), gold["eval_mask"])
+    dl.pr = 0
+    n_users = 0
+    for users, mask in dl:
+        assert mask[0].max() < users.shape[0] and mask[0].min() >= 0
+        n_users += users.shape[0]
+    assert n_users == len(dl.get_eval_items()) == len(dl.get_eval_len_list())
+    for a, b in zip(dl.get_eval_items()[:128], gold["eval_pos_items"]):
+        assert sorted(a.tolist()) == sorted(b.tolist())
+
+
+def test_evaluator_matches_reference_metrics(tiny_run, golden):
+    cfg, g, tr, va, te = tiny_run
+    gold = golden("lightgcn_tiny.npz")
+    U, I = int(gold["n_users"]), int(gold["n_items"])
+    adj = O.norm_adj_coo(gold["inter_row"], gold["inter_col"], U, I)
+    ue, ie = torch.from_numpy(gold["param0.embedding_dict.user_emb"]), torch.from_numpy(gold["param0.embedding_dict.item_emb"])
+    u, i = O.lightgcn_forward(adj, ue, ie, int(gold["cfg_n_layers"]))
+    dl = EvalDataLoader(cfg, te, additional_dataset=tr, batch_size=128)
+    lists = []
+    for users, mask in dl:
+        s = O.full_sort_scores(u, i, users)
+        lists.append(O.mask_topk(s, mask, 50)[1])
+    res = TopKEvaluator(cfg).evaluate(lists, dl)
+    got = np.array([res[k] for k in gold["metric_names"]])
+    np.testing.assert_allclose(got, gold["test_metric_values"], atol=1e-12)
+    # vectorised hit matrix == the reference's membership loop
+    topk = torch.cat(lists).numpy()
+    slow = np.array([[x in set(m.tolist()) for x in n] for m, n in zip(dl.get_eval_items(), topk)])
+    assert np.array_equal(hit_matrix(topk, dl.get_eval_items()), slow)
+
+
+def test_early_stopping_and_plugin_loader():
+    best, step, stop, upd = early_stopping(0.5, 0.4, 3, max_step=5, bigger=True)
+    assert (best, step, stop, upd) == (0.5, 0, False, True)
+    best, step, stop, upd = early_stopping(0.3, 0.5, 5, max_step=5, bigger=True)
+    assert (best, step, stop, upd) == (0.5, 6, True, False)
+    for name in ("FREEDOM", "BM3", "MGCN", "LightGCN", "LayerGCN"):
+        cls = get_model(name)
+        assert cls.__name__ == name
+        for meth in ("calculate_loss", "full_sort_predict", "forward", "pre_epoch_processing", "post_epoch_processing"):
+            assert hasattr(cls, meth)
+
+
+def test_models_fail_loudly_without_cuda(tiny_run):
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from mmrec_b200._lib import MMRecError
+    cfg, g, tr, va, te = tiny_run
+    dl = TrainDataLoader(cfg, tr, batch_size=512)
+    for k in cfg["hyper_parameters"]:
+        if isinstance(cfg[k], list):
+            cfg[k] = cfg[k][0]
+    with pytest.raises(MMRecError):
+        get_model("FREEDOM")(cfg, dl)
