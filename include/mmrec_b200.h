@@ -59,12 +59,12 @@ int mmrec_csr_from_coo(int64_t nnz, const int64_t* row, const int64_t* col, cons
 
 /* Work plan for mmrec_spmm_f32: rows longer than `seg` non-zeros are split into segments so that
  * the power-law item rows do not serialise on one warp.
- *   tasks      int32[4 * max_tasks]  {row, begin, end, split_id(-1 = whole row)}
+ *   tasks      int32[4 * max_tasks]  {row, begin, end, split_id(-1 = whole row)}, sorted longest first
  *   split_rows int32[4 * max_split]  {first_slot, n_seg, row_begin, seg}
  *   counts     int64[4] on the device: {n_tasks, n_split_rows, n_slots, longest_row}
  * max_tasks = n_rows + nnz / seg + 1 and max_split = nnz / seg + 1 are always enough. */
-size_t mmrec_spmm_plan_workspace_bytes(int64_t n_rows);
-int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg,
+size_t mmrec_spmm_plan_workspace_bytes(int64_t n_rows, int64_t max_tasks);
+int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, int64_t max_tasks,
                     int32_t* tasks, int32_t* split_rows, int64_t* counts,
                     void* ws, size_t ws_bytes, void* stream);
 
@@ -94,6 +94,8 @@ int mmrec_bipartite_norm_f32(int64_t n_edges, const int64_t* users, const int64_
  * fp32[n_slots * d]); tasks == NULL selects one warp per row.  Summation order is fixed, so the
  * result is bit-reproducible run to run.
  * ------------------------------------------------------------------------------------------- */
+/* tuning knob: lanes that cooperate on one row (0 = default d/8; a power of two, d/(4*lanes) float4 per lane) */
+int mmrec_spmm_set_lanes(int lanes_per_row);
 int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d,
                    const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    const int32_t* tasks, int64_t n_tasks, const int32_t* split_rows,
@@ -122,6 +124,8 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
  * `scores[mask[0], mask[1]] = -1e10; torch.topk(scores, k)` (src/common/trainer.py:304-309).
  *
  * mmrec_score_f32:    S[b, i] = <Ue[users ? users[b] : b, :], Ie[i, :]>            S [B, ldS]
+ *                     ws (mmrec_score_workspace_bytes) holds the re-tiled hi/lo operands of the tensor-core
+ *                     path; ws == NULL selects the CUDA-core fp32 path.
  * mmrec_mask_f32:     S[mask_rows[j], mask_cols[j] - item_offset] = -1e10 for columns inside
  *                     [item_offset, item_offset + n_items)
  * mmrec_topk_rows_f32: out_idx/out_val [B, k], descending value, ties -> lower index, index
@@ -134,9 +138,10 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
 /* arithmetic path of mmrec_score_f32 / mmrec_score_topk_f32: 1 = tcgen05 3xTF32 where the shape fits
  * (default; env MMREC_SCORE_PATH=simt|tc sets the initial value), 0 = exact fp32 on CUDA cores. */
 int mmrec_score_set_path(int tensor_core);
+size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d);
 int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu,
                     int64_t n_items, const float* Ie, int64_t ldi, int d,
-                    float* S, int64_t ldS, void* stream);
+                    float* S, int64_t ldS, void* ws, size_t ws_bytes, void* stream);
 int mmrec_mask_f32(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols,
                    int64_t B, int64_t n_items, int64_t item_offset, float* S, int64_t ldS, void* stream);
 int mmrec_topk_rows_f32(int64_t B, int64_t n_items, const float* S, int64_t ldS, int k,

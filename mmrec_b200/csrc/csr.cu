@@ -105,7 +105,8 @@ __global__ void plan_count_kernel(int64_t n_rows, const int32_t* __restrict__ ro
 __global__ void plan_fill_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr, int seg,
                                  const int32_t* __restrict__ t_off, const int32_t* __restrict__ s_off,
                                  const int32_t* __restrict__ l_off, const int* __restrict__ longest,
-                                 int4* __restrict__ tasks, int4* __restrict__ split_rows, int64_t* __restrict__ counts) {
+                                 int4* __restrict__ tasks, uint32_t* __restrict__ keys, int4* __restrict__ split_rows,
+                                 int64_t* __restrict__ counts) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r == 0) {
         counts[0] = t_off[n_rows]; counts[1] = s_off[n_rows]; counts[2] = l_off[n_rows]; counts[3] = *longest;
@@ -116,6 +117,7 @@ __global__ void plan_fill_kernel(int64_t n_rows, const int32_t* __restrict__ row
     int t0 = t_off[r];
     if (nt == 1) {
         tasks[t0] = make_int4((int)r, b, e, -1);
+        keys[t0] = (uint32_t)(seg - (e - b));          // ascending key = longest task first
     } else {
         int sid = s_off[r];
         split_rows[sid] = make_int4(l_off[r], nt, b, seg);
@@ -123,8 +125,16 @@ __global__ void plan_fill_kernel(int64_t n_rows, const int32_t* __restrict__ row
             int sb = b + j * seg;
             int se = sb + seg < e ? sb + seg : e;
             tasks[t0 + j] = make_int4((int)r, sb, se, sid);
+            keys[t0 + j] = (uint32_t)(seg - (se - sb));
         }
     }
+}
+
+__global__ void plan_pad_kernel(int64_t max_tasks, uint32_t* __restrict__ keys, int4* __restrict__ tasks) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= max_tasks) return;
+    keys[t] = 255u;                                    // unused slots sort behind every real task
+    tasks[t] = make_int4(-1, 0, 0, -1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -202,34 +212,44 @@ namespace {
 struct PlanWs {
     int32_t *nt, *ns, *nl, *t_off, *s_off, *l_off;
     int* longest;
+    uint32_t *keys_a, *keys_b;
+    int4* tasks_tmp;
     void* cub_tmp;
     size_t cub_bytes, total;
 };
-PlanWs plan_ws_layout(int64_t n_rows, void* base) {
+PlanWs plan_ws_layout(int64_t n_rows, int64_t max_tasks, void* base) {
     PlanWs w;
     size_t n = (size_t)n_rows + 1;
-    size_t scan_bytes = 0;
+    size_t m = (size_t)(max_tasks > 0 ? max_tasks : 1);
+    size_t scan_bytes = 0, sort_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int64_t)n);
-    w.cub_bytes = scan_bytes;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int4*)nullptr,
+                                    (int4*)nullptr, (int64_t)m, 0, 8);
+    w.cub_bytes = scan_bytes > sort_bytes ? scan_bytes : sort_bytes;
     char* p = (char*)base;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* q = p ? p + off : nullptr; off += mmrec::align_up(bytes, 256); return q; };
     w.nt = (int32_t*)take(n * 4); w.ns = (int32_t*)take(n * 4); w.nl = (int32_t*)take(n * 4);
     w.t_off = (int32_t*)take(n * 4); w.s_off = (int32_t*)take(n * 4); w.l_off = (int32_t*)take(n * 4);
     w.longest = (int*)take(256);
+    w.keys_a = (uint32_t*)take(m * 4); w.keys_b = (uint32_t*)take(m * 4);
+    w.tasks_tmp = (int4*)take(m * 16);
     w.cub_tmp = take(w.cub_bytes);
     w.total = off;
     return w;
 }
 }  // namespace
 
-extern "C" size_t mmrec_spmm_plan_workspace_bytes(int64_t n_rows) { return plan_ws_layout(n_rows, nullptr).total; }
+extern "C" size_t mmrec_spmm_plan_workspace_bytes(int64_t n_rows, int64_t max_tasks) {
+    return plan_ws_layout(n_rows, max_tasks, nullptr).total;
+}
 
-extern "C" int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, int32_t* tasks, int32_t* split_rows,
-                               int64_t* counts, void* ws, size_t ws_bytes, void* stream_) {
+extern "C" int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, int64_t max_tasks, int32_t* tasks,
+                               int32_t* split_rows, int64_t* counts, void* ws, size_t ws_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    MMREC_CHECK_ARG(n_rows >= 0 && seg >= 32 && rowptr && tasks && split_rows && counts, "spmm_plan: bad argument");
-    PlanWs w = plan_ws_layout(n_rows, ws);
+    MMREC_CHECK_ARG(n_rows >= 0 && seg >= 32 && seg <= 254 && max_tasks >= n_rows && rowptr && tasks && split_rows && counts,
+                    "spmm_plan: bad argument (need 32 <= seg <= 254, max_tasks >= n_rows)");
+    PlanWs w = plan_ws_layout(n_rows, max_tasks, ws);
     if (ws_bytes < w.total || !ws) {
         set_error("spmm_plan: workspace %zu < %zu", ws_bytes, w.total);
         return MMREC_EWORKSPACE;
@@ -245,9 +265,18 @@ extern "C" int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, i
     MMREC_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.ns, w.s_off, n_rows + 1, stream));
     tmp = w.cub_bytes;
     MMREC_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tmp, w.nl, w.l_off, n_rows + 1, stream));
+    if (max_tasks > 0) {
+        plan_pad_kernel<<<(unsigned)((max_tasks + T - 1) / T), T, 0, stream>>>(max_tasks, w.keys_a, w.tasks_tmp);
+        MMREC_LAUNCH_CHECK();
+    }
     plan_fill_kernel<<<(unsigned)nb, T, 0, stream>>>(n_rows, rowptr, seg, w.t_off, w.s_off, w.l_off, w.longest,
-                                                    (int4*)tasks, (int4*)split_rows, counts);
+                                                    w.tasks_tmp, w.keys_a, (int4*)split_rows, counts);
     MMREC_LAUNCH_CHECK();
+    if (max_tasks > 0) {   // longest tasks first: homogeneous work inside a warp, heavy rows never in the tail
+        tmp = w.cub_bytes;
+        MMREC_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_a, w.keys_b, w.tasks_tmp, (int4*)tasks, max_tasks, 0, 8,
+                                                   stream));
+    }
     return MMREC_OK;
 }
 

@@ -16,7 +16,8 @@
 namespace mmrec {
 // implemented in score_tc.cu; returns 1 if it handled the call, 0 if the shape is unsupported, <0 on error
 int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie,
-             int64_t ldi, int d, float* S, int64_t ldS, cudaStream_t stream);
+             int64_t ldi, int d, float* S, int64_t ldS, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t score_tc_workspace_bytes(int64_t B, int64_t n_items, int d);
 
 int mask_apply(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int64_t row0, int64_t B,
                int64_t n_items, int64_t item_offset, float* S, int64_t ldS, cudaStream_t stream);
@@ -35,14 +36,19 @@ using namespace mmrec;
 
 extern "C" int mmrec_score_set_path(int tc) { g_score_path = tc ? 1 : 0; return MMREC_OK; }
 
+extern "C" size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d) {
+    return score_tc_workspace_bytes(B, n_items, d) + 256;
+}
+
 extern "C" int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items,
-                               const float* Ie, int64_t ldi, int d, float* S, int64_t ldS, void* stream_) {
+                               const float* Ie, int64_t ldi, int d, float* S, int64_t ldS, void* ws, size_t ws_bytes,
+                               void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MMREC_CHECK_ARG(B >= 0 && n_items >= 0 && d >= 1, "score: bad sizes");
     if (B == 0 || n_items == 0) return MMREC_OK;
     MMREC_CHECK_ARG(Ue && Ie && S && ldu >= d && ldi >= d && ldS >= n_items, "score: null pointer or bad leading dimension");
     if (score_path() == 1) {
-        int r = score_tc(B, users, Ue, ldu, n_items, Ie, ldi, d, S, ldS, stream);
+        int r = score_tc(B, users, Ue, ldu, n_items, Ie, ldi, d, S, ldS, ws, ws_bytes, stream);
         if (r != 0) return r < 0 ? r : MMREC_OK;
     }
     GemmNT p;
@@ -62,7 +68,9 @@ static int64_t score_block_rows(int64_t B, int64_t n_items) {
 extern "C" size_t mmrec_score_topk_workspace_bytes(int64_t B, int64_t n_items, int d, int k) {
     (void)d; (void)k;
     if (B <= 0 || n_items <= 0) return 256;
-    return (size_t)score_block_rows(B, n_items) * (size_t)((n_items + 3) / 4 * 4) * sizeof(float) + 256;
+    const int64_t rows = score_block_rows(B, n_items);
+    return align_up((size_t)rows * (size_t)((n_items + 3) / 4 * 4) * sizeof(float) + 256, 1024) +
+           mmrec_score_workspace_bytes(rows, n_items, d);
 }
 
 extern "C" int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items,
@@ -79,10 +87,13 @@ extern "C" int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float
     float* S = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const int64_t ldS = (n_items + 3) / 4 * 4;
     const int64_t rows = score_block_rows(B, n_items);
+    const size_t s_bytes = align_up((size_t)rows * (size_t)ldS * sizeof(float) + 256, 1024);
+    void* ws2 = (char*)ws + s_bytes;
+    const size_t ws2_bytes = ws_bytes - s_bytes;
     for (int64_t r0 = 0; r0 < B; r0 += rows) {
         const int64_t nb = (B - r0) < rows ? (B - r0) : rows;
         int rc = mmrec_score_f32(nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_items, Ie, ldi, d, S,
-                                 ldS, stream_);
+                                 ldS, ws2, ws2_bytes, stream_);
         if (rc) return rc;
         if (mask_nnz > 0) {
             // mask rows are positions in the whole batch: the kernel shifts by r0 and ignores rows outside [0, nb)

@@ -2,13 +2,15 @@
 // cosine gate).  HBM/L2-bound gather kernel: no tensor cores (0.25-0.5 flop/byte).
 //
 // Mapping (D = embedding width, a multiple of 32 floats):
-//   * one warp per task; a task is a whole row or, for rows longer than the plan's segment length, one
-//     segment of it (mmrec_spmm_plan) -- the power-law item rows would otherwise serialise on one warp;
-//   * inside a warp a row of X is D*4 bytes = LPR lanes x float4 (LPR = D/4, at most 32): every lane group
-//     issues ONE coalesced 16-byte-per-lane request per non-zero, G = 32/LPR groups work on G non-zeros at a
-//     time, each lane keeps UNR independent loads in flight;
-//   * column indices / values are fetched 32 at a time with one coalesced load per warp and handed round
-//     with shuffles; group partial sums are combined with shuffles at the end of the row;
+//   * a task is a whole row or, for rows longer than the plan's segment length, one segment of it
+//     (mmrec_spmm_plan; tasks arrive sorted longest-first) -- the power-law item rows would otherwise
+//     serialise on one warp;
+//   * T lanes (default D/8) own one task, a warp runs 32/T tasks side by side; each lane holds V = D/(4T)
+//     float4 of the row, so one row of X is V coalesced T*16-byte requests; UNR rows of X are in flight per
+//     lane group before the first FMA;
+//   * column indices / values are fetched T at a time with one coalesced load per group and handed round
+//     with width-T shuffles; the next task's descriptor and the running-sum row of the epilogue are
+//     prefetched while the gather is in flight;
 //   * split rows: each segment writes its partial sum to scratch, the LAST segment to arrive (per-row
 //     counter) adds the partials in segment order -> the summation order never depends on scheduling, so
 //     results are bit-reproducible.
@@ -28,33 +30,37 @@ struct SpmmParams {
     int d;
 };
 
-template <int D>
+// T lanes cooperate on one task (row or row segment); a warp runs 32/T tasks at once.  Fewer lanes per row
+// means more rows in flight per SM -- the kernel is bound by dependent-load latency (task descriptor -> column
+// indices -> rows of X), not by bytes, so rows in flight is what buys throughput at Amazon-scale graphs.
+template <int D, int T>
 struct VecCfg {
-    static constexpr int V = D >= 128 ? D / 128 : 1;   // float4 per lane
-    static constexpr int LPR = D >= 128 ? 32 : D / 4;  // lanes per row
-    static constexpr int G = 32 / LPR;                 // rows of X in flight per shuffle step
-    static constexpr int UNR = (V >= 2) ? 4 : 8;       // independent row loads per lane
+    static_assert(D % (4 * T) == 0, "row must split into float4 per lane");
+    static constexpr int V = D / (4 * T);              // float4 per lane per row of X
+    static constexpr int GPW = 32 / T;                 // tasks per warp
+    static constexpr int UNR = (V >= 4) ? 2 : (V == 2 ? 4 : 8);   // rows of X in flight per lane group
 };
 
-template <int D>
-__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, int l, float4 (&y)[VecCfg<D>::V]) {
-    using C = VecCfg<D>;
-    // called by lanes [0, LPR) of the warp, all of which hold the finished row
+template <int D, int T>
+__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, int l, unsigned gmask,
+                                              float4 (&y)[VecCfg<D, T>::V], const float4 (&accin)[VecCfg<D, T>::V]) {
+    using C = VecCfg<D, T>;
+    // lane l of the group owns floats [ (v*T + l)*4, +4 ) of the row, v = 0..V-1: every v is one coalesced
+    // T*16-byte request per group
     if (p.gate_ref) {
         float dot = 0.f, ny = 0.f, nr = 0.f;
 #pragma unroll
         for (int v = 0; v < C::V; ++v) {
-            float4 r = ldg4(p.gate_ref + (int64_t)row * p.ldgate + v * 128 + l * 4);
+            float4 r = ldg4(p.gate_ref + (int64_t)row * p.ldgate + (v * T + l) * 4);
             dot += y[v].x * r.x + y[v].y * r.y + y[v].z * r.z + y[v].w * r.w;
             ny += y[v].x * y[v].x + y[v].y * y[v].y + y[v].z * y[v].z + y[v].w * y[v].w;
             nr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
         }
-        const unsigned m = C::LPR == 32 ? 0xffffffffu : ((1u << C::LPR) - 1u);
 #pragma unroll
-        for (int o = C::LPR / 2; o > 0; o >>= 1) {
-            dot += __shfl_xor_sync(m, dot, o);
-            ny += __shfl_xor_sync(m, ny, o);
-            nr += __shfl_xor_sync(m, nr, o);
+        for (int o = T / 2; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(gmask, dot, o);
+            ny += __shfl_xor_sync(gmask, ny, o);
+            nr += __shfl_xor_sync(gmask, nr, o);
         }
         // F.cosine_similarity(eps=1e-8): <x/max(|x|,eps), y/max(|y|,eps)>  (layergcn.py:132)
         float c = dot / (fmaxf(sqrtf(ny), 1e-8f) * fmaxf(sqrtf(nr), 1e-8f));
@@ -64,120 +70,124 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, int 
     if (p.Y) {
 #pragma unroll
         for (int v = 0; v < C::V; ++v)
-            *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + v * 128 + l * 4) = y[v];
+            *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + (v * T + l) * 4) = y[v];
     }
     if (p.acc_out) {
 #pragma unroll
         for (int v = 0; v < C::V; ++v) {
             float4 a = y[v];
-            if (p.acc_in) {
-                float4 b = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + v * 128 + l * 4);
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-            }
+            if (p.acc_in) { a.x += accin[v].x; a.y += accin[v].y; a.z += accin[v].z; a.w += accin[v].w; }
             if (p.acc_div != 1.0f) {
                 a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
                 a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
             }
-            *reinterpret_cast<float4*>(p.acc_out + (int64_t)row * p.ldacc + v * 128 + l * 4) = a;
+            *reinterpret_cast<float4*>(p.acc_out + (int64_t)row * p.ldacc + (v * T + l) * 4) = a;
         }
     }
 }
 
-template <int D>
+template <int D, int T>
 __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
-    using C = VecCfg<D>;
+    using C = VecCfg<D, T>;
     const int lane = threadIdx.x & 31;
-    const int g = lane / C::LPR, l = lane % C::LPR;
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int g = lane / T, l = lane % T;
+    const unsigned gmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (g * T));
+    const int64_t group0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * C::GPW + g;
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x >> 5) * C::GPW;
     const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
 
-    for (int64_t t = warp0; t < n_work; t += nwarps) {
-        int row, b, e, sid;
-        if (p.tasks) {
-            int4 tk = __ldg(p.tasks + t);
-            row = tk.x; b = tk.y; e = tk.z; sid = tk.w;
-        } else {
-            row = (int)t; b = __ldg(p.rowptr + t); e = __ldg(p.rowptr + t + 1); sid = -1;
+    // software pipeline across tasks: the descriptor of the NEXT task is in flight while this one gathers
+    int4 nxt = make_int4(-1, 0, 0, -1);
+    if (group0 < n_work) {
+        if (p.tasks) nxt = __ldg(p.tasks + group0);
+        else nxt = make_int4((int)group0, __ldg(p.rowptr + group0), __ldg(p.rowptr + group0 + 1), -1);
+    }
+    for (int64_t t = group0; t < n_work; t += ngroups) {
+        const int row = nxt.x, b = nxt.y, e = nxt.z, sid = nxt.w;
+        const int64_t tn = t + ngroups;
+        if (tn < n_work) {
+            if (p.tasks) nxt = __ldg(p.tasks + tn);
+            else nxt = make_int4((int)tn, __ldg(p.rowptr + tn), __ldg(p.rowptr + tn + 1), -1);
+        }
+        // the epilogue's read of the running sum does not depend on the gather: issue it now
+        float4 accin[C::V];
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) accin[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.acc_in && sid < 0) {
+#pragma unroll
+            for (int v = 0; v < C::V; ++v)
+                accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
         }
         float4 acc[C::V];
 #pragma unroll
         for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        for (int base = b; base < e; base += 32) {
-            const int n = min(32, e - base);
+        for (int base = b; base < e; base += T) {
+            const int n = min(T, e - base);
             int c = 0; float w = 0.f;
-            if (lane < n) { c = __ldg(p.colidx + base + lane); w = __ldg(p.vals + base + lane); }
-            const int iters = (n + C::G - 1) / C::G;
-            for (int j0 = 0; j0 < iters; j0 += C::UNR) {
-                float4 x[C::UNR][C::V];
-                float wj[C::UNR];
+            if (l < n) { c = __ldg(p.colidx + base + l); w = __ldg(p.vals + base + l); }
 #pragma unroll
-                for (int u = 0; u < C::UNR; ++u) {
-                    const int src = (j0 + u) * C::G + g;
-                    const int cj = __shfl_sync(0xffffffffu, c, src & 31);
-                    wj[u] = __shfl_sync(0xffffffffu, w, src & 31);
-                    const bool ok = src < n;
-                    if (!ok) wj[u] = 0.f;
+            for (int j0 = 0; j0 < T; j0 += C::UNR) {
+                if (j0 < n) {
+                    float4 x[C::UNR][C::V];
+                    float wj[C::UNR];
 #pragma unroll
-                    for (int v = 0; v < C::V; ++v)
-                        x[u][v] = ok ? ldg4(p.X + (int64_t)cj * p.ldx + v * 128 + l * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                    for (int u = 0; u < C::UNR; ++u) {
+                        const int src = j0 + u;
+                        const int cj = __shfl_sync(gmask, c, src, T);
+                        wj[u] = __shfl_sync(gmask, w, src, T);
+                        const bool ok = src < n;
+                        if (!ok) wj[u] = 0.f;
 #pragma unroll
-                for (int u = 0; u < C::UNR; ++u) {
+                        for (int v = 0; v < C::V; ++v)
+                            x[u][v] = ok ? ldg4(p.X + (int64_t)cj * p.ldx + (v * T + l) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
-                    for (int v = 0; v < C::V; ++v) {
-                        acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x);
-                        acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);
-                        acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z);
-                        acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);
+                    for (int u = 0; u < C::UNR; ++u) {
+#pragma unroll
+                        for (int v = 0; v < C::V; ++v) {
+                            acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x);
+                            acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);
+                            acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z);
+                            acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);
+                        }
                     }
                 }
             }
         }
-        // combine the G lane groups (fixed order)
-#pragma unroll
-        for (int o = 16; o >= C::LPR; o >>= 1) {
-#pragma unroll
-            for (int v = 0; v < C::V; ++v) {
-                acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
-                acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
-                acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
-                acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
-            }
-        }
         if (sid < 0) {
-            if (g == 0) spmm_epilogue<D>(p, row, l, acc);
+            spmm_epilogue<D, T>(p, row, l, gmask, acc, accin);
         } else {
             const int4 sr = __ldg(p.split_rows + sid);   // {first_slot, n_seg, row_begin, seg_len}
             const int seg = (b - sr.z) / sr.w;
             float* slot = p.partial + ((int64_t)sr.x + seg) * D;
-            if (g == 0) {
 #pragma unroll
-                for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(slot + v * 128 + l * 4) = acc[v];
-            }
+            for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(slot + (v * T + l) * 4) = acc[v];
             __threadfence();
-            __syncwarp();
+            __syncwarp(gmask);
             int old = 0;
-            if (lane == 0) old = atomicAdd(p.counters + sid, 1);
-            old = __shfl_sync(0xffffffffu, old, 0);
+            if (l == 0) old = atomicAdd(p.counters + sid, 1);
+            old = __shfl_sync(gmask, old, 0, T);
             if (old == sr.y - 1) {            // last segment to arrive: reduce in segment order
                 __threadfence();
-                if (g == 0) {
-                    float4 tot[C::V];
+                float4 tot[C::V];
 #pragma unroll
-                    for (int v = 0; v < C::V; ++v) tot[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int s = 0; s < sr.y; ++s) {
-                        const float* ps = p.partial + ((int64_t)sr.x + s) * D;
+                for (int v = 0; v < C::V; ++v) tot[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s2 = 0; s2 < sr.y; ++s2) {
+                    const float* ps = p.partial + ((int64_t)sr.x + s2) * D;
 #pragma unroll
-                        for (int v = 0; v < C::V; ++v) {
-                            float4 q = __ldcg(reinterpret_cast<const float4*>(ps + v * 128 + l * 4));
-                            tot[v].x += q.x; tot[v].y += q.y; tot[v].z += q.z; tot[v].w += q.w;
-                        }
+                    for (int v = 0; v < C::V; ++v) {
+                        float4 q = __ldcg(reinterpret_cast<const float4*>(ps + (v * T + l) * 4));
+                        tot[v].x += q.x; tot[v].y += q.y; tot[v].z += q.z; tot[v].w += q.w;
                     }
-                    spmm_epilogue<D>(p, row, l, tot);
                 }
-                if (lane == 0) p.counters[sid] = 0;   // self-cleaning for the next launch
+                if (p.acc_in) {
+#pragma unroll
+                    for (int v = 0; v < C::V; ++v)
+                        accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
+                }
+                spmm_epilogue<D, T>(p, row, l, gmask, tot, accin);
+                if (l == 0) p.counters[sid] = 0;   // self-cleaning for the next launch
             }
         }
     }
@@ -219,26 +229,47 @@ __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmParams p) {
     }
 }
 
-template <int D>
+int g_spmm_lanes = 0;   // 0 = default lanes per task for the width; set by mmrec_spmm_set_lanes (tuning knob)
+
+template <int D, int T>
 static int launch_vec(const SpmmParams& p, cudaStream_t stream) {
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-        MMREC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, spmm_vec_kernel<D>, 256, 0));
+        MMREC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, spmm_vec_kernel<D, T>, 256, 0));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
-    int64_t grid = (n_work + 7) / 8;
+    const int per_block = 8 * (32 / T);
+    int64_t grid = (n_work + per_block - 1) / per_block;
     const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) return MMREC_OK;
-    spmm_vec_kernel<D><<<(unsigned)grid, 256, 0, stream>>>(p);
+    spmm_vec_kernel<D, T><<<(unsigned)grid, 256, 0, stream>>>(p);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
+}
+
+template <int D>
+static int launch_vec_d(const SpmmParams& p, cudaStream_t stream) {
+    constexpr int T4 = D / 4 > 32 ? 32 : D / 4;      // 1 float4 per lane
+    constexpr int T8 = D / 8 > 32 ? 32 : D / 8;      // 2 float4 per lane
+    constexpr int T16 = D / 16 > 32 ? 32 : D / 16;   // 4 float4 per lane
+    int T = g_spmm_lanes ? g_spmm_lanes : T8;
+    if (T == T4) return launch_vec<D, T4>(p, stream);
+    if (T == T16) return launch_vec<D, T16>(p, stream);
+    return launch_vec<D, T8>(p, stream);
 }
 
 }  // namespace mmrec
 
 using namespace mmrec;
+
+extern "C" int mmrec_spmm_set_lanes(int lanes_per_row) {
+    MMREC_CHECK_ARG(lanes_per_row == 0 || lanes_per_row == 2 || lanes_per_row == 4 || lanes_per_row == 8 ||
+                    lanes_per_row == 16 || lanes_per_row == 32, "spmm_set_lanes: 0 (default) or a power of two <= 32");
+    g_spmm_lanes = lanes_per_row;
+    return MMREC_OK;
+}
 
 extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32_t* rowptr, const int32_t* colidx,
                               const float* vals, const int32_t* tasks, int64_t n_tasks, const int32_t* split_rows,
@@ -263,10 +294,10 @@ extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32
                         al16(gate_ref, ldgate) && al16(partial, 4);
     if (vec_ok) {
         switch (d) {
-            case 32: return launch_vec<32>(p, stream);
-            case 64: return launch_vec<64>(p, stream);
-            case 128: return launch_vec<128>(p, stream);
-            case 256: return launch_vec<256>(p, stream);
+            case 32: return launch_vec_d<32>(p, stream);
+            case 64: return launch_vec_d<64>(p, stream);
+            case 128: return launch_vec_d<128>(p, stream);
+            case 256: return launch_vec_d<256>(p, stream);
             default: break;
         }
     }

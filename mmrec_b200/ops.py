@@ -111,10 +111,10 @@ class CSR:
         tasks = torch.empty(4 * max_tasks, dtype=torch.int32, device=dev)
         split = torch.empty(4 * max_split, dtype=torch.int32, device=dev)
         counts = torch.zeros(4, dtype=torch.int64, device=dev)
-        ws = _ws("plan", lib.mmrec_spmm_plan_workspace_bytes(self.n_rows), dev)
-        check(lib.mmrec_spmm_plan(self.n_rows, _ptr(self.rowptr), self.seg, _ptr(tasks), _ptr(split), _ptr(counts),
-                                  _ptr(ws), ws.numel(), _stream()), "mmrec_spmm_plan")
-        _count(5)
+        ws = _ws("plan", lib.mmrec_spmm_plan_workspace_bytes(self.n_rows, max_tasks), dev)
+        check(lib.mmrec_spmm_plan(self.n_rows, _ptr(self.rowptr), self.seg, max_tasks, _ptr(tasks), _ptr(split),
+                                  _ptr(counts), _ptr(ws), ws.numel(), _stream()), "mmrec_spmm_plan")
+        _count(8)
         c = counts.tolist()
         self.n_tasks, self.n_split, self.n_slots, self.longest_row = int(c[0]), int(c[1]), int(c[2]), int(c[3])
         self.tasks = tasks[:4 * max(self.n_tasks, 1)]
@@ -334,9 +334,10 @@ def score(user_e, item_e, users=None) -> torch.Tensor:
     B = user_e.shape[0] if users is None else users.numel()
     n_items, d = item_e.shape
     out = torch.empty(B, n_items, dtype=torch.float32, device=item_e.device)
+    ws = _ws("score", lib.mmrec_score_workspace_bytes(B, n_items, d), item_e.device)
     check(lib.mmrec_score_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e), item_e.stride(0), d,
-                              _ptr(out), n_items, _stream()), "mmrec_score_f32")
-    _count()
+                              _ptr(out), n_items, _ptr(ws), ws.numel(), _stream()), "mmrec_score_f32")
+    _count(3)
     return out
 
 

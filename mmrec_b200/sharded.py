@@ -1,0 +1,186 @@
+"""Item-sharded hot path over N GPUs (one process per GPU, torch.distributed / NCCL over NVLink) -- SURVEY.md 8(e).
+
+The reference has no multi-GPU code at all (`src/utils/configurator.py:114-118` picks one device); the
+partitioning follows BASELINE.json's north star: shard the ITEM axis.
+
+  * rank g owns the items {i : i mod N == g} (round-robin, so the Zipf head does not land on one rank), relabelled
+    to a contiguous local range; it holds their embeddings, and the column block R_g = R[:, I_g] of the
+    interaction matrix as two CSRs (users x local items, and its transpose) with the GLOBAL degree normalisation
+    of `get_norm_adj_mat` (`src/models/freedom.py:102-126`);
+  * one UI layer:  items   E'_Ig = R_g^T E_U              -- local SpMM, needs the full user table
+                   users   E'_U  = sum_g R_g E_Ig         -- local SpMM, then ONE all-reduce of the [U, d] partial
+    (= the reduce-scatter + all-gather of user embeddings the north star names);
+  * eval: every rank scores all users against its item shard with the fused score+mask+top-k kernel, the
+    [B, k] (value, global index) lists are all-gathered and merged by `mmrec_topk_merge` (per-user top-k
+    all-reduce).
+
+`spmm` / `score_topk` / `merge` are injectable so that the orchestration + collectives can be exercised on CPU
+under gloo (tests/test_sharded_gloo.py); the defaults are this library's CUDA kernels.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class ItemShard:
+    """Host-side partition of the bipartite training graph for one rank (numpy only)."""
+
+    def __init__(self, inter_row, inter_col, n_users, n_items, rank, world):
+        r = np.asarray(inter_row, dtype=np.int64)
+        c = np.asarray(inter_col, dtype=np.int64)
+        key = np.unique(r * n_items + c)
+        r, c = key // n_items, key % n_items
+        self.rank, self.world, self.n_users, self.n_items = rank, world, n_users, n_items
+        self.local_items = np.arange(rank, n_items, world, dtype=np.int64)     # global ids of my items, ascending
+        self.n_local = len(self.local_items)
+        # global degrees + 1e-7, float64, exactly as the single-GPU builder (freedom.py:113-116)
+        du = np.bincount(r, minlength=n_users).astype(np.float64) + 1e-7
+        di = np.bincount(c, minlength=n_items).astype(np.float64) + 1e-7
+        mine = (c % world) == rank
+        self.u = r[mine]
+        self.i_local = c[mine] // world
+        self.val = ((np.power(du[self.u], -0.5) * 1.0) * np.power(di[c[mine]], -0.5)).astype(np.float32)
+        self.nnz = int(mine.sum())
+
+    def to_global(self, local_idx):
+        return local_idx * self.world + self.rank
+
+    def csrs(self, device):
+        """(users x local items, local items x users) as device CSRs."""
+        from .ops import CSR
+        u = torch.from_numpy(self.u).to(device)
+        i = torch.from_numpy(self.i_local).to(device)
+        v = torch.from_numpy(self.val).to(device)
+        a_ui = CSR.from_coo(u, i, v, self.n_users, self.n_local, sum_duplicates=False)
+        a_iu = CSR.from_coo(i, u, v, self.n_local, self.n_users, sum_duplicates=False)
+        return a_ui, a_iu
+
+
+def _cuda_spmm(A, X, acc_in=None, acc_div=1.0, want_y=True):
+    from . import ops
+    Y = torch.empty(A.n_rows, X.shape[1], dtype=torch.float32, device=X.device) if want_y else None
+    acc = None
+    if acc_in is not None:
+        acc = acc_in
+        ops.spmm_raw(A, X, Y=Y, acc_in=acc_in, acc_out=acc, acc_div=acc_div)
+    else:
+        ops.spmm_raw(A, X, Y=Y)
+    return Y, acc
+
+
+def propagate_mean_sharded(a_ui, a_iu, user_emb, item_emb_local, n_layers, spmm=_cuda_spmm, group=None):
+    """mean over layers 0..L of the LightGCN propagation, item-sharded.  Returns (users [U,d] replicated,
+    items [I_local,d]).  Per layer: 2 local SpMMs + one all-reduce of the user partial."""
+    eu, ei = user_emb, item_emb_local
+    acc_u = user_emb.clone()
+    acc_i = item_emb_local.clone()
+    for l in range(1, n_layers + 1):
+        last = l == n_layers
+        div = float(n_layers + 1) if last else 1.0
+        part_u, _ = spmm(a_ui, ei)                                   # R_g E_Ig : partial user sums
+        work = dist.all_reduce(part_u, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        ei_next, acc_i = spmm(a_iu, eu, acc_in=acc_i, acc_div=div, want_y=not last)    # overlaps the all-reduce
+        work.wait()
+        acc_u = acc_u + part_u
+        if last:
+            acc_u = acc_u / div
+        eu, ei = part_u, ei_next
+    return acc_u, acc_i
+
+
+def score_topk_sharded(shard: ItemShard, user_e, item_e_local, users, mask, k, score_topk=None, merge=None, group=None):
+    """Global top-k over all shards.  `mask` holds GLOBAL item ids ([2, nnz]: batch row, item)."""
+    from . import ops
+    score_topk = score_topk or ops.score_topk
+    merge = merge or ops.topk_merge
+    world = shard.world
+    lm = None
+    if mask is not None and mask.numel() > 0:
+        sel = (mask[1] % world) == shard.rank
+        lm = torch.stack([mask[0][sel], mask[1][sel] // world])
+    val, idx = score_topk(user_e, item_e_local, users, lm, k)
+    idx = idx * world + shard.rank                                   # back to global item ids
+    vals = [torch.empty_like(val) for _ in range(world)]
+    idxs = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(vals, val, group=group)
+    dist.all_gather(idxs, idx, group=group)
+    return merge(torch.stack(vals), torch.stack(idxs))
+
+
+# ------------------------------------------------------------------------------------------------------
+# bench driver for N > 1 (weak scaling: every rank keeps 7,000 items and ~160k edges as N grows)
+# ------------------------------------------------------------------------------------------------------
+def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
+    from . import ops
+    TOPK, EVAL_BATCH = 50, 4096
+    wl = Workload(args.workload, n_layers=3, items_scale=world)
+    U, I, d = wl.U, wl.I, wl.d
+    shard = ItemShard(wl.tr_u, wl.tr_i, U, I, rank, world)
+    a_ui, a_iu = shard.csrs(dev)
+    ue = torch.from_numpy(wl.user_emb).to(dev)
+    ie = torch.from_numpy(wl.item_emb[shard.local_items]).to(dev)
+    batches = []
+    for lo in range(0, U, EVAL_BATCH):
+        hi = min(U, lo + EVAL_BATCH)
+        batches.append((torch.arange(lo, hi, device=dev), torch.from_numpy(wl.eval_mask(lo, hi)).to(dev)))
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    edges_local = wl.n_layers * 2 * shard.nnz
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    tA = tC = 0.0
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    launches0 = 0
+    with torch.no_grad():
+        for step in range(args.warmup + args.steps):
+            if step == args.warmup:
+                torch.cuda.synchronize(); dist.barrier()
+                if rank == 0:
+                    sampler.start()
+                launches0 = ops.LAUNCHES
+            flush.zero_()
+            dist.barrier()
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            u_g, i_g = propagate_mean_sharded(a_ui, a_iu, ue, ie, wl.n_layers)
+            e[1].record()
+            e[2].record()
+            outs = [score_topk_sharded(shard, u_g, i_g, users, mask, TOPK) for users, mask in batches]
+            e[3].record()
+            torch.cuda.synchronize()
+            if step >= args.warmup:
+                tA += e[0].elapsed_time(e[1]); tC += e[2].elapsed_time(e[3])
+    dist.barrier()
+    t = torch.tensor([tA, tC], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                         # max over ranks, device-timed
+    e_all = torch.tensor([float(edges_local)], device=dev, dtype=torch.float64)
+    dist.all_reduce(e_all, op=dist.ReduceOp.SUM)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        K = args.steps
+        msA, msC = t[0].item() / K, t[1].item() / K
+        edges = e_all.item()
+        pk = peaks()
+        algo_bytes = wl.n_layers * (a_ui.algorithmic_bytes(d) + a_iu.algorithmic_bytes(d)) * world
+        print(json.dumps({
+            "metric": "graph-prop edges/sec (+ full-catalog scored-items/sec in extra) @ d=64",
+            "value": edges / (msA * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": msA + msC, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"FREEDOM synthetic {wl.name} x{world} items: {U} users, {I} items ({I // world} per GPU), "
+                                   f"{len(wl.tr_u)} train edges, d={d}, {wl.n_layers} UI layers, top-{TOPK} over all users",
+                       "l2": "flushed (512 MiB write) before every step",
+                       "parallelism": f"item-sharded x{world}: all-reduce of user embeddings per layer, top-k all-gather + merge"},
+            "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U * I / (msC * 1e-3)},
+            "roofline": {"kernel": "spmm_vec_kernel<64> (per rank: 2 per layer)", "bound": "hbm",
+                         "achieved": algo_bytes / (msA * 1e-3) / 1e9 / world, "peak": pk["hbm_gbs"], "unit": "GB/s per GPU",
+                         "frac": algo_bytes / (msA * 1e-3) / 1e9 / world / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
+                         "note": "includes the per-layer NCCL all-reduce of the [U,d] user partials"},
+            "gpu_launches": int(ops.LAUNCHES - launches0), "clocks": clocks,
+            "e2e": None,
+        }))
+    dist.destroy_process_group()

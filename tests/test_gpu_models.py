@@ -121,8 +121,12 @@ def test_model_matches_reference(env, golden, name, file, over):
     np.testing.assert_allclose(loss.detach().cpu().numpy().reshape(-1), ref_val, rtol=2e-5)
     named = dict(model.named_parameters())
     assert ref_grads
+    gmax = max(float(np.abs(g).max()) for g in ref_grads.values())
     for k, gref in ref_grads.items():
-        assert rel(named[k].grad, gref) < 1e-4, f"grad {k}"
+        # gradients that are pure cancellation noise (softmax-invariant biases, ~1e-11) carry no signal:
+        # measure the error against the scale of the whole gradient, not of the vanishing entry
+        err = (named[k].grad.detach().cpu().double() - torch.from_numpy(gref).double()).norm().item()
+        assert err < 1e-4 * max(float(np.linalg.norm(gref)), 1e-6 * gmax), f"grad {k}"
     # (4) full_sort_predict + trainer mask/top-k on the reference's first eval batch
     model.eval()
     with torch.no_grad():
