@@ -42,31 +42,34 @@ struct VecCfg {
 };
 
 template <int D, int T>
-__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, int l, unsigned gmask,
-                                              float4 (&y)[VecCfg<D, T>::V], const float4 (&accin)[VecCfg<D, T>::V]) {
+__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, bool on, int row, int l, float4 (&y)[VecCfg<D, T>::V],
+                                              const float4 (&accin)[VecCfg<D, T>::V]) {
     using C = VecCfg<D, T>;
-    // lane l of the group owns floats [ (v*T + l)*4, +4 ) of the row, v = 0..V-1: every v is one coalesced
-    // T*16-byte request per group
+    // Called by ALL 32 lanes (warp-uniform control flow); `on` predicates the memory traffic of this lane group.
+    // Lane l of the group owns floats [(v*T + l)*4, +4) of the row: each v is one coalesced T*16-byte request.
     if (p.gate_ref) {
         float dot = 0.f, ny = 0.f, nr = 0.f;
+        if (on) {
 #pragma unroll
-        for (int v = 0; v < C::V; ++v) {
-            float4 r = ldg4(p.gate_ref + (int64_t)row * p.ldgate + (v * T + l) * 4);
-            dot += y[v].x * r.x + y[v].y * r.y + y[v].z * r.z + y[v].w * r.w;
-            ny += y[v].x * y[v].x + y[v].y * y[v].y + y[v].z * y[v].z + y[v].w * y[v].w;
-            nr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+            for (int v = 0; v < C::V; ++v) {
+                float4 r = ldg4(p.gate_ref + (int64_t)row * p.ldgate + (v * T + l) * 4);
+                dot += y[v].x * r.x + y[v].y * r.y + y[v].z * r.z + y[v].w * r.w;
+                ny += y[v].x * y[v].x + y[v].y * y[v].y + y[v].z * y[v].z + y[v].w * y[v].w;
+                nr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+            }
         }
 #pragma unroll
-        for (int o = T / 2; o > 0; o >>= 1) {
-            dot += __shfl_xor_sync(gmask, dot, o);
-            ny += __shfl_xor_sync(gmask, ny, o);
-            nr += __shfl_xor_sync(gmask, nr, o);
+        for (int o = T / 2; o > 0; o >>= 1) {       // xor distances < T stay inside the lane group
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            ny += __shfl_xor_sync(0xffffffffu, ny, o);
+            nr += __shfl_xor_sync(0xffffffffu, nr, o);
         }
         // F.cosine_similarity(eps=1e-8): <x/max(|x|,eps), y/max(|y|,eps)>  (layergcn.py:132)
         float c = dot / (fmaxf(sqrtf(ny), 1e-8f) * fmaxf(sqrtf(nr), 1e-8f));
 #pragma unroll
         for (int v = 0; v < C::V; ++v) { y[v].x *= c; y[v].y *= c; y[v].z *= c; y[v].w *= c; }
     }
+    if (!on) return;
     if (p.Y) {
 #pragma unroll
         for (int v = 0; v < C::V; ++v)
@@ -86,34 +89,35 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, int 
     }
 }
 
+// Control flow is warp-uniform throughout: the 32/T lane groups of a warp run their tasks in lock step (trip
+// count = longest task of the warp; the plan sorts tasks by length, so neighbours are alike) and everything
+// per-group is predicated.  No shuffles in the gather loop: every lane loads the (column, value) pair it
+// needs -- the T lanes of a group read the same address, which is one broadcast transaction.
 template <int D, int T>
 __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
     using C = VecCfg<D, T>;
     const int lane = threadIdx.x & 31;
     const int g = lane / T, l = lane % T;
-    const unsigned gmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (g * T));
-    const int64_t group0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * C::GPW + g;
-    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x >> 5) * C::GPW;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
 
-    // software pipeline across tasks: the descriptor of the NEXT task is in flight while this one gathers
-    int4 nxt = make_int4(-1, 0, 0, -1);
-    if (group0 < n_work) {
-        if (p.tasks) nxt = __ldg(p.tasks + group0);
-        else nxt = make_int4((int)group0, __ldg(p.rowptr + group0), __ldg(p.rowptr + group0 + 1), -1);
-    }
-    for (int64_t t = group0; t < n_work; t += ngroups) {
-        const int row = nxt.x, b = nxt.y, e = nxt.z, sid = nxt.w;
-        const int64_t tn = t + ngroups;
-        if (tn < n_work) {
-            if (p.tasks) nxt = __ldg(p.tasks + tn);
-            else nxt = make_int4((int)tn, __ldg(p.rowptr + tn), __ldg(p.rowptr + tn + 1), -1);
-        }
-        // the epilogue's read of the running sum does not depend on the gather: issue it now
+    auto fetch = [&](int64_t t) -> int4 {
+        if (t >= n_work) return make_int4(-1, 0, 0, -1);
+        if (p.tasks) return __ldg(p.tasks + t);
+        return make_int4((int)t, __ldg(p.rowptr + t), __ldg(p.rowptr + t + 1), -1);
+    };
+    int4 nxt = fetch(warp0 * C::GPW + g);
+    for (int64_t tw = warp0 * C::GPW; tw < n_work; tw += nwarps * C::GPW) {
+        const int row = nxt.x, b = nxt.y, sid = nxt.w;
+        const int len = nxt.z - nxt.y;
+        const bool valid = row >= 0;
+        nxt = fetch(tw + nwarps * C::GPW + g);                      // next task's descriptor: in flight during the gather
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
         float4 accin[C::V];
 #pragma unroll
         for (int v = 0; v < C::V; ++v) accin[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.acc_in && sid < 0) {
+        if (valid && p.acc_in && sid < 0) {                         // epilogue operand does not depend on the gather
 #pragma unroll
             for (int v = 0; v < C::V; ++v)
                 accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
@@ -122,63 +126,69 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
 #pragma unroll
         for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        for (int base = b; base < e; base += T) {
-            const int n = min(T, e - base);
-            int c = 0; float w = 0.f;
-            if (l < n) { c = __ldg(p.colidx + base + l); w = __ldg(p.vals + base + l); }
+        int cj[C::UNR]; float wj[C::UNR];
 #pragma unroll
-            for (int j0 = 0; j0 < T; j0 += C::UNR) {
-                if (j0 < n) {
-                    float4 x[C::UNR][C::V];
-                    float wj[C::UNR];
+        for (int u = 0; u < C::UNR; ++u) {
+            const bool ok = u < len;
+            cj[u] = ok ? __ldg(p.colidx + b + u) : 0;
+            wj[u] = ok ? __ldg(p.vals + b + u) : 0.f;
+        }
+        for (int j0 = 0; j0 < maxlen; j0 += C::UNR) {
+            float4 x[C::UNR][C::V];
 #pragma unroll
-                    for (int u = 0; u < C::UNR; ++u) {
-                        const int src = j0 + u;
-                        const int cj = __shfl_sync(gmask, c, src, T);
-                        wj[u] = __shfl_sync(gmask, w, src, T);
-                        const bool ok = src < n;
-                        if (!ok) wj[u] = 0.f;
+            for (int u = 0; u < C::UNR; ++u) {
+                const bool ok = j0 + u < len;
 #pragma unroll
-                        for (int v = 0; v < C::V; ++v)
-                            x[u][v] = ok ? ldg4(p.X + (int64_t)cj * p.ldx + (v * T + l) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                for (int v = 0; v < C::V; ++v)
+                    x[u][v] = ok ? ldg4(p.X + (int64_t)cj[u] * p.ldx + (v * T + l) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float wc[C::UNR];
 #pragma unroll
-                    for (int u = 0; u < C::UNR; ++u) {
+            for (int u = 0; u < C::UNR; ++u) wc[u] = wj[u];
+            // indices of the next batch travel while this batch's rows of X are in flight
 #pragma unroll
-                        for (int v = 0; v < C::V; ++v) {
-                            acc[v].x = fmaf(wj[u], x[u][v].x, acc[v].x);
-                            acc[v].y = fmaf(wj[u], x[u][v].y, acc[v].y);
-                            acc[v].z = fmaf(wj[u], x[u][v].z, acc[v].z);
-                            acc[v].w = fmaf(wj[u], x[u][v].w, acc[v].w);
-                        }
-                    }
+            for (int u = 0; u < C::UNR; ++u) {
+                const bool ok = j0 + C::UNR + u < len;
+                cj[u] = ok ? __ldg(p.colidx + b + j0 + C::UNR + u) : 0;
+                wj[u] = ok ? __ldg(p.vals + b + j0 + C::UNR + u) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < C::UNR; ++u) {
+#pragma unroll
+                for (int v = 0; v < C::V; ++v) {
+                    acc[v].x = fmaf(wc[u], x[u][v].x, acc[v].x);
+                    acc[v].y = fmaf(wc[u], x[u][v].y, acc[v].y);
+                    acc[v].z = fmaf(wc[u], x[u][v].z, acc[v].z);
+                    acc[v].w = fmaf(wc[u], x[u][v].w, acc[v].w);
                 }
             }
         }
-        if (sid < 0) {
-            spmm_epilogue<D, T>(p, row, l, gmask, acc, accin);
-        } else {
-            const int4 sr = __ldg(p.split_rows + sid);   // {first_slot, n_seg, row_begin, seg_len}
-            const int seg = (b - sr.z) / sr.w;
-            float* slot = p.partial + ((int64_t)sr.x + seg) * D;
+        bool do_epi = valid && sid < 0;
+        const bool split = valid && sid >= 0;
+        if (__any_sync(0xffffffffu, split)) {
+            int4 sr = make_int4(0, 1, 0, 1);
+            int old = -1;
+            if (split) {
+                sr = __ldg(p.split_rows + sid);                     // {first_slot, n_seg, row_begin, seg_len}
+                const int seg = (b - sr.z) / sr.w;
+                float* slot = p.partial + ((int64_t)sr.x + seg) * D;
 #pragma unroll
-            for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(slot + (v * T + l) * 4) = acc[v];
-            __threadfence();
-            __syncwarp(gmask);
-            int old = 0;
-            if (l == 0) old = atomicAdd(p.counters + sid, 1);
-            old = __shfl_sync(gmask, old, 0, T);
-            if (old == sr.y - 1) {            // last segment to arrive: reduce in segment order
+                for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(slot + (v * T + l) * 4) = acc[v];
                 __threadfence();
-                float4 tot[C::V];
+            }
+            __syncwarp();
+            if (split && l == 0) old = atomicAdd(p.counters + sid, 1);
+            old = __shfl_sync(0xffffffffu, old, 0, T);
+            if (split && old == sr.y - 1) {                         // last segment to arrive: reduce in segment order
+                __threadfence();
 #pragma unroll
-                for (int v = 0; v < C::V; ++v) tot[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int s2 = 0; s2 < sr.y; ++s2) {
                     const float* ps = p.partial + ((int64_t)sr.x + s2) * D;
 #pragma unroll
                     for (int v = 0; v < C::V; ++v) {
                         float4 q = __ldcg(reinterpret_cast<const float4*>(ps + (v * T + l) * 4));
-                        tot[v].x += q.x; tot[v].y += q.y; tot[v].z += q.z; tot[v].w += q.w;
+                        acc[v].x += q.x; acc[v].y += q.y; acc[v].z += q.z; acc[v].w += q.w;
                     }
                 }
                 if (p.acc_in) {
@@ -186,10 +196,12 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
                     for (int v = 0; v < C::V; ++v)
                         accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
                 }
-                spmm_epilogue<D, T>(p, row, l, gmask, tot, accin);
-                if (l == 0) p.counters[sid] = 0;   // self-cleaning for the next launch
+                if (l == 0) p.counters[sid] = 0;                    // self-cleaning for the next launch
+                do_epi = true;
             }
+            __syncwarp();
         }
+        spmm_epilogue<D, T>(p, do_epi, row, l, acc, accin);
     }
 }
 

@@ -15,7 +15,8 @@ from . import _lib
 from ._lib import MMRecError, check
 
 _ws_cache: dict = {}
-SEG = 128          # non-zeros per SpMM task (rows longer than this are split)
+import os as _os
+SEG = int(_os.environ.get("MMREC_SPMM_SEG", "64"))   # non-zeros per SpMM task (rows longer than this are split)
 LAUNCHES = 0       # kernels of this library launched so far (bench.py's gpu_launches)
 
 
