@@ -135,9 +135,10 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
  * mmrec_topk_merge:   merge `parts` sorted lists per user ([parts, B, k] values + indices) into
  *                     one (the per-user top-k reduction across item shards).
  * ------------------------------------------------------------------------------------------- */
-/* arithmetic path of mmrec_score_f32 / mmrec_score_topk_f32: 1 = tcgen05 3xTF32 where the shape fits
- * (default; env MMREC_SCORE_PATH=simt|tc sets the initial value), 0 = exact fp32 on CUDA cores. */
-int mmrec_score_set_path(int tensor_core);
+/* arithmetic path of mmrec_score_f32 / mmrec_score_topk_f32: 2 = tcgen05 3xTF32 with the top-k fused into the
+ * GEMM epilogue (default), 1 = tcgen05 3xTF32 + separate mask/top-k kernels, 0 = exact fp32 on CUDA cores.
+ * env MMREC_SCORE_PATH = simt | tc | fused sets the initial value. */
+int mmrec_score_set_path(int path);
 size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d);
 int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu,
                     int64_t n_items, const float* Ie, int64_t ldi, int d,

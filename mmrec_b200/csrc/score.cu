@@ -18,15 +18,20 @@ namespace mmrec {
 int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie,
              int64_t ldi, int d, float* S, int64_t ldS, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t score_tc_workspace_bytes(int64_t B, int64_t n_items, int d);
+// score_fused.cu: 1 handled, 0 unsupported
+int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie, int64_t ldi,
+                int d, int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int k, int64_t item_offset,
+                int64_t* out_idx, float* out_val, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t score_fused_workspace_bytes(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz);
 
 int mask_apply(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int64_t row0, int64_t B,
                int64_t n_items, int64_t item_offset, float* S, int64_t ldS, cudaStream_t stream);
 
-static int g_score_path = -1;   // -1 unset, 0 simt, 1 tc
+static int g_score_path = -1;   // -1 unset, 0 simt, 1 tensor cores (unfused top-k), 2 tensor cores + fused top-k
 static int score_path() {
     if (g_score_path < 0) {
         const char* e = getenv("MMREC_SCORE_PATH");
-        g_score_path = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+        g_score_path = (e && strcmp(e, "simt") == 0) ? 0 : ((e && strcmp(e, "tc") == 0) ? 1 : 2);
     }
     return g_score_path;
 }
@@ -34,7 +39,7 @@ static int score_path() {
 
 using namespace mmrec;
 
-extern "C" int mmrec_score_set_path(int tc) { g_score_path = tc ? 1 : 0; return MMREC_OK; }
+extern "C" int mmrec_score_set_path(int path) { g_score_path = path < 0 ? 0 : (path > 2 ? 2 : path); return MMREC_OK; }
 
 extern "C" size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d) {
     return score_tc_workspace_bytes(B, n_items, d) + 256;
@@ -47,7 +52,7 @@ extern "C" int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue,
     MMREC_CHECK_ARG(B >= 0 && n_items >= 0 && d >= 1, "score: bad sizes");
     if (B == 0 || n_items == 0) return MMREC_OK;
     MMREC_CHECK_ARG(Ue && Ie && S && ldu >= d && ldi >= d && ldS >= n_items, "score: null pointer or bad leading dimension");
-    if (score_path() == 1) {
+    if (score_path() >= 1) {
         int r = score_tc(B, users, Ue, ldu, n_items, Ie, ldi, d, S, ldS, ws, ws_bytes, stream);
         if (r != 0) return r < 0 ? r : MMREC_OK;
     }
@@ -69,8 +74,10 @@ extern "C" size_t mmrec_score_topk_workspace_bytes(int64_t B, int64_t n_items, i
     (void)d; (void)k;
     if (B <= 0 || n_items <= 0) return 256;
     const int64_t rows = score_block_rows(B, n_items);
-    return align_up((size_t)rows * (size_t)((n_items + 3) / 4 * 4) * sizeof(float) + 256, 1024) +
-           mmrec_score_workspace_bytes(rows, n_items, d);
+    const size_t unfused = align_up((size_t)rows * (size_t)((n_items + 3) / 4 * 4) * sizeof(float) + 256, 1024) +
+                           mmrec_score_workspace_bytes(rows, n_items, d);
+    const size_t fused = score_fused_workspace_bytes(B, n_items, d, k, B * 64 + 4096);   // mask_nnz is not known here
+    return unfused > fused ? unfused : fused;
 }
 
 extern "C" int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items,
@@ -83,6 +90,11 @@ extern "C" int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float
     if (!ws || ws_bytes < need) {
         set_error("score_topk: workspace %zu < %zu", ws_bytes, need);
         return MMREC_EWORKSPACE;
+    }
+    if (score_path() == 2 && score_fused_workspace_bytes(B, n_items, d, k, mask_nnz) <= ws_bytes) {
+        int r = score_fused(B, users, Ue, ldu, n_items, Ie, ldi, d, mask_nnz, mask_rows, mask_cols, k, item_offset, out_idx,
+                            out_val, ws, ws_bytes, (cudaStream_t)stream_);
+        if (r != 0) return r < 0 ? r : MMREC_OK;
     }
     float* S = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
     const int64_t ldS = (n_items + 3) / 4 * 4;

@@ -1,0 +1,541 @@
+// K3 fused: scores on tcgen05 (3xTF32, same pipeline as score_tc.cu) whose epilogue never writes the score matrix.
+//
+// Each epilogue thread owns one user row of the 128 x 256 accumulator tile and streams the items of its CTA's
+// item range through a threshold filter:
+//   * tile 0: thr0 = min over the eight 32-column groups of the group maximum (>= 8 items are above it); it seeds a
+//     32-bin linear histogram [thr0, thr0 + 2 (max0 - thr0)) of the values that pass;
+//   * every value >= thr is appended as a (value, item) pair to the row's candidate list in global memory and
+//     counted in the histogram; after each tile the threshold rises to the highest bin edge that still has
+//     `need` = k + (masked items of the row) candidates above it.  Masked train positives are NOT removed here:
+//     asking for k + m candidates guarantees k unmasked ones survive, so the mask is applied once, on the ~100
+//     finalists, instead of on 7,000 scores;
+//   * select kernel: per row, the finalists (value >= final threshold) of all item splits are gathered, masked
+//     items dropped, and a bitonic sort on (value desc, item asc) emits the top-k -- the contract of topk.cu.
+// Anything the filter cannot certify (candidate overflow, a degenerate histogram, NaNs) raises a per-row flag and
+// the row is recomputed by the exact fp32 kernel at the end of this file; no host round trip.
+#include <cub/device/device_scan.cuh>
+
+#include "tc_common.cuh"
+
+namespace mmrec {
+
+using namespace tc;
+
+constexpr int FZ_NB = 32;               // histogram bins per row
+constexpr int FZ_MAXFINAL = 2048;       // finalists the select kernel can sort per row
+
+struct FusedParams {
+    const float *Uhi, *Ulo, *Ihi, *Ilo;
+    int KP, n_itiles, tiles_per_split, n_splits, cap, k;
+    int64_t B, n_items;
+    const int32_t* mask_ptr;            // [B+1] CSR over batch rows (may be null = no mask)
+    float2* cand;                       // [B][n_splits][cap]
+    int32_t* cnt;                       // [B][n_splits]
+    float* thr;                         // [B][n_splits]
+    int32_t* flags;                     // [B] fallback flags
+};
+
+struct FzSmem {
+    uint32_t u_hi, u_lo, slab0, hist, bars, tmem_ptr, total;
+    int stages;
+};
+__host__ __device__ inline FzSmem fz_smem(int KP) {
+    FzSmem L;
+    const uint32_t u_bytes = TC_M * KP * 4;
+    L.stages = KP >= 128 ? 2 : 4;
+    L.u_hi = 0; L.u_lo = u_bytes; L.slab0 = 2 * u_bytes;
+    L.hist = L.slab0 + L.stages * TC_SLAB_BYTES;
+    L.bars = L.hist + FZ_NB * TC_M * 2;
+    L.tmem_ptr = L.bars + 16 * 8;
+    L.total = L.tmem_ptr + 16;
+    return L;
+}
+
+// producer / MMA issuer: identical protocol to score_tc.cu (barrier slots: 0 u_full | 1..4 full | 5..8 empty |
+// 9,10 tmem_full | 11,12 tmem_empty)
+__device__ __forceinline__ void fz_producer(const FusedParams& p, const FzSmem& L, uint32_t sbase, int ut, int it0, int it1) {
+    const uint32_t bar = sbase + L.bars;
+    const uint32_t u_bytes = TC_M * p.KP * 4;
+    mbar_expect_tx(bar, 2 * u_bytes);
+    for (uint32_t o = 0; o < u_bytes; o += 16384) {
+        bulk_g2s(sbase + L.u_hi + o, (const char*)(p.Uhi + (int64_t)ut * TC_M * p.KP) + o, 16384, bar);
+        bulk_g2s(sbase + L.u_lo + o, (const char*)(p.Ulo + (int64_t)ut * TC_M * p.KP) + o, 16384, bar);
+    }
+    const int kchunks = p.KP / TC_KC;
+    uint32_t s = 0;
+    for (int it = it0; it < it1; ++it)
+        for (int c = 0; c < 2 * kchunks; ++c, ++s) {
+            const uint32_t slot = s % L.stages, use = s / L.stages;
+            mbar_wait(bar + (5 + slot) * 8, (use & 1) ^ 1);
+            mbar_expect_tx(bar + (1 + slot) * 8, TC_SLAB_BYTES);
+            const float* src = (c < kchunks ? p.Ihi : p.Ilo) + ((int64_t)it * p.KP / 4 + (c % kchunks) * (TC_KC / 4)) * (TC_N / 8) * 32;
+            bulk_g2s(sbase + L.slab0 + slot * TC_SLAB_BYTES, src, TC_SLAB_BYTES, bar + (1 + slot) * 8);
+        }
+}
+
+__device__ __forceinline__ void fz_mma(const FusedParams& p, const FzSmem& L, uint32_t sbase, uint32_t tmem_base, int it0, int it1) {
+    const uint32_t bar = sbase + L.bars;
+    constexpr uint32_t LBO_A = (TC_M / 8) * 128, LBO_B = (TC_N / 8) * 128, SBO = 128;
+    const uint32_t idesc = idesc_tf32(TC_M, TC_N);
+    const int kchunks = p.KP / TC_KC;
+    mbar_wait(bar, 0);
+    fence_after_sync();
+    uint32_t s = 0;
+    for (int it = it0, t = 0; it < it1; ++it, ++t) {
+        const uint32_t buf = t & 1;
+        mbar_wait(bar + (11 + buf) * 8, ((t >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * TC_N;
+        uint32_t acc = 0;
+        for (int c = 0; c < 2 * kchunks; ++c, ++s) {
+            const uint32_t slot = s % L.stages, use = s / L.stages;
+            mbar_wait(bar + (1 + slot) * 8, use & 1);
+            fence_after_sync();
+            const bool item_lo = c >= kchunks;
+            const int kc = c % kchunks;
+            const uint32_t b_base = sbase + L.slab0 + slot * TC_SLAB_BYTES;
+#pragma unroll
+            for (int j = 0; j < TC_KC / 8; ++j) {
+                const uint64_t bd = smem_desc(b_base + j * 2 * LBO_B, LBO_B, SBO);
+                const uint32_t a_off = (kc * (TC_KC / 4) + 2 * j) * LBO_A;
+                mma_tf32(d_tmem, smem_desc(sbase + L.u_hi + a_off, LBO_A, SBO), bd, idesc, acc);
+                acc = 1;
+                if (!item_lo) mma_tf32(d_tmem, smem_desc(sbase + L.u_lo + a_off, LBO_A, SBO), bd, idesc, 1);
+            }
+            mma_commit(bar + (5 + slot) * 8);
+        }
+        mma_commit(bar + (9 + buf) * 8);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const FzSmem L = fz_smem(p.KP);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar = sbase + L.bars;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 11; ++i) mbar_init(bar + i * 8, 1);
+        mbar_init(bar + 11 * 8, 128); mbar_init(bar + 12 * 8, 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) { tmem_alloc(sbase + L.tmem_ptr, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr);
+    const int ut = blockIdx.x / p.n_splits, sp = blockIdx.x % p.n_splits;
+    const int it0 = sp * p.tiles_per_split;
+    const int it1 = min(p.n_itiles, it0 + p.tiles_per_split);
+
+    if (warp == 0) {
+        if (lane == 0 && it0 < it1) fz_producer(p, L, sbase, ut, it0, it1);
+    } else if (warp == 1) {
+        if (lane == 0 && it0 < it1) fz_mma(p, L, sbase, tmem_base, it0, it1);
+    } else {
+        const int q = warp & 3;
+        const int rl = q * 32 + lane;                               // row inside the tile = TMEM lane
+        const int64_t row = (int64_t)ut * TC_M + rl;
+        const bool live = row < p.B;
+        uint16_t* hist = reinterpret_cast<uint16_t*>(smem + L.hist);   // [bin][row]
+        int need = p.k;
+        if (live && p.mask_ptr) need += p.mask_ptr[row + 1] - p.mask_ptr[row];
+        float2* cand = p.cand + ((int64_t)(live ? row : 0) * p.n_splits + sp) * p.cap;
+        float thr = 0.f, lo = 0.f, scale = 0.f, width = 0.f;
+        int cnt = 0, bad = 0;
+
+        auto bin_of = [&](float v) -> int {
+            int b = (int)((v - lo) * scale);
+            return b < 0 ? 0 : (b > FZ_NB - 1 ? FZ_NB - 1 : b);
+        };
+        bool cert = false;                                          // >= need candidates counted above thr
+        auto consider = [&](float v, int col) {                     // v >= thr already established
+            if (cnt < p.cap) cand[cnt] = make_float2(v, __int_as_float(col));
+            else bad = 1;
+            ++cnt;
+            uint16_t& h = hist[bin_of(v) * TC_M + rl];
+            if (h < 0xffff) ++h;
+        };
+
+        for (int it = it0, t = 0; it < it1; ++it, ++t) {
+            const uint32_t buf = t & 1;
+            mbar_wait(bar + (9 + buf) * 8, (t >> 1) & 1);
+            fence_after_sync();
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_N;
+            const int col_base = it * TC_N;
+            const bool partial = (int64_t)col_base + TC_N > p.n_items;
+            if (t == 0) {
+                // seed: thr0 = min of the 32-column group maxima, max0 = row maximum of the tile
+                float gmin = INFINITY, gmax = -INFINITY;
+#pragma unroll 1
+                for (int c8 = 0; c8 < TC_N / 32; ++c8) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tbase + c8 * 32, v);
+                    tmem_ld_wait();
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]);
+                        if (partial && (int64_t)col_base + c8 * 32 + j >= p.n_items) x = -INFINITY;
+                        m = fmaxf(m, x);
+                    }
+                    if (m > -INFINITY) { gmin = fminf(gmin, m); gmax = fmaxf(gmax, m); }
+                }
+                thr = lo = gmin;
+                width = (gmax - gmin) * (2.0f / FZ_NB);
+                if (!(width > 0.f) || !(gmin > -INFINITY) || !(gmax < INFINITY)) { bad = 1; width = 1.f; lo = 0.f; thr = INFINITY; }
+                if (!live) thr = INFINITY;                          // padding rows: nothing passes, nothing is written
+                scale = 1.0f / width;
+#pragma unroll
+                for (int b = 0; b < FZ_NB; ++b) hist[b * TC_M + rl] = 0;
+            }
+#pragma unroll 1
+            for (int c8 = 0; c8 < TC_N / 32; ++c8) {
+                uint32_t v[32];
+                tmem_ld_32x32(tbase + c8 * 32, v);
+                tmem_ld_wait();
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (partial && (int64_t)col_base + c8 * 32 + j >= p.n_items) v[j] = 0xff800000u;   // -inf
+                    m = fmaxf(m, __uint_as_float(v[j]));
+                }
+                if (m >= thr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = __uint_as_float(v[j]);
+                        if (x >= thr) consider(x, col_base + c8 * 32 + j);
+                    }
+                }
+            }
+            // accumulator drained: hand the TMEM buffer back before the (SMEM-only) threshold update
+            fence_before_sync();
+            mbar_arrive(bar + (11 + buf) * 8);
+            // raise the threshold to the highest bin edge that keeps `need` candidates above it
+            int c = 0, b = FZ_NB - 1;
+            for (; b >= 0; --b) {
+                c += hist[b * TC_M + rl];
+                if (c >= need) break;
+            }
+            cert = b >= 0;
+            if (b > 0) {
+                const float edge = lo + (float)b * width;
+                const float safe = edge - 2e-6f * fmaxf(fmaxf(fabsf(edge), fabsf(lo)), width);   // bin_of() rounding slack
+                if (safe > thr) thr = safe;
+                if (b == FZ_NB - 1 && !bad) {
+                    // everything needed sits in the clamped top bin: slide the window up and recount the survivors
+                    lo = safe;
+#pragma unroll
+                    for (int bb = 0; bb < FZ_NB; ++bb) hist[bb * TC_M + rl] = 0;
+                    const int n = cnt < p.cap ? cnt : p.cap;
+                    for (int j = 0; j < n; ++j) {
+                        const float x = cand[j].x;
+                        if (x >= thr) { uint16_t& h = hist[bin_of(x) * TC_M + rl]; if (h < 0xffff) ++h; }
+                    }
+                }
+            }
+        }
+        if (live && it0 < it1) {
+            p.cnt[row * p.n_splits + sp] = cnt < p.cap ? cnt : p.cap;
+            p.thr[row * p.n_splits + sp] = thr;
+            // uncertified split (fewer than `need` candidates counted above the threshold, e.g. a user with more
+            // train positives than the candidate list holds): the row goes to the exact kernel
+            if (bad || !cert) atomicOr(p.flags + row, 1);
+        } else if (live) {
+            p.cnt[row * p.n_splits + sp] = 0;
+            p.thr[row * p.n_splits + sp] = INFINITY;
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// mask CSR over batch rows (input order is free)
+// ------------------------------------------------------------------------------------------------------
+__global__ void mask_count_kernel(int64_t nnz, const int64_t* __restrict__ rows, int64_t B, int32_t* __restrict__ counts) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < nnz && rows[j] >= 0 && rows[j] < B) atomicAdd(counts + rows[j], 1);
+}
+__global__ void mask_fill_kernel(int64_t nnz, const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t B,
+                                 int64_t item_offset, const int32_t* __restrict__ ptr, int32_t* __restrict__ cursor,
+                                 int32_t* __restrict__ items) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= nnz || rows[j] < 0 || rows[j] >= B) return;
+    const int pos = ptr[rows[j]] + atomicAdd(cursor + rows[j], 1);
+    items[pos] = (int32_t)(cols[j] - item_offset);     // may fall outside [0, n_items): then it never matches
+}
+
+// ------------------------------------------------------------------------------------------------------
+// select: finalists of all splits -> drop masked -> top-k in contract order
+// ------------------------------------------------------------------------------------------------------
+__device__ void fz_bitonic_desc(uint64_t* a, int n) {
+    for (int size = 2; size <= n; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t x = a[lo], y = a[hi];
+                if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+            }
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_splits, int cap, int k, int64_t item_offset,
+                                                           const float2* __restrict__ cand, const int32_t* __restrict__ cnt,
+                                                           const float* __restrict__ thr, const int32_t* __restrict__ mask_ptr,
+                                                           const int32_t* __restrict__ mask_items, int32_t* __restrict__ flags,
+                                                           int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    __shared__ uint64_t fin[FZ_MAXFINAL];
+    __shared__ int n_fin, over;
+    const int64_t row = blockIdx.x;
+    if (flags[row]) return;                                          // already condemned to the exact kernel
+    if (threadIdx.x == 0) { n_fin = 0; over = 0; }
+    __syncthreads();
+    const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
+    for (int s = 0; s < n_splits; ++s) {
+        const int n = cnt[row * n_splits + s];
+        const float th = thr[row * n_splits + s];
+        const float2* cs = cand + (row * n_splits + s) * cap;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const float2 c = cs[j];
+            if (!(c.x >= th)) continue;
+            const int item = __float_as_int(c.y);
+            bool masked = false;
+            for (int q = m0; q < m1; ++q) masked |= (mask_items[q] == item);
+            if (masked) continue;
+            const int pos = atomicAdd(&n_fin, 1);
+            if (pos < FZ_MAXFINAL) fin[pos] = ((uint64_t)float_key(c.x) << 32) | (uint32_t)(~(uint32_t)item);
+            else over = 1;
+        }
+    }
+    __syncthreads();
+    const int n = n_fin;
+    if (over || n < k) {                                             // cannot certify this row: exact kernel takes it
+        if (threadIdx.x == 0) flags[row] = 1;
+        return;
+    }
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int t = n + threadIdx.x; t < n2; t += blockDim.x) fin[t] = 0;
+    fz_bitonic_desc(fin, n2);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const uint64_t c = fin[t];
+        out_idx[row * k + t] = (int64_t)(uint32_t)(~(uint32_t)c) + item_offset;
+        out_val[row * k + t] = key_float((uint32_t)(c >> 32));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exact fp32 rows (flagged only): scores recomputed on the fly with the fmaf chain of the CUDA-core GEMM, masked,
+// radix-selected -- the same contract as mmrec_topk_rows_f32, no score matrix
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t* __restrict__ users, const float* __restrict__ Ue,
+                                                        int64_t ldu, int64_t n_items, const float* __restrict__ Ie, int64_t ldi,
+                                                        int d, int k, int64_t item_offset, const int32_t* __restrict__ mask_ptr,
+                                                        const int32_t* __restrict__ mask_items, const int32_t* __restrict__ flags,
+                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    extern __shared__ float urow[];                                  // d floats
+    __shared__ unsigned hist[256];
+    __shared__ uint64_t sel[1024];
+    __shared__ unsigned s_prefix, s_need, s_count, s_base;
+    __shared__ unsigned warp_tot[8];
+    const int64_t row = blockIdx.x;
+    if (!flags[row]) return;
+    const int tid = threadIdx.x;
+    const float* u = Ue + (users ? users[row] : row) * ldu;
+    for (int c = tid; c < d; c += 256) urow[c] = u[c];
+    __syncthreads();
+    const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
+    auto key_at = [&](int64_t i) -> unsigned {
+        const float* v = Ie + i * ldi;
+        float acc = 0.f;
+        for (int c = 0; c < d; ++c) acc = fmaf(urow[c], __ldg(v + c), acc);
+        for (int q = m0; q < m1; ++q)
+            if (mask_items[q] == (int32_t)i) acc = -1e10f;
+        return float_key(acc);
+    };
+    unsigned prefix = 0, need = (unsigned)k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const unsigned hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        hist[tid] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < n_items; i += 256) {
+            unsigned key = key_at(i);
+            if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned cum = 0;
+            int dgt = 255;
+            for (; dgt > 0; --dgt) {
+                if (cum + hist[dgt] >= need) break;
+                cum += hist[dgt];
+            }
+            s_prefix = prefix | ((unsigned)dgt << shift);
+            s_need = need - cum;
+        }
+        __syncthreads();
+        prefix = s_prefix; need = s_need;
+        __syncthreads();
+    }
+    const unsigned kth = prefix;
+    if (tid == 0) { s_count = 0; s_base = 0; }
+    __syncthreads();
+    for (int64_t i = tid; i < n_items; i += 256) {
+        unsigned key = key_at(i);
+        if (key > kth) { unsigned pos = atomicAdd(&s_count, 1u); sel[pos] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)i); }
+    }
+    __syncthreads();
+    const unsigned n_gt = s_count;
+    for (int64_t i0 = 0; i0 < n_items; i0 += 256) {
+        if (s_base >= need) break;
+        const int64_t i = i0 + tid;
+        const bool eq = i < n_items && key_at(i) == kth;
+        const unsigned bal = __ballot_sync(0xffffffffu, eq);
+        const int lane = tid & 31, wid = tid >> 5;
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        unsigned off = s_base;
+        for (int w = 0; w < wid; ++w) off += warp_tot[w];
+        const unsigned rank = off + __popc(bal & ((1u << lane) - 1u));
+        if (eq && rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~(uint32_t)i);
+        __syncthreads();
+        if (tid == 0) { unsigned tot = 0; for (int w = 0; w < 8; ++w) tot += warp_tot[w]; s_base += tot; }
+        __syncthreads();
+    }
+    int n2 = 1;
+    while (n2 < k) n2 <<= 1;
+    for (int t = k + tid; t < n2; t += 256) sel[t] = 0;
+    fz_bitonic_desc(sel, n2);
+    for (int t = tid; t < k; t += 256) {
+        const uint64_t c = sel[t];
+        out_idx[row * k + t] = (int64_t)(uint32_t)(~(uint32_t)c) + item_offset;
+        out_val[row * k + t] = key_float((uint32_t)(c >> 32));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static inline int fz_kp(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
+
+struct FzPlan {
+    int KP, splits, tiles_per_split, cap;
+    int64_t n_ut, n_it, rows_blk;
+    size_t off_uhi, off_ulo, off_ihi, off_ilo, off_cand, off_cnt, off_thr, off_flags, off_mptr, off_mcur, off_mitems, off_cub,
+        cub_bytes, total;
+};
+
+static FzPlan fz_plan(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz) {
+    FzPlan P;
+    P.KP = fz_kp(d);
+    P.rows_blk = B < 4096 ? B : 4096;
+    P.n_ut = (P.rows_blk + TC_M - 1) / TC_M;
+    P.n_it = (n_items + TC_N - 1) / TC_N;
+    const int sms = sm_count();
+    int splits = (int)((sms + P.n_ut - 1) / P.n_ut);
+    if (splits > P.n_it) splits = (int)P.n_it;
+    // every split must see enough items to fill a top-(k+m) list comfortably
+    while (splits > 1 && (P.n_it / splits) * TC_N < 8 * (int64_t)k + 512) --splits;
+    if (splits < 1) splits = 1;
+    P.tiles_per_split = (int)((P.n_it + splits - 1) / splits);
+    P.splits = (int)((P.n_it + P.tiles_per_split - 1) / P.tiles_per_split);
+    P.cap = (int64_t)P.tiles_per_split * TC_N > 20000 ? 1024 : 512;
+    if (P.cap < 4 * k) P.cap = 4 * k;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+    P.off_uhi = take((size_t)P.n_ut * TC_M * P.KP * 4); P.off_ulo = take((size_t)P.n_ut * TC_M * P.KP * 4);
+    P.off_ihi = take((size_t)P.n_it * TC_N * P.KP * 4); P.off_ilo = take((size_t)P.n_it * TC_N * P.KP * 4);
+    P.off_cand = take((size_t)P.rows_blk * P.splits * P.cap * 8);
+    P.off_cnt = take((size_t)P.rows_blk * P.splits * 4); P.off_thr = take((size_t)P.rows_blk * P.splits * 4);
+    P.off_flags = take((size_t)P.rows_blk * 4);
+    P.off_mptr = take((size_t)(B + 2) * 4); P.off_mcur = take((size_t)(B + 2) * 4);
+    P.off_mitems = take((size_t)(mask_nnz > 0 ? mask_nnz : 1) * 4);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int64_t)(B + 1));
+    P.cub_bytes = scan_bytes;
+    P.off_cub = take(scan_bytes);
+    P.total = off + 1024;
+    return P;
+}
+
+bool score_fused_supported(int64_t B, int64_t n_items, int d, int k) {
+    return B > 0 && d <= 128 && k >= 1 && k <= 256 && n_items >= 8 * (int64_t)k + 512 && n_items < (1ll << 31);
+}
+
+size_t score_fused_workspace_bytes(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz) {
+    if (!score_fused_supported(B, n_items, d, k)) return 0;
+    return fz_plan(B, n_items, d, k, mask_nnz).total;
+}
+
+// returns 1 = done, 0 = unsupported shape / workspace (caller uses the unfused path), <0 error
+int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie, int64_t ldi,
+                int d, int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int k, int64_t item_offset,
+                int64_t* out_idx, float* out_val, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!score_fused_supported(B, n_items, d, k) || !ws) return 0;
+    const FzPlan P = fz_plan(B, n_items, d, k, mask_nnz);
+    if (ws_bytes < P.total) return 0;
+    char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    float *Uhi = (float*)(base + P.off_uhi), *Ulo = (float*)(base + P.off_ulo);
+    float *Ihi = (float*)(base + P.off_ihi), *Ilo = (float*)(base + P.off_ilo);
+    int32_t *mptr = (int32_t*)(base + P.off_mptr), *mcur = (int32_t*)(base + P.off_mcur), *mitems = (int32_t*)(base + P.off_mitems);
+    const int T = 256;
+    // mask -> CSR over batch rows
+    const bool has_mask = mask_nnz > 0;
+    if (has_mask) {
+        MMREC_CUDA(cudaMemsetAsync(mcur, 0, (size_t)(B + 2) * 4, stream));
+        mask_count_kernel<<<(unsigned)((mask_nnz + T - 1) / T), T, 0, stream>>>(mask_nnz, mask_rows, B, mcur);
+        MMREC_LAUNCH_CHECK();
+        size_t tmp = P.cub_bytes;
+        MMREC_CUDA(cub::DeviceScan::ExclusiveSum(base + P.off_cub, tmp, mcur, mptr, B + 1, stream));
+        MMREC_CUDA(cudaMemsetAsync(mcur, 0, (size_t)(B + 2) * 4, stream));
+        mask_fill_kernel<<<(unsigned)((mask_nnz + T - 1) / T), T, 0, stream>>>(mask_nnz, mask_rows, mask_cols, B, item_offset, mptr,
+                                                                              mcur, mitems);
+        MMREC_LAUNCH_CHECK();
+    }
+    // items: split + re-tile once for all row blocks
+    {
+        const int64_t ti = P.n_it * TC_N * (P.KP / 4);
+        pack_split_kernel<TC_N><<<(unsigned)((ti + T - 1) / T), T, 0, stream>>>(n_items, nullptr, Ie, ldi, d, P.KP, Ihi, Ilo, P.n_it);
+        MMREC_LAUNCH_CHECK();
+    }
+    const FzSmem L = fz_smem(P.KP);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMREC_CUDA(cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    for (int64_t r0 = 0; r0 < B; r0 += P.rows_blk) {
+        const int64_t nb = (B - r0) < P.rows_blk ? (B - r0) : P.rows_blk;
+        const int64_t n_ut = (nb + TC_M - 1) / TC_M;
+        const int64_t tu = n_ut * TC_M * (P.KP / 4);
+        pack_split_kernel<TC_M><<<(unsigned)((tu + T - 1) / T), T, 0, stream>>>(nb, users ? users + r0 : nullptr,
+                                                                                users ? Ue : Ue + r0 * ldu, ldu, d, P.KP, Uhi, Ulo, n_ut);
+        MMREC_LAUNCH_CHECK();
+        MMREC_CUDA(cudaMemsetAsync(base + P.off_flags, 0, (size_t)nb * 4, stream));
+        FusedParams p;
+        p.Uhi = Uhi; p.Ulo = Ulo; p.Ihi = Ihi; p.Ilo = Ilo; p.KP = P.KP; p.n_itiles = (int)P.n_it;
+        p.tiles_per_split = P.tiles_per_split; p.n_splits = P.splits; p.cap = P.cap; p.k = k; p.B = nb; p.n_items = n_items;
+        p.mask_ptr = has_mask ? mptr + r0 : nullptr;
+        p.cand = (float2*)(base + P.off_cand); p.cnt = (int32_t*)(base + P.off_cnt); p.thr = (float*)(base + P.off_thr);
+        p.flags = (int32_t*)(base + P.off_flags);
+        score_fused_kernel<<<(unsigned)(n_ut * P.splits), TC_THREADS, L.total, stream>>>(p);
+        MMREC_LAUNCH_CHECK();
+        fused_select_kernel<<<(unsigned)nb, 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,
+                                                              mitems, p.flags, out_idx + r0 * k, out_val + r0 * k);
+        MMREC_LAUNCH_CHECK();
+        exact_row_kernel<<<(unsigned)nb, 256, (size_t)d * sizeof(float), stream>>>(nb, users ? users + r0 : nullptr,
+                                                                                  users ? Ue : Ue + r0 * ldu, ldu, n_items, Ie, ldi, d, k,
+                                                                                  item_offset, p.mask_ptr, mitems, p.flags,
+                                                                                  out_idx + r0 * k, out_val + r0 * k);
+        MMREC_LAUNCH_CHECK();
+    }
+    return 1;
+}
+
+}  // namespace mmrec

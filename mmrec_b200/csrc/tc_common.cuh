@@ -115,4 +115,39 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 }  // namespace tc
+
+// ---- tile geometry shared by the tensor-core kernels ---------------------------------------------------------
+constexpr int TC_M = 128;          // users per CTA tile = TMEM lanes
+constexpr int TC_N = 256;          // items per accumulator = TMEM columns
+constexpr int TC_KC = 32;          // k per slab
+constexpr int TC_SLAB_BYTES = TC_N * TC_KC * 4;    // 32 KB
+constexpr int TC_THREADS = 192;    // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+
+// operand packing: split into tf32 hi/lo and re-tile as [tile][kblk = KP/4][row group = R/8][8 rows][4 floats], the
+// UMMA canonical K-major no-swizzle layout, so that a K slab of a tile is one contiguous byte range
+template <int R>
+__global__ void pack_split_kernel(int64_t n_rows, const int64_t* __restrict__ idx, const float* __restrict__ E, int64_t ld,
+                                  int d, int KP, float* __restrict__ hi, float* __restrict__ lo, int64_t n_tiles) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per (padded row, kblk)
+    const int kblks = KP / 4;
+    const int64_t total = n_tiles * R * kblks;
+    if (t >= total) return;
+    const int64_t row = t / kblks;
+    const int kb = (int)(t % kblks);
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < n_rows) {
+        const float* src = E + (idx ? idx[row] : row) * ld;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (kb * 4 + e < d) x[e] = __ldg(src + kb * 4 + e);
+    }
+    float4 h, l;
+    tc::split_tf32(x[0], h.x, l.x); tc::split_tf32(x[1], h.y, l.y); tc::split_tf32(x[2], h.z, l.z); tc::split_tf32(x[3], h.w, l.w);
+    const int64_t tile = row / R;
+    const int rr = (int)(row % R);
+    const int64_t off = ((tile * kblks + kb) * (R / 8) + rr / 8) * 32 + (rr % 8) * 4;
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+
 }  // namespace mmrec

@@ -320,8 +320,14 @@ def project(table, weight, bias=None, idx=None, l2_normalize=False) -> torch.Ten
 # ------------------------------------------------------------------------------------------------
 # K3: scoring, mask, top-k
 # ------------------------------------------------------------------------------------------------
-def set_score_path(tensor_core: bool):
-    _lib.load().mmrec_score_set_path(int(bool(tensor_core)))
+def set_score_path(path):
+    """0 / "simt": exact fp32 CUDA cores; 1 / "tc": tcgen05 3xTF32, unfused top-k; 2 / "fused" (default): tcgen05
+    with the top-k fused into the epilogue.  True/False are accepted as 2/0."""
+    if isinstance(path, str):
+        path = {"simt": 0, "tc": 1, "fused": 2}[path]
+    elif isinstance(path, bool):
+        path = 2 if path else 0
+    _lib.load().mmrec_score_set_path(int(path))
 
 
 def score(user_e, item_e, users=None) -> torch.Tensor:
@@ -380,7 +386,7 @@ def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0):
     if mask is not None and mask.numel() > 0:
         mask = mask.to(torch.int64).contiguous()
         m0, m1, nnz = mask[0], mask[1], mask.shape[1]
-    nbytes = lib.mmrec_score_topk_workspace_bytes(B, n_items, d, k)
+    nbytes = lib.mmrec_score_topk_workspace_bytes(B, n_items, d, k) + 4 * nnz + 4096
     ws = _ws("score_topk", nbytes, item_e.device)
     check(lib.mmrec_score_topk_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e),
                                    item_e.stride(0), d, nnz, _ptr(m0), _ptr(m1), k, item_offset, _ptr(idx), _ptr(val),
