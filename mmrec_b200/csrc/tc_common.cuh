@@ -30,11 +30,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap, not hang the GPU (the box is shared and a hang is a strike).
+// Bounded wait: a protocol bug must trap within ~2 s of wall time, not hang the GPU (the box is shared and a hang
+// is a strike).  The clock is only consulted after the fast path failed a few thousand times.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 28)) {
+        if (++spins == 4096u) t0 = global_ns();
+        if (spins > 4096u && (spins & 1023u) == 0 && global_ns() - t0 > 2000000000ull) {
             printf("mmrec: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
             __trap();
         }

@@ -126,7 +126,7 @@ def test_model_matches_reference(env, golden, name, file, over):
         # gradients that are pure cancellation noise (softmax-invariant biases, ~1e-11) carry no signal:
         # measure the error against the scale of the whole gradient, not of the vanishing entry
         err = (named[k].grad.detach().cpu().double() - torch.from_numpy(gref).double()).norm().item()
-        assert err < 1e-4 * max(float(np.linalg.norm(gref)), 1e-6 * gmax), f"grad {k}"
+        assert err < 1e-4 * float(np.linalg.norm(gref)) + 1e-7 * gmax * np.sqrt(gref.size), f"grad {k}"
     # (4) full_sort_predict + trainer mask/top-k on the reference's first eval batch
     model.eval()
     with torch.no_grad():
