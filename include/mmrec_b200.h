@@ -153,6 +153,8 @@ int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64
                          int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols,
                          int k, int64_t item_offset, int64_t* out_idx, float* out_val,
                          void* ws, size_t ws_bytes, void* stream);
+/* diagnostic, synchronising: rows of the last row block of the last fused call on `ws` that needed the exact kernel */
+int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz);
 int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, const int64_t* idx,
                      int64_t* out_idx, float* out_val, void* stream);
 

@@ -36,6 +36,7 @@ PROTOTYPES = {
     "mmrec_score_topk_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "mmrec_score_topk_f32": (_i32, [_i64, _p, _p, _i64, _i64, _p, _i64, _i32, _i64, _p, _p, _i32, _i64, _p, _p, _p,
                                     _sz, _p]),
+    "mmrec_debug_fused_fallback_rows": (_i64, [_p, _i64, _i64, _i32, _i32, _i64]),
     "mmrec_topk_merge": (_i32, [_i32, _i64, _i32, _p, _p, _p, _p, _p]),
 }
 

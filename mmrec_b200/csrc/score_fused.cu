@@ -238,12 +238,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
         if (live && it0 < it1) {
             p.cnt[row * p.n_splits + sp] = cnt < p.cap ? cnt : p.cap;
             p.thr[row * p.n_splits + sp] = thr;
-            // uncertified split (fewer than `need` candidates counted above the threshold, e.g. a user with more
-            // train positives than the candidate list holds): the row goes to the exact kernel
-            if (bad || !cert) atomicOr(p.flags + row, 1);
+            // (a split that never collected `need` candidates keeps a low threshold; the select kernel certifies the
+            // row globally, see there)
+            if (bad) atomicOr(p.flags + row, 1);
+            (void)cert;
         } else if (live) {
             p.cnt[row * p.n_splits + sp] = 0;
-            p.thr[row * p.n_splits + sp] = INFINITY;
+            p.thr[row * p.n_splits + sp] = -INFINITY;
         }
     }
     fence_before_sync();
@@ -296,9 +297,13 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
     if (threadIdx.x == 0) { n_fin = 0; over = 0; }
     __syncthreads();
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
+    // Certificate: every split's list holds ALL of its items with value >= its own final threshold, hence all items
+    // >= T = max over splits.  If at least k unmasked items clear T, the global top-k is among them.
+    float T = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) T = fmaxf(T, thr[row * n_splits + s]);
     for (int s = 0; s < n_splits; ++s) {
         const int n = cnt[row * n_splits + s];
-        const float th = thr[row * n_splits + s];
+        const float th = T;
         const float2* cs = cand + (row * n_splits + s) * cap;
         for (int j = threadIdx.x; j < n; j += blockDim.x) {
             const float2 c = cs[j];
@@ -330,15 +335,17 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
 }
 
 // ------------------------------------------------------------------------------------------------------
-// exact fp32 rows (flagged only): scores recomputed on the fly with the fmaf chain of the CUDA-core GEMM, masked,
-// radix-selected -- the same contract as mmrec_topk_rows_f32, no score matrix
+// exact fp32 rows (flagged only): the row's scores are recomputed per sweep with the fmaf chain of the CUDA-core GEMM,
+// masked and radix-selected -- the same contract as mmrec_topk_rows_f32, no score matrix
 // ------------------------------------------------------------------------------------------------------
+constexpr int EX_TILE = 256;   // items staged per tile = threads per CTA
+
 __global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t* __restrict__ users, const float* __restrict__ Ue,
                                                         int64_t ldu, int64_t n_items, const float* __restrict__ Ie, int64_t ldi,
                                                         int d, int k, int64_t item_offset, const int32_t* __restrict__ mask_ptr,
                                                         const int32_t* __restrict__ mask_items, const int32_t* __restrict__ flags,
                                                         int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
-    extern __shared__ float urow[];                                  // d floats
+    extern __shared__ float ex_sm[];                                 // urow[d] | tile[EX_TILE][d + 1]
     __shared__ unsigned hist[256];
     __shared__ uint64_t sel[1024];
     __shared__ unsigned s_prefix, s_need, s_count, s_base;
@@ -346,16 +353,26 @@ __global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t
     const int64_t row = blockIdx.x;
     if (!flags[row]) return;
     const int tid = threadIdx.x;
+    float* urow = ex_sm;
+    float* tile = ex_sm + d;
+    const int ldt = d + 1;
     const float* u = Ue + (users ? users[row] : row) * ldu;
     for (int c = tid; c < d; c += 256) urow[c] = u[c];
-    __syncthreads();
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
-    auto key_at = [&](int64_t i) -> unsigned {
-        const float* v = Ie + i * ldi;
+    // key of item i0 + tid: fmaf chain of the CUDA-core GEMM (k ascending); the 256 items of a tile are staged
+    // through shared memory so that the global reads are coalesced.  Returns 0 for tid beyond the catalogue.
+    auto tile_key = [&](int64_t i0, bool& valid) -> unsigned {
+        __syncthreads();
+        const int nt = (int)((n_items - i0) < EX_TILE ? (n_items - i0) : EX_TILE);
+        for (int e = tid; e < nt * d; e += 256) tile[(e / d) * ldt + (e % d)] = __ldg(Ie + (i0 + e / d) * ldi + (e % d));
+        __syncthreads();
+        valid = tid < nt;
+        if (!valid) return 0u;
         float acc = 0.f;
-        for (int c = 0; c < d; ++c) acc = fmaf(urow[c], __ldg(v + c), acc);
+        for (int c = 0; c < d; ++c) acc = fmaf(urow[c], tile[tid * ldt + c], acc);
+        const int32_t item = (int32_t)(i0 + tid);
         for (int q = m0; q < m1; ++q)
-            if (mask_items[q] == (int32_t)i) acc = -1e10f;
+            if (mask_items[q] == item) acc = -1e10f;
         return float_key(acc);
     };
     unsigned prefix = 0, need = (unsigned)k;
@@ -363,10 +380,10 @@ __global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t
         const int shift = 24 - 8 * pass;
         const unsigned hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
         hist[tid] = 0;
-        __syncthreads();
-        for (int64_t i = tid; i < n_items; i += 256) {
-            unsigned key = key_at(i);
-            if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        for (int64_t i0 = 0; i0 < n_items; i0 += EX_TILE) {
+            bool valid;
+            const unsigned key = tile_key(i0, valid);
+            if (valid && (key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
         if (tid == 0) {
@@ -386,16 +403,13 @@ __global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t
     const unsigned kth = prefix;
     if (tid == 0) { s_count = 0; s_base = 0; }
     __syncthreads();
-    for (int64_t i = tid; i < n_items; i += 256) {
-        unsigned key = key_at(i);
-        if (key > kth) { unsigned pos = atomicAdd(&s_count, 1u); sel[pos] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)i); }
-    }
-    __syncthreads();
-    const unsigned n_gt = s_count;
-    for (int64_t i0 = 0; i0 < n_items; i0 += 256) {
-        if (s_base >= need) break;
-        const int64_t i = i0 + tid;
-        const bool eq = i < n_items && key_at(i) == kth;
+    const unsigned n_gt = (unsigned)k - need;
+    // one ordered sweep: strictly greater keys anywhere, ties on the k-th key in index order
+    for (int64_t i0 = 0; i0 < n_items; i0 += EX_TILE) {
+        bool valid;
+        const unsigned key = tile_key(i0, valid);
+        if (valid && key > kth) { unsigned pos = atomicAdd(&s_count, 1u); sel[pos] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)(i0 + tid)); }
+        const bool eq = valid && key == kth;
         const unsigned bal = __ballot_sync(0xffffffffu, eq);
         const int lane = tid & 31, wid = tid >> 5;
         if (lane == 0) warp_tot[wid] = __popc(bal);
@@ -403,11 +417,11 @@ __global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t
         unsigned off = s_base;
         for (int w = 0; w < wid; ++w) off += warp_tot[w];
         const unsigned rank = off + __popc(bal & ((1u << lane) - 1u));
-        if (eq && rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~(uint32_t)i);
+        if (eq && rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~(uint32_t)(i0 + tid));
         __syncthreads();
         if (tid == 0) { unsigned tot = 0; for (int w = 0; w < 8; ++w) tot += warp_tot[w]; s_base += tot; }
-        __syncthreads();
     }
+    __syncthreads();
     int n2 = 1;
     while (n2 < k) n2 <<= 1;
     for (int t = k + tid; t < n2; t += 256) sel[t] = 0;
@@ -507,6 +521,7 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
     const FzSmem L = fz_smem(P.KP);
     static bool attr_set = false;
     if (!attr_set) {
+        MMREC_CUDA(cudaFuncSetAttribute(exact_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         MMREC_CUDA(cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
@@ -529,13 +544,28 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         fused_select_kernel<<<(unsigned)nb, 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,
                                                               mitems, p.flags, out_idx + r0 * k, out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
-        exact_row_kernel<<<(unsigned)nb, 256, (size_t)d * sizeof(float), stream>>>(nb, users ? users + r0 : nullptr,
-                                                                                  users ? Ue : Ue + r0 * ldu, ldu, n_items, Ie, ldi, d, k,
-                                                                                  item_offset, p.mask_ptr, mitems, p.flags,
-                                                                                  out_idx + r0 * k, out_val + r0 * k);
+        exact_row_kernel<<<(unsigned)nb, 256, (size_t)(d + EX_TILE * (d + 1)) * sizeof(float), stream>>>(
+            nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_items, Ie, ldi, d, k, item_offset, p.mask_ptr, mitems,
+            p.flags, out_idx + r0 * k, out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
     }
     return 1;
 }
 
 }  // namespace mmrec
+
+// Diagnostic (synchronises the device): rows of the LAST row block of the last mmrec_score_topk_f32 call on this
+// workspace that were handed to the exact kernel.  -1 if the fused path does not apply to this shape.
+extern "C" int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz) {
+    using namespace mmrec;
+    if (!score_fused_supported(B, n_items, d, k) || !ws) return -1;
+    const FzPlan P = fz_plan(B, n_items, d, k, mask_nnz);
+    const char* base = (const char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    const int64_t nb = B % P.rows_blk ? B % P.rows_blk : P.rows_blk;
+    int32_t* h = (int32_t*)malloc((size_t)nb * 4);
+    if (!h || cudaMemcpy(h, base + P.off_flags, (size_t)nb * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { free(h); return -1; }
+    int64_t n = 0;
+    for (int64_t i = 0; i < nb; ++i) n += h[i] != 0;
+    free(h);
+    return n;
+}

@@ -395,6 +395,12 @@ def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0):
     return val, idx
 
 
+def fused_fallback_rows(B, n_items, d, k, mask_nnz, device) -> int:
+    """Diagnostic: how many rows of the last fused score_topk call went through the exact fp32 kernel."""
+    ws = _ws_cache.get(("score_topk", device.index))
+    return -1 if ws is None else int(_lib.load().mmrec_debug_fused_fallback_rows(_ptr(ws), B, n_items, d, k, mask_nnz))
+
+
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor):
     """Merge per-shard top-k lists [parts, B, k] into the global top-k [B, k] (SURVEY.md 8e eval collective)."""
     _need_cuda(vals, idx)
