@@ -35,8 +35,10 @@ struct FusedParams {
     int32_t* flags;                     // [B] fallback flags
 };
 
+constexpr int FZ_STASH = 16;            // per-row ring of the current tile's passing values (feeds the histogram)
+
 struct FzSmem {
-    uint32_t u_hi, u_lo, slab0, hist, bars, tmem_ptr, total;
+    uint32_t u_hi, u_lo, slab0, hist, stash, bars, tmem_ptr, total;
     int stages;
 };
 __host__ __device__ inline FzSmem fz_smem(int KP) {
@@ -45,7 +47,8 @@ __host__ __device__ inline FzSmem fz_smem(int KP) {
     L.stages = KP >= 128 ? 2 : 4;
     L.u_hi = 0; L.u_lo = u_bytes; L.slab0 = 2 * u_bytes;
     L.hist = L.slab0 + L.stages * TC_SLAB_BYTES;
-    L.bars = L.hist + FZ_NB * TC_M * 2;
+    L.stash = L.hist + FZ_NB * TC_M * 2;
+    L.bars = L.stash + FZ_STASH * TC_M * 4;
     L.tmem_ptr = L.bars + 16 * 8;
     L.total = L.tmem_ptr + 16;
     return L;
@@ -138,23 +141,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
         const int64_t row = (int64_t)ut * TC_M + rl;
         const bool live = row < p.B;
         uint16_t* hist = reinterpret_cast<uint16_t*>(smem + L.hist);   // [bin][row]
+        float* stash = reinterpret_cast<float*>(smem + L.stash);       // [slot][row]
         int need = p.k;
         if (live && p.mask_ptr) need += p.mask_ptr[row + 1] - p.mask_ptr[row];
         float2* cand = p.cand + ((int64_t)(live ? row : 0) * p.n_splits + sp) * p.cap;
-        float thr = 0.f, lo = 0.f, scale = 0.f, width = 0.f;
-        int cnt = 0, bad = 0;
+        float thr = INFINITY, lo = 0.f, scale = 0.f, width = 1.f;
+        int cnt = 0, ns = 0, bad = 0;
+        const int n_items32 = (int)p.n_items;
 
         auto bin_of = [&](float v) -> int {
             int b = (int)((v - lo) * scale);
             return b < 0 ? 0 : (b > FZ_NB - 1 ? FZ_NB - 1 : b);
-        };
-        bool cert = false;                                          // >= need candidates counted above thr
-        auto consider = [&](float v, int col) {                     // v >= thr already established
-            if (cnt < p.cap) cand[cnt] = make_float2(v, __int_as_float(col));
-            else bad = 1;
-            ++cnt;
-            uint16_t& h = hist[bin_of(v) * TC_M + rl];
-            if (h < 0xffff) ++h;
         };
 
         for (int it = it0, t = 0; it < it1; ++it, ++t) {
@@ -163,27 +160,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
             fence_after_sync();
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_N;
             const int col_base = it * TC_N;
-            const bool partial = (int64_t)col_base + TC_N > p.n_items;
+            const int n_valid = n_items32 - col_base;                // columns of this tile inside the catalogue (>= 256: all)
             if (t == 0) {
-                // seed: thr0 = min of the 32-column group maxima, max0 = row maximum of the tile
-                float gmin = INFINITY, gmax = -INFINITY;
+                // Seed.  gm[] = maxima of the 32 groups of 8 columns; thr0 = the r-th largest of them, so about r of the
+                // 256 scores of this tile pass.  r aims at ~2.5x the share the row finally needs (need / n_items) and is
+                // at least 8: with 4-5 item splits the row threshold (max over splits) then still leaves >= need items
+                // above it in all but a fraction of a percent of the rows (those go to the exact kernel).
+                float gm[32];
 #pragma unroll 1
                 for (int c8 = 0; c8 < TC_N / 32; ++c8) {
                     uint32_t v[32];
                     tmem_ld_32x32(tbase + c8 * 32, v);
                     tmem_ld_wait();
-                    float m = -INFINITY;
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float x = (c8 * 32 + gq * 8 + j < n_valid) ? __uint_as_float(v[gq * 8 + j]) : -INFINITY;
+                            m = fmaxf(m, x);
+                        }
+#pragma unroll
+                        for (int s2 = 0; s2 < 8; ++s2)               // static register index: gm[c8*4+gq] = m
+                            if (s2 == c8) gm[s2 * 4 + gq] = m;
+                    }
+                }
+                float gmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) gmax = fmaxf(gmax, gm[j]);
+                int r = (int)ceilf(2.5f * (float)need * 256.f / (float)p.n_items);
+                r = r < 8 ? 8 : (r > 32 ? 32 : r);
+                float cur = gmax;
+                for (int i = 1; i < r; ++i) {                        // peel off the i-th largest (one instance at a time)
+                    float nxt = -INFINITY;
+                    bool removed = false;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(v[j]);
-                        if (partial && (int64_t)col_base + c8 * 32 + j >= p.n_items) x = -INFINITY;
-                        m = fmaxf(m, x);
+                        if (!removed && gm[j] == cur) { gm[j] = -INFINITY; removed = true; }
+                        nxt = fmaxf(nxt, gm[j]);
                     }
-                    if (m > -INFINITY) { gmin = fminf(gmin, m); gmax = fmaxf(gmax, m); }
+                    cur = nxt;
                 }
-                thr = lo = gmin;
-                width = (gmax - gmin) * (2.0f / FZ_NB);
-                if (!(width > 0.f) || !(gmin > -INFINITY) || !(gmax < INFINITY)) { bad = 1; width = 1.f; lo = 0.f; thr = INFINITY; }
+                thr = lo = cur;
+                width = (gmax - cur) * (1.0f / 16.f);
+                if (!(width > 0.f) || !(cur > -INFINITY) || !(gmax < INFINITY)) { bad = 1; width = 1.f; lo = 0.f; thr = INFINITY; }
                 if (!live) thr = INFINITY;                          // padding rows: nothing passes, nothing is written
                 scale = 1.0f / width;
 #pragma unroll
@@ -194,30 +214,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
                 uint32_t v[32];
                 tmem_ld_32x32(tbase + c8 * 32, v);
                 tmem_ld_wait();
+                if (n_valid < TC_N) {                                // last, partial tile only
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c8 * 32 + j >= n_valid) v[j] = 0xff800000u;   // -inf
+                }
                 float m = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (partial && (int64_t)col_base + c8 * 32 + j >= p.n_items) v[j] = 0xff800000u;   // -inf
-                    m = fmaxf(m, __uint_as_float(v[j]));
-                }
+                for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
                 if (m >= thr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float x = __uint_as_float(v[j]);
-                        if (x >= thr) consider(x, col_base + c8 * 32 + j);
+                        if (x >= thr) {                              // the hit path is kept to two stores
+                            if (cnt < p.cap) cand[cnt] = make_float2(x, __int_as_float(col_base + c8 * 32 + j));
+                            stash[(ns & (FZ_STASH - 1)) * TC_M + rl] = x;
+                            ++cnt; ++ns;
+                        }
                     }
                 }
             }
             // accumulator drained: hand the TMEM buffer back before the (SMEM-only) threshold update
             fence_before_sync();
             mbar_arrive(bar + (11 + buf) * 8);
-            // raise the threshold to the highest bin edge that keeps `need` candidates above it
+            if (cnt > p.cap) bad = 1;
+            // histogram of this tile's passing values (at most FZ_STASH of them are counted: undercounting only
+            // makes the threshold rise later)
+            {
+                const int n = ns < FZ_STASH ? ns : FZ_STASH;
+                for (int i = 0; i < n; ++i) {
+                    const float x = stash[i * TC_M + rl];
+                    if (x >= thr) { uint16_t& h = hist[bin_of(x) * TC_M + rl]; if (h < 0xffff) ++h; }
+                }
+                ns = 0;
+            }
+            // raise the threshold to the highest bin edge that keeps `need` counted candidates above it
             int c = 0, b = FZ_NB - 1;
             for (; b >= 0; --b) {
                 c += hist[b * TC_M + rl];
                 if (c >= need) break;
             }
-            cert = b >= 0;
             if (b > 0) {
                 const float edge = lo + (float)b * width;
                 const float safe = edge - 2e-6f * fmaxf(fmaxf(fabsf(edge), fabsf(lo)), width);   // bin_of() rounding slack
@@ -241,7 +277,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
             // (a split that never collected `need` candidates keeps a low threshold; the select kernel certifies the
             // row globally, see there)
             if (bad) atomicOr(p.flags + row, 1);
-            (void)cert;
         } else if (live) {
             p.cnt[row * p.n_splits + sp] = 0;
             p.thr[row * p.n_splits + sp] = -INFINITY;
@@ -323,14 +358,15 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
         if (threadIdx.x == 0) flags[row] = 1;
         return;
     }
-    int n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    for (int t = n + threadIdx.x; t < n2; t += blockDim.x) fin[t] = 0;
-    fz_bitonic_desc(fin, n2);
-    for (int t = threadIdx.x; t < k; t += blockDim.x) {
-        const uint64_t c = fin[t];
-        out_idx[row * k + t] = (int64_t)(uint32_t)(~(uint32_t)c) + item_offset;
-        out_val[row * k + t] = key_float((uint32_t)(c >> 32));
+    // composites are unique (item index in the low word): rank = number of larger composites = output position
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const uint64_t me = fin[t];
+        int rank = 0;
+        for (int u = 0; u < n; ++u) rank += fin[u] > me;
+        if (rank < k) {
+            out_idx[row * k + rank] = (int64_t)(uint32_t)(~(uint32_t)me) + item_offset;
+            out_val[row * k + rank] = key_float((uint32_t)(me >> 32));
+        }
     }
 }
 
@@ -452,7 +488,8 @@ static FzPlan fz_plan(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz
     P.n_ut = (P.rows_blk + TC_M - 1) / TC_M;
     P.n_it = (n_items + TC_N - 1) / TC_N;
     const int sms = sm_count();
-    int splits = (int)((sms + P.n_ut - 1) / P.n_ut);
+    int splits = (int)(sms / P.n_ut);            // user tiles x item splits <= SM count: one wave, no tail
+    if (splits < 1) splits = 1;
     if (splits > P.n_it) splits = (int)P.n_it;
     // every split must see enough items to fill a top-(k+m) list comfortably
     while (splits > 1 && (P.n_it / splits) * TC_N < 8 * (int64_t)k + 512) --splits;

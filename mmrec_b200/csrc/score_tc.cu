@@ -194,7 +194,7 @@ int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
     p.B = B; p.n_items = n_items; p.S = S; p.ldS = ldS;
     // fill the machine: user tiles x item splits ~ a multiple of the SM count
     const int sms = sm_count();
-    int splits = (int)((sms + n_ut - 1) / n_ut);
+    int splits = (int)(sms / n_ut);                // user tiles x item splits <= SM count: one wave, no tail
     if (splits > n_it) splits = (int)n_it;
     if (splits < 1) splits = 1;
     p.tiles_per_split = (int)((n_it + splits - 1) / splits);

@@ -10,13 +10,19 @@ from mmrec_b200.utils import synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="baby"); ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--reps", type=int, default=20); ap.add_argument("--d", type=int, default=0)
+ap.add_argument("--uniform", action="store_true", help="uniform item popularity (no heavy rows): isolates the cost of the power-law tail")
 ap.add_argument("--users", type=int, default=0); ap.add_argument("--items", type=int, default=0); ap.add_argument("--edges", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 U, I, E, d, _ = synth.SHAPES[a.workload]
 U, I, E, d = a.users or U, a.items or I, a.edges or E, a.d or d
-g = synth.make_graph(U, I, E, 0)
-tu, ti = g.train
+if a.uniform:
+    rng = np.random.default_rng(0)
+    key = np.unique(rng.integers(0, U, int(E * 1.02)) * I + rng.integers(0, I, int(E * 1.02)))
+    tu, ti = key // I, key % I
+else:
+    g = synth.make_graph(U, I, E, 0)
+    tu, ti = g.train
 n = U + I
 rows_, cols_, vals_ = graph.norm_adj_entries(tu, ti, U, I)
 def build(seg):
