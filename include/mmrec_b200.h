@@ -57,14 +57,17 @@ int mmrec_csr_from_coo(int64_t nnz, const int64_t* row, const int64_t* col, cons
                        int32_t* rowptr, int32_t* colidx, float* vals, int64_t* nnz_out,
                        void* ws, size_t ws_bytes, void* stream);
 
-/* Work plan for mmrec_spmm_f32: rows longer than `seg` non-zeros are split into segments so that
- * the power-law item rows do not serialise on one warp.
- *   tasks      int32[4 * max_tasks]  {row, begin, end, split_id(-1 = whole row)}, sorted longest first
+/* Work plan for mmrec_spmm_f32.  A task is a whole row or, for rows longer than `seg` non-zeros, one segment of it.
+ * Tasks longer than `light_max` are run by a whole CTA (its lane groups split the task and reduce through shared
+ * memory), the others by one lane group each -- the power-law item rows neither serialise on one warp nor sit on
+ * the critical path.
+ *   tasks      int32[4 * max_tasks]  {row, begin, end, split_id(-1 = whole row)}, sorted longest first, so the
+ *                                    CTA-run tasks are the first counts[4] entries
  *   split_rows int32[4 * max_split]  {first_slot, n_seg, row_begin, seg}
- *   counts     int64[4] on the device: {n_tasks, n_split_rows, n_slots, longest_row}
+ *   counts     int64[8] on the device: {n_tasks, n_split_rows, n_slots, longest_row, n_cta_tasks, 0, 0, 0}
  * max_tasks = n_rows + nnz / seg + 1 and max_split = nnz / seg + 1 are always enough. */
 size_t mmrec_spmm_plan_workspace_bytes(int64_t n_rows, int64_t max_tasks);
-int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, int64_t max_tasks,
+int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, int light_max, int64_t max_tasks,
                     int32_t* tasks, int32_t* split_rows, int64_t* counts,
                     void* ws, size_t ws_bytes, void* stream);
 
@@ -89,7 +92,7 @@ int mmrec_bipartite_norm_f32(int64_t n_edges, const int64_t* users, const int64_
  *   if acc_out:  acc_out[r,:] = ((acc_in ? acc_in[r,:] : 0) + y[r,:]) / acc_div
  *
  * acc_in may alias acc_out.  d in {32, 64, 128, 256} runs the vectorised kernel, any other d >= 1
- * the generic one.  tasks/n_tasks/split_rows/counters/partial come from mmrec_spmm_plan
+ * the generic one.  tasks/n_tasks/n_cta_tasks/split_rows/counters/partial come from mmrec_spmm_plan
  * (counters: int32[n_split_rows], zero on entry and zero again on exit; partial:
  * fp32[n_slots * d]); tasks == NULL selects one warp per row.  Summation order is fixed, so the
  * result is bit-reproducible run to run.
@@ -98,7 +101,7 @@ int mmrec_bipartite_norm_f32(int64_t n_edges, const int64_t* users, const int64_
 int mmrec_spmm_set_lanes(int lanes_per_row);
 int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d,
                    const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                   const int32_t* tasks, int64_t n_tasks, const int32_t* split_rows,
+                   const int32_t* tasks, int64_t n_tasks, int64_t n_cta_tasks, const int32_t* split_rows,
                    int32_t* counters, float* partial,
                    const float* X, int64_t ldx,
                    float* Y, int64_t ldy,

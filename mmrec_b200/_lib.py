@@ -21,11 +21,11 @@ PROTOTYPES = {
     "mmrec_csr_from_coo_workspace_bytes": (_sz, [_i64, _i64]),
     "mmrec_csr_from_coo": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "mmrec_spmm_plan_workspace_bytes": (_sz, [_i64, _i64]),
-    "mmrec_spmm_plan": (_i32, [_i64, _p, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
+    "mmrec_spmm_plan": (_i32, [_i64, _p, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
     "mmrec_bipartite_norm_workspace_bytes": (_sz, [_i64, _i64]),
     "mmrec_bipartite_norm_f32": (_i32, [_i64, _p, _p, _i64, _i64, _f32, _p, _p, _sz, _p]),
     "mmrec_spmm_set_lanes": (_i32, [_i32]),
-    "mmrec_spmm_f32": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64,
+    "mmrec_spmm_f32": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64,
                               _f32, _p, _i64, _p]),
     "mmrec_project_f32": (_i32, [_i64, _p, _p, _i64, _i64, _p, _p, _i32, _i32, _p, _i64, _p]),
     "mmrec_score_set_path": (_i32, [_i32]),

@@ -102,7 +102,7 @@ __global__ void plan_count_kernel(int64_t n_rows, const int32_t* __restrict__ ro
     nt[r] = t; ns[r] = s; nl[r] = l;
 }
 
-__global__ void plan_fill_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr, int seg,
+__global__ void plan_fill_kernel(int64_t n_rows, const int32_t* __restrict__ rowptr, int seg, int light_max,
                                  const int32_t* __restrict__ t_off, const int32_t* __restrict__ s_off,
                                  const int32_t* __restrict__ l_off, const int* __restrict__ longest,
                                  int4* __restrict__ tasks, uint32_t* __restrict__ keys, int4* __restrict__ split_rows,
@@ -115,6 +115,16 @@ __global__ void plan_fill_kernel(int64_t n_rows, const int32_t* __restrict__ row
     int b = rowptr[r], e = rowptr[r + 1];
     int nt = t_off[r + 1] - t_off[r];
     int t0 = t_off[r];
+    // tasks longer than light_max are run by a whole CTA; sorted longest-first they form a prefix of the list
+    {
+        int heavy = 0;
+        for (int j = 0; j < nt; ++j) {
+            int sb = b + j * seg;
+            int se = (nt == 1) ? e : (sb + seg < e ? sb + seg : e);
+            heavy += (se - sb) > light_max;
+        }
+        if (heavy) atomicAdd((unsigned long long*)(counts + 4), (unsigned long long)heavy);
+    }
     if (nt == 1) {
         tasks[t0] = make_int4((int)r, b, e, -1);
         keys[t0] = (uint32_t)(seg - (e - b));          // ascending key = longest task first
@@ -133,7 +143,7 @@ __global__ void plan_fill_kernel(int64_t n_rows, const int32_t* __restrict__ row
 __global__ void plan_pad_kernel(int64_t max_tasks, uint32_t* __restrict__ keys, int4* __restrict__ tasks) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= max_tasks) return;
-    keys[t] = 255u;                                    // unused slots sort behind every real task
+    keys[t] = 4095u;                                   // unused slots sort behind every real task
     tasks[t] = make_int4(-1, 0, 0, -1);
 }
 
@@ -224,7 +234,7 @@ PlanWs plan_ws_layout(int64_t n_rows, int64_t max_tasks, void* base) {
     size_t scan_bytes = 0, sort_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int64_t)n);
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int4*)nullptr,
-                                    (int4*)nullptr, (int64_t)m, 0, 8);
+                                    (int4*)nullptr, (int64_t)m, 0, 12);
     w.cub_bytes = scan_bytes > sort_bytes ? scan_bytes : sort_bytes;
     char* p = (char*)base;
     size_t off = 0;
@@ -244,11 +254,14 @@ extern "C" size_t mmrec_spmm_plan_workspace_bytes(int64_t n_rows, int64_t max_ta
     return plan_ws_layout(n_rows, max_tasks, nullptr).total;
 }
 
-extern "C" int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, int64_t max_tasks, int32_t* tasks,
-                               int32_t* split_rows, int64_t* counts, void* ws, size_t ws_bytes, void* stream_) {
+extern "C" int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, int light_max, int64_t max_tasks,
+                               int32_t* tasks, int32_t* split_rows, int64_t* counts, void* ws, size_t ws_bytes,
+                               void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    MMREC_CHECK_ARG(n_rows >= 0 && seg >= 32 && seg <= 254 && max_tasks >= n_rows && rowptr && tasks && split_rows && counts,
-                    "spmm_plan: bad argument (need 32 <= seg <= 254, max_tasks >= n_rows)");
+    MMREC_CHECK_ARG(n_rows >= 0 && seg >= 32 && seg <= 4000 && light_max >= 1 && max_tasks >= n_rows && rowptr && tasks &&
+                        split_rows && counts,
+                    "spmm_plan: bad argument (need 32 <= seg <= 4000, light_max >= 1, max_tasks >= n_rows)");
+    MMREC_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int64_t), stream));
     PlanWs w = plan_ws_layout(n_rows, max_tasks, ws);
     if (ws_bytes < w.total || !ws) {
         set_error("spmm_plan: workspace %zu < %zu", ws_bytes, w.total);
@@ -269,12 +282,12 @@ extern "C" int mmrec_spmm_plan(int64_t n_rows, const int32_t* rowptr, int seg, i
         plan_pad_kernel<<<(unsigned)((max_tasks + T - 1) / T), T, 0, stream>>>(max_tasks, w.keys_a, w.tasks_tmp);
         MMREC_LAUNCH_CHECK();
     }
-    plan_fill_kernel<<<(unsigned)nb, T, 0, stream>>>(n_rows, rowptr, seg, w.t_off, w.s_off, w.l_off, w.longest,
+    plan_fill_kernel<<<(unsigned)nb, T, 0, stream>>>(n_rows, rowptr, seg, light_max, w.t_off, w.s_off, w.l_off, w.longest,
                                                     w.tasks_tmp, w.keys_a, (int4*)split_rows, counts);
     MMREC_LAUNCH_CHECK();
     if (max_tasks > 0) {   // longest tasks first: homogeneous work inside a warp, heavy rows never in the tail
         tmp = w.cub_bytes;
-        MMREC_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_a, w.keys_b, w.tasks_tmp, (int4*)tasks, max_tasks, 0, 8,
+        MMREC_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_a, w.keys_b, w.tasks_tmp, (int4*)tasks, max_tasks, 0, 12,
                                                    stream));
     }
     return MMREC_OK;

@@ -35,10 +35,10 @@ struct FusedParams {
     int32_t* flags;                     // [B] fallback flags
 };
 
-constexpr int FZ_STASH = 16;            // per-row ring of the current tile's passing values (feeds the histogram)
+constexpr int FZ_SCRATCH_BYTES = 4 * 32 * 32 * 4;   // per epilogue warp: one 32 x 32 chunk, thread-private columns
 
 struct FzSmem {
-    uint32_t u_hi, u_lo, slab0, hist, stash, bars, tmem_ptr, total;
+    uint32_t u_hi, u_lo, slab0, hist, scratch, bars, tmem_ptr, total;
     int stages;
 };
 __host__ __device__ inline FzSmem fz_smem(int KP) {
@@ -47,8 +47,8 @@ __host__ __device__ inline FzSmem fz_smem(int KP) {
     L.stages = KP >= 128 ? 2 : 4;
     L.u_hi = 0; L.u_lo = u_bytes; L.slab0 = 2 * u_bytes;
     L.hist = L.slab0 + L.stages * TC_SLAB_BYTES;
-    L.stash = L.hist + FZ_NB * TC_M * 2;
-    L.bars = L.stash + FZ_STASH * TC_M * 4;
+    L.scratch = L.hist + FZ_NB * TC_M * 2;
+    L.bars = L.scratch + FZ_SCRATCH_BYTES;
     L.tmem_ptr = L.bars + 16 * 8;
     L.total = L.tmem_ptr + 16;
     return L;
@@ -141,12 +141,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
         const int64_t row = (int64_t)ut * TC_M + rl;
         const bool live = row < p.B;
         uint16_t* hist = reinterpret_cast<uint16_t*>(smem + L.hist);   // [bin][row]
-        float* stash = reinterpret_cast<float*>(smem + L.stash);       // [slot][row]
+        // this thread's column of its warp's chunk scratch: sc[j * 32] is value j of the current chunk (dynamic index)
+        float* sc = reinterpret_cast<float*>(smem + L.scratch) + (warp & 3) * 1024 + lane;
         int need = p.k;
         if (live && p.mask_ptr) need += p.mask_ptr[row + 1] - p.mask_ptr[row];
         float2* cand = p.cand + ((int64_t)(live ? row : 0) * p.n_splits + sp) * p.cap;
         float thr = INFINITY, lo = 0.f, scale = 0.f, width = 1.f;
-        int cnt = 0, ns = 0, bad = 0;
+        int cnt = 0, bad = 0;
         const int n_items32 = (int)p.n_items;
 
         auto bin_of = [&](float v) -> int {
@@ -219,18 +220,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
                     for (int j = 0; j < 32; ++j)
                         if (c8 * 32 + j >= n_valid) v[j] = 0xff800000u;   // -inf
                 }
-                float m = -INFINITY;
+                // Branch-free filter: one bit per value.  Rows (= lanes) hit at different columns, so a per-value branch
+                // would run its body for almost every column; instead the hits are walked per lane afterwards.
+                uint32_t hits = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-                if (m >= thr) {
+                for (int j = 0; j < 32; ++j) hits |= (__uint_as_float(v[j]) >= thr ? 1u : 0u) << j;
+                if (__any_sync(0xffffffffu, hits != 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = __uint_as_float(v[j]);
-                        if (x >= thr) {                              // the hit path is kept to two stores
-                            if (cnt < p.cap) cand[cnt] = make_float2(x, __int_as_float(col_base + c8 * 32 + j));
-                            stash[(ns & (FZ_STASH - 1)) * TC_M + rl] = x;
-                            ++cnt; ++ns;
-                        }
+                    for (int j = 0; j < 32; ++j) sc[j * 32] = __uint_as_float(v[j]);   // own column only: no sync needed
+                    while (hits) {
+                        const int j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const float x = sc[j * 32];
+                        if (cnt < p.cap) cand[cnt] = make_float2(x, __int_as_float(col_base + c8 * 32 + j));
+                        ++cnt;
+                        uint16_t& h = hist[bin_of(x) * TC_M + rl];
+                        if (h < 0xffff) ++h;
                     }
                 }
             }
@@ -238,16 +243,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
             fence_before_sync();
             mbar_arrive(bar + (11 + buf) * 8);
             if (cnt > p.cap) bad = 1;
-            // histogram of this tile's passing values (at most FZ_STASH of them are counted: undercounting only
-            // makes the threshold rise later)
-            {
-                const int n = ns < FZ_STASH ? ns : FZ_STASH;
-                for (int i = 0; i < n; ++i) {
-                    const float x = stash[i * TC_M + rl];
-                    if (x >= thr) { uint16_t& h = hist[bin_of(x) * TC_M + rl]; if (h < 0xffff) ++h; }
-                }
-                ns = 0;
-            }
             // raise the threshold to the highest bin edge that keeps `need` counted candidates above it
             int c = 0, b = FZ_NB - 1;
             for (; b >= 0; --b) {
@@ -371,24 +366,162 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
 }
 
 // ------------------------------------------------------------------------------------------------------
-// exact fp32 rows (flagged only): the row's scores are recomputed per sweep with the fmaf chain of the CUDA-core GEMM,
-// masked and radix-selected -- the same contract as mmrec_topk_rows_f32, no score matrix
+// exact fp32 rows (flagged only).  Three small kernels, all of which exit at once for rows that are not flagged:
+//   exact_slots  : flagged rows take a slot in the key scratch (atomic counter)
+//   exact_keys   : EX_SPLIT CTAs per flagged row recompute its scores with the fmaf chain of the CUDA-core GEMM
+//                  (k ascending, items staged through shared memory so the reads are coalesced), apply the mask and
+//                  store order-preserving keys
+//   exact_select : radix select + ordered tie gather + sort, the contract of mmrec_topk_rows_f32
+// The scratch holds `cap_rows` rows; when more rows are flagged the host runs the pair in rounds.
 // ------------------------------------------------------------------------------------------------------
-constexpr int EX_TILE = 256;   // items staged per tile = threads per CTA
+constexpr int EX_SPLIT = 16;
 
-__global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t* __restrict__ users, const float* __restrict__ Ue,
-                                                        int64_t ldu, int64_t n_items, const float* __restrict__ Ie, int64_t ldi,
-                                                        int d, int k, int64_t item_offset, const int32_t* __restrict__ mask_ptr,
-                                                        const int32_t* __restrict__ mask_items, const int32_t* __restrict__ flags,
-                                                        int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+constexpr int EX_SLOTS = 128;           // flagged rows served by the cached-key kernels per row block
+
+__global__ void exact_slots_kernel(int64_t B, const int32_t* __restrict__ flags, int32_t* __restrict__ slot, int32_t* __restrict__ counter,
+                                   int32_t* __restrict__ row_of_slot) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    int sl = -1;
+    if (flags[r]) {
+        sl = atomicAdd(counter, 1);
+        if (sl < EX_SLOTS) row_of_slot[sl] = (int32_t)r;
+    }
+    slot[r] = sl;
+}
+
+__global__ void __launch_bounds__(256) exact_keys_kernel(const int64_t* __restrict__ users, const float* __restrict__ Ue, int64_t ldu,
+                                                         int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int d,
+                                                         const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
+                                                         const int32_t* __restrict__ counter, const int32_t* __restrict__ row_of_slot,
+                                                         int tile_rows, unsigned* __restrict__ keys) {
+    extern __shared__ float ex_sm[];                                 // urow[d] | tile[tile_rows][d + 1]
+    const int sl = blockIdx.x;
+    if (sl >= *counter) return;
+    const int64_t row = row_of_slot[sl];
+    const int tid = threadIdx.x;
+    float* urow = ex_sm;
+    float* tile = ex_sm + d;
+    const int ldt = d + 1;
+    const float* u = Ue + (users ? users[row] : row) * ldu;
+    for (int c = tid; c < d; c += 256) urow[c] = u[c];
+    const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
+    unsigned* out = keys + (int64_t)sl * n_items;
+    for (int64_t i0 = (int64_t)blockIdx.y * tile_rows; i0 < n_items; i0 += (int64_t)gridDim.y * tile_rows) {
+        __syncthreads();
+        const int nt = (int)((n_items - i0) < tile_rows ? (n_items - i0) : tile_rows);
+        for (int e = tid; e < nt * d; e += 256) tile[(e / d) * ldt + (e % d)] = __ldg(Ie + (i0 + e / d) * ldi + (e % d));
+        __syncthreads();
+        if (tid < nt) {
+            float acc = 0.f;
+            for (int c = 0; c < d; ++c) acc = fmaf(urow[c], tile[tid * ldt + c], acc);
+            const int32_t item = (int32_t)(i0 + tid);
+            for (int q = m0; q < m1; ++q)
+                if (mask_items[q] == item) acc = -1e10f;
+            out[i0 + tid] = float_key(acc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) exact_select_kernel(int64_t n_items, int k, int64_t item_offset, const int32_t* __restrict__ counter,
+                                                           const int32_t* __restrict__ row_of_slot, const unsigned* __restrict__ keys_all,
+                                                           int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    __shared__ unsigned hist[256];
+    __shared__ uint64_t sel[1024];
+    __shared__ unsigned s_prefix, s_need, s_count, s_base;
+    __shared__ unsigned warp_tot[8];
+    const int sl = blockIdx.x;
+    if (sl >= *counter) return;
+    const int64_t row = row_of_slot[sl];
+    const unsigned* keys = keys_all + (int64_t)sl * n_items;
+    const int tid = threadIdx.x;
+    unsigned prefix = 0, need = (unsigned)k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const unsigned hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        hist[tid] = 0;
+        __syncthreads();
+        for (int64_t i = tid; i < n_items; i += 256) {
+            const unsigned key = keys[i];
+            if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned cum = 0;
+            int dgt = 255;
+            for (; dgt > 0; --dgt) {
+                if (cum + hist[dgt] >= need) break;
+                cum += hist[dgt];
+            }
+            s_prefix = prefix | ((unsigned)dgt << shift);
+            s_need = need - cum;
+        }
+        __syncthreads();
+        prefix = s_prefix; need = s_need;
+        __syncthreads();
+    }
+    const unsigned kth = prefix;
+    if (tid == 0) { s_count = 0; s_base = 0; }
+    __syncthreads();
+    const unsigned n_gt = (unsigned)k - need;
+    for (int64_t i0 = 0; i0 < n_items; i0 += 256) {
+        const int64_t i = i0 + tid;
+        const unsigned key = i < n_items ? keys[i] : 0u;
+        if (i < n_items && key > kth) { unsigned pos = atomicAdd(&s_count, 1u); sel[pos] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)i); }
+        const bool eq = i < n_items && key == kth;
+        const unsigned bal = __ballot_sync(0xffffffffu, eq);
+        const int lane = tid & 31, wid = tid >> 5;
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        unsigned off = s_base;
+        for (int w = 0; w < wid; ++w) off += warp_tot[w];
+        const unsigned rank = off + __popc(bal & ((1u << lane) - 1u));
+        if (eq && rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~(uint32_t)i);
+        __syncthreads();
+        if (tid == 0) { unsigned tot = 0; for (int w = 0; w < 8; ++w) tot += warp_tot[w]; s_base += tot; }
+        __syncthreads();
+    }
+    int n2 = 1;
+    while (n2 < k) n2 <<= 1;
+    for (int t = k + tid; t < n2; t += 256) sel[t] = 0;
+    fz_bitonic_desc(sel, n2);
+    for (int t = tid; t < k; t += 256) {
+        const uint64_t c = sel[t];
+        out_idx[row * k + t] = (int64_t)(uint32_t)(~(uint32_t)c) + item_offset;
+        out_val[row * k + t] = key_float((uint32_t)(c >> 32));
+    }
+}
+
+constexpr int EX_TILE = 128;   // items staged per tile in the overflow kernel (fits 48 KB of shared memory up to d = 90, opt-in above)
+
+// Overflow path: more rows were flagged than the key scratch has slots (only degenerate inputs, e.g. all scores equal).
+// Each CTA owns 256 consecutive rows and works through those whose slot is >= first_overflow, recomputing the keys
+// in every sweep instead of caching them.
+__global__ void __launch_bounds__(256) exact_overflow_kernel(int64_t B, const int64_t* __restrict__ users, const float* __restrict__ Ue,
+                                                             int64_t ldu, int64_t n_items, const float* __restrict__ Ie, int64_t ldi,
+                                                             int d, int k, int64_t item_offset, const int32_t* __restrict__ mask_ptr,
+                                                             const int32_t* __restrict__ mask_items, const int32_t* __restrict__ slot,
+                                                             int first_overflow, int64_t* __restrict__ out_idx,
+                                                             float* __restrict__ out_val) {
     extern __shared__ float ex_sm[];                                 // urow[d] | tile[EX_TILE][d + 1]
     __shared__ unsigned hist[256];
     __shared__ uint64_t sel[1024];
     __shared__ unsigned s_prefix, s_need, s_count, s_base;
     __shared__ unsigned warp_tot[8];
-    const int64_t row = blockIdx.x;
-    if (!flags[row]) return;
+    __shared__ int todo[256];
+    __shared__ int n_todo;
     const int tid = threadIdx.x;
+    if (tid == 0) n_todo = 0;
+    __syncthreads();
+    {
+        const int64_t r = (int64_t)blockIdx.x * 256 + tid;
+        if (r < B && slot[r] >= first_overflow) todo[atomicAdd(&n_todo, 1)] = (int)r;
+    }
+    __syncthreads();
+    const int n_rows_todo = n_todo;
+    for (int ti = 0; ti < n_rows_todo; ++ti) {
+    __syncthreads();
+    const int64_t row = todo[ti];
     float* urow = ex_sm;
     float* tile = ex_sm + d;
     const int ldt = d + 1;
@@ -467,6 +600,7 @@ __global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t
         out_idx[row * k + t] = (int64_t)(uint32_t)(~(uint32_t)c) + item_offset;
         out_val[row * k + t] = key_float((uint32_t)(c >> 32));
     }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -475,9 +609,10 @@ __global__ void __launch_bounds__(256) exact_row_kernel(int64_t B, const int64_t
 static inline int fz_kp(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
 
 struct FzPlan {
-    int KP, splits, tiles_per_split, cap;
+    int KP, splits, tiles_per_split, cap, cap_rows;
     int64_t n_ut, n_it, rows_blk;
-    size_t off_uhi, off_ulo, off_ihi, off_ilo, off_cand, off_cnt, off_thr, off_flags, off_mptr, off_mcur, off_mitems, off_cub,
+    size_t off_uhi, off_ulo, off_ihi, off_ilo, off_cand, off_cnt, off_thr, off_flags, off_mptr, off_mcur, off_mitems, off_cub, off_slot,
+        off_keys,
         cub_bytes, total;
 };
 
@@ -511,6 +646,9 @@ static FzPlan fz_plan(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int64_t)(B + 1));
     P.cub_bytes = scan_bytes;
     P.off_cub = take(scan_bytes);
+    P.off_slot = take((size_t)(P.rows_blk + 1 + EX_SLOTS) * 4);
+    P.cap_rows = EX_SLOTS;
+    P.off_keys = take((size_t)EX_SLOTS * n_items * 4);   // cached keys of up to EX_SLOTS flagged rows
     P.total = off + 1024;
     return P;
 }
@@ -558,7 +696,8 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
     const FzSmem L = fz_smem(P.KP);
     static bool attr_set = false;
     if (!attr_set) {
-        MMREC_CUDA(cudaFuncSetAttribute(exact_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(exact_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(exact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         MMREC_CUDA(cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
@@ -581,10 +720,29 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         fused_select_kernel<<<(unsigned)nb, 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,
                                                               mitems, p.flags, out_idx + r0 * k, out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
-        exact_row_kernel<<<(unsigned)nb, 256, (size_t)(d + EX_TILE * (d + 1)) * sizeof(float), stream>>>(
-            nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_items, Ie, ldi, d, k, item_offset, p.mask_ptr, mitems,
-            p.flags, out_idx + r0 * k, out_val + r0 * k);
-        MMREC_LAUNCH_CHECK();
+        // rows the filter could not certify: exact fp32 recompute (normally none or a handful per block)
+        {
+            int32_t* slot = (int32_t*)(base + P.off_slot);
+            int32_t* counter = slot + P.rows_blk;
+            int32_t* row_of_slot = counter + 1;
+            unsigned* keys = (unsigned*)(base + P.off_keys);
+            MMREC_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
+            exact_slots_kernel<<<(unsigned)((nb + T - 1) / T), T, 0, stream>>>(nb, p.flags, slot, counter, row_of_slot);
+            MMREC_LAUNCH_CHECK();
+            const int tile_rows = d <= 64 ? 256 : 128;
+            const size_t ex_smem = (size_t)(d + tile_rows * (d + 1)) * sizeof(float);
+            const int64_t* ub = users ? users + r0 : nullptr;
+            const float* ue = users ? Ue : Ue + r0 * ldu;
+            exact_keys_kernel<<<dim3(EX_SLOTS, EX_SPLIT), 256, ex_smem, stream>>>(ub, ue, ldu, n_items, Ie, ldi, d, p.mask_ptr, mitems,
+                                                                                 counter, row_of_slot, tile_rows, keys);
+            MMREC_LAUNCH_CHECK();
+            exact_select_kernel<<<EX_SLOTS, 256, 0, stream>>>(n_items, k, item_offset, counter, row_of_slot, keys, out_idx + r0 * k,
+                                                             out_val + r0 * k);
+            MMREC_LAUNCH_CHECK();
+            exact_overflow_kernel<<<(unsigned)((nb + 255) / 256), 256, (size_t)(d + EX_TILE * (d + 1)) * sizeof(float), stream>>>(
+                nb, ub, ue, ldu, n_items, Ie, ldi, d, k, item_offset, p.mask_ptr, mitems, slot, EX_SLOTS, out_idx + r0 * k, out_val + r0 * k);
+            MMREC_LAUNCH_CHECK();
+        }
     }
     return 1;
 }

@@ -22,7 +22,7 @@ namespace mmrec {
 struct SpmmParams {
     int64_t n_rows, n_cols;
     const int32_t* rowptr; const int32_t* colidx; const float* vals;
-    const int4* tasks; int64_t n_tasks; const int4* split_rows; int32_t* counters; float* partial;
+    const int4* tasks; int64_t n_tasks, n_heavy; const int4* split_rows; int32_t* counters; float* partial;
     const float* X; int64_t ldx;
     float* Y; int64_t ldy;
     const float* acc_in; float* acc_out; int64_t ldacc; float acc_div;
@@ -89,31 +89,187 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, bool on, int 
     }
 }
 
-// Control flow is warp-uniform throughout: the 32/T lane groups of a warp run their tasks in lock step (trip
-// count = longest task of the warp; the plan sorts tasks by length, so neighbours are alike) and everything
-// per-group is predicated.  No shuffles in the gather loop: every lane loads the (column, value) pair it
-// needs -- the T lanes of a group read the same address, which is one broadcast transaction.
+// Gather of one task range [b, b + len) by one lane group: UNR rows of X in flight, the next batch's indices
+// travel while they are.  `maxlen` is the trip bound shared by every group that runs in lock step with this one.
+template <int D, int T>
+__device__ __forceinline__ void spmm_gather(const SpmmParams& p, int b, int len, int maxlen, int l, float4 (&acc)[VecCfg<D, T>::V]) {
+    using C = VecCfg<D, T>;
+    int cj[C::UNR]; float wj[C::UNR];
+#pragma unroll
+    for (int u = 0; u < C::UNR; ++u) {
+        const bool ok = u < len;
+        cj[u] = ok ? __ldg(p.colidx + b + u) : 0;
+        wj[u] = ok ? __ldg(p.vals + b + u) : 0.f;
+    }
+    for (int j0 = 0; j0 < maxlen; j0 += C::UNR) {
+        float4 x[C::UNR][C::V];
+#pragma unroll
+        for (int u = 0; u < C::UNR; ++u) {
+            const bool ok = j0 + u < len;
+#pragma unroll
+            for (int v = 0; v < C::V; ++v)
+                x[u][v] = ok ? ldg4(p.X + (int64_t)cj[u] * p.ldx + (v * T + l) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float wc[C::UNR];
+#pragma unroll
+        for (int u = 0; u < C::UNR; ++u) wc[u] = wj[u];
+#pragma unroll
+        for (int u = 0; u < C::UNR; ++u) {
+            const bool ok = j0 + C::UNR + u < len;
+            cj[u] = ok ? __ldg(p.colidx + b + j0 + C::UNR + u) : 0;
+            wj[u] = ok ? __ldg(p.vals + b + j0 + C::UNR + u) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < C::UNR; ++u) {
+#pragma unroll
+            for (int v = 0; v < C::V; ++v) {
+                acc[v].x = fmaf(wc[u], x[u][v].x, acc[v].x);
+                acc[v].y = fmaf(wc[u], x[u][v].y, acc[v].y);
+                acc[v].z = fmaf(wc[u], x[u][v].z, acc[v].z);
+                acc[v].w = fmaf(wc[u], x[u][v].w, acc[v].w);
+            }
+        }
+    }
+}
+
+// A finished task of a split row: publish the partial, and if this is the last segment of the row to arrive, add
+// the partials in segment order and return true (the caller then runs the epilogue).  Warp-collective (full mask);
+// `split` marks the lane groups that hold such a task.
+template <int D, int T>
+__device__ __forceinline__ bool spmm_split_finish(const SpmmParams& p, bool split, int row, int b, int sid, int l,
+                                                  float4 (&acc)[VecCfg<D, T>::V], float4 (&accin)[VecCfg<D, T>::V]) {
+    using C = VecCfg<D, T>;
+    int4 sr = make_int4(0, 1, 0, 1);
+    int old = -1;
+    bool last = false;
+    if (split) {
+        sr = __ldg(p.split_rows + sid);                     // {first_slot, n_seg, row_begin, seg_len}
+        const int seg = (b - sr.z) / sr.w;
+        float* slot = p.partial + ((int64_t)sr.x + seg) * D;
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(slot + (v * T + l) * 4) = acc[v];
+        __threadfence();
+    }
+    __syncwarp();
+    if (split && l == 0) old = atomicAdd(p.counters + sid, 1);
+    old = __shfl_sync(0xffffffffu, old, 0, T);
+    if (split && old == sr.y - 1) {
+        __threadfence();
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int RB = 8;                               // partials in flight; the order of the adds stays fixed
+        for (int s2 = 0; s2 < sr.y; s2 += RB) {
+            float4 q[RB][C::V];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const float* ps = p.partial + ((int64_t)sr.x + s2 + r) * D;
+#pragma unroll
+                for (int v = 0; v < C::V; ++v)
+                    q[r][v] = (s2 + r < sr.y) ? __ldcg(reinterpret_cast<const float4*>(ps + (v * T + l) * 4))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+#pragma unroll
+                for (int v = 0; v < C::V; ++v) {
+                    acc[v].x += q[r][v].x; acc[v].y += q[r][v].y; acc[v].z += q[r][v].z; acc[v].w += q[r][v].w;
+                }
+            }
+        }
+        if (p.acc_in) {
+#pragma unroll
+            for (int v = 0; v < C::V; ++v)
+                accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
+        }
+        if (l == 0) p.counters[sid] = 0;                    // self-cleaning for the next launch
+        last = true;
+    }
+    __syncwarp();
+    return last;
+}
+
+// Phase 1: the n_heavy longest tasks, one CTA each -- its 256/T lane groups split the task evenly, reduce through
+// shared memory in group order, warp 0 finishes the row.  A 5,000-nnz item row becomes ~10 CTA tasks of one or two
+// load batches per group instead of a chain of dozens of dependent batches on one warp.
+// Phase 2: the remaining (short) tasks, one lane group each, 32/T per warp in lock step: warp-uniform control flow
+// (trip count = longest task of the warp; the plan sorts by length so neighbours are alike), everything per-group
+// predicated, no shuffles in the gather loop (the T lanes of a group read the same (col, val) address = one
+// broadcast transaction).  Warps walk the sorted list boustrophedon, so whoever got the longest tasks in one sweep
+// gets the shortest in the next.
 template <int D, int T>
 __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
     using C = VecCfg<D, T>;
-    const int lane = threadIdx.x & 31;
+    constexpr int G = 256 / T;                              // lane groups per CTA
+    __shared__ __align__(16) float red[G * D];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / T, l = lane % T;
-    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
+    const int64_t n_heavy = p.tasks ? p.n_heavy : 0;
 
-    auto fetch = [&](int64_t t) -> int4 {
-        if (t >= n_work) return make_int4(-1, 0, 0, -1);
-        if (p.tasks) return __ldg(p.tasks + t);
+    // ---------------- phase 1: CTA-cooperative tasks
+    for (int64_t ct = blockIdx.x; ct < n_heavy; ct += gridDim.x) {
+        const int4 tk = __ldg(p.tasks + ct);
+        const int row = tk.x, sid = tk.w;
+        const int len = tk.z - tk.y;
+        const int chunk = (len + G - 1) / G;
+        const int gi = warp * C::GPW + g;
+        const int mb = tk.y + gi * chunk;
+        int mylen = tk.z - mb;
+        mylen = mylen < 0 ? 0 : (mylen > chunk ? chunk : mylen);
+        float4 accin[C::V];
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) accin[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (warp == 0 && g == 0 && p.acc_in && sid < 0) {
+#pragma unroll
+            for (int v = 0; v < C::V; ++v)
+                accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
+        }
+        float4 acc[C::V];
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        spmm_gather<D, T>(p, mb, mylen, chunk, l, acc);
+#pragma unroll
+        for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(red + gi * D + (v * T + l) * 4) = acc[v];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g == 0) {
+                for (int q = 0; q < G; ++q) {               // group order: fixed summation order
+#pragma unroll
+                    for (int v = 0; v < C::V; ++v) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(red + q * D + (v * T + l) * 4);
+                        acc[v].x += r4.x; acc[v].y += r4.y; acc[v].z += r4.z; acc[v].w += r4.w;
+                    }
+                }
+            }
+            bool do_epi = g == 0 && sid < 0;
+            if (sid >= 0) do_epi = spmm_split_finish<D, T>(p, g == 0, row, tk.y, sid, l, acc, accin);
+            spmm_epilogue<D, T>(p, do_epi, row, l, acc, accin);
+        }
+        __syncthreads();
+    }
+
+    // ---------------- phase 2: one lane group per task
+    const int64_t W = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t n_light = n_work - n_heavy;
+    auto slot_of = [&](int64_t it) -> int64_t { return it * W + ((it & 1) ? (W - 1 - w) : w); };   // boustrophedon
+    auto fetch = [&](int64_t slot) -> int4 {
+        const int64_t t = slot * C::GPW + g;
+        if (t >= n_light) return make_int4(-1, 0, 0, -1);
+        if (p.tasks) return __ldg(p.tasks + n_heavy + t);
         return make_int4((int)t, __ldg(p.rowptr + t), __ldg(p.rowptr + t + 1), -1);
     };
-    int4 nxt = fetch(warp0 * C::GPW + g);
-    for (int64_t tw = warp0 * C::GPW; tw < n_work; tw += nwarps * C::GPW) {
+    const int64_t n_slots = (n_light + C::GPW - 1) / C::GPW;
+    const int64_t n_iter = (n_slots + W - 1) / W;                   // the same for every warp of the grid
+    int4 nxt = fetch(slot_of(0));
+    for (int64_t it = 0; it < n_iter; ++it) {
         const int row = nxt.x, b = nxt.y, sid = nxt.w;
         const int len = nxt.z - nxt.y;
         const bool valid = row >= 0;
-        nxt = fetch(tw + nwarps * C::GPW + g);                      // next task's descriptor: in flight during the gather
-        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        nxt = fetch(slot_of(it + 1));                               // next task's descriptor: in flight during the gather
+        const int maxlen = __reduce_max_sync(0xffffffffu, valid ? len : 0);
         float4 accin[C::V];
 #pragma unroll
         for (int v = 0; v < C::V; ++v) accin[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -125,94 +281,11 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
         float4 acc[C::V];
 #pragma unroll
         for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        int cj[C::UNR]; float wj[C::UNR];
-#pragma unroll
-        for (int u = 0; u < C::UNR; ++u) {
-            const bool ok = u < len;
-            cj[u] = ok ? __ldg(p.colidx + b + u) : 0;
-            wj[u] = ok ? __ldg(p.vals + b + u) : 0.f;
-        }
-        for (int j0 = 0; j0 < maxlen; j0 += C::UNR) {
-            float4 x[C::UNR][C::V];
-#pragma unroll
-            for (int u = 0; u < C::UNR; ++u) {
-                const bool ok = j0 + u < len;
-#pragma unroll
-                for (int v = 0; v < C::V; ++v)
-                    x[u][v] = ok ? ldg4(p.X + (int64_t)cj[u] * p.ldx + (v * T + l) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            float wc[C::UNR];
-#pragma unroll
-            for (int u = 0; u < C::UNR; ++u) wc[u] = wj[u];
-            // indices of the next batch travel while this batch's rows of X are in flight
-#pragma unroll
-            for (int u = 0; u < C::UNR; ++u) {
-                const bool ok = j0 + C::UNR + u < len;
-                cj[u] = ok ? __ldg(p.colidx + b + j0 + C::UNR + u) : 0;
-                wj[u] = ok ? __ldg(p.vals + b + j0 + C::UNR + u) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < C::UNR; ++u) {
-#pragma unroll
-                for (int v = 0; v < C::V; ++v) {
-                    acc[v].x = fmaf(wc[u], x[u][v].x, acc[v].x);
-                    acc[v].y = fmaf(wc[u], x[u][v].y, acc[v].y);
-                    acc[v].z = fmaf(wc[u], x[u][v].z, acc[v].z);
-                    acc[v].w = fmaf(wc[u], x[u][v].w, acc[v].w);
-                }
-            }
-        }
+        spmm_gather<D, T>(p, b, valid ? len : 0, maxlen, l, acc);
         bool do_epi = valid && sid < 0;
         const bool split = valid && sid >= 0;
         if (__any_sync(0xffffffffu, split)) {
-            int4 sr = make_int4(0, 1, 0, 1);
-            int old = -1;
-            if (split) {
-                sr = __ldg(p.split_rows + sid);                     // {first_slot, n_seg, row_begin, seg_len}
-                const int seg = (b - sr.z) / sr.w;
-                float* slot = p.partial + ((int64_t)sr.x + seg) * D;
-#pragma unroll
-                for (int v = 0; v < C::V; ++v) *reinterpret_cast<float4*>(slot + (v * T + l) * 4) = acc[v];
-                __threadfence();
-            }
-            __syncwarp();
-            if (split && l == 0) old = atomicAdd(p.counters + sid, 1);
-            old = __shfl_sync(0xffffffffu, old, 0, T);
-            if (split && old == sr.y - 1) {                         // last segment to arrive: reduce in segment order
-                __threadfence();
-#pragma unroll
-                for (int v = 0; v < C::V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                // partial sums are added in segment order (fixed -> reproducible); loads are issued RB at a time so
-                // that a 5,000-nnz row does not pay one L2 round trip per segment
-                constexpr int RB = 8;
-                for (int s2 = 0; s2 < sr.y; s2 += RB) {
-                    float4 q[RB][C::V];
-#pragma unroll
-                    for (int r = 0; r < RB; ++r) {
-                        const float* ps = p.partial + ((int64_t)sr.x + s2 + r) * D;
-#pragma unroll
-                        for (int v = 0; v < C::V; ++v)
-                            q[r][v] = (s2 + r < sr.y) ? __ldcg(reinterpret_cast<const float4*>(ps + (v * T + l) * 4))
-                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int r = 0; r < RB; ++r) {
-#pragma unroll
-                        for (int v = 0; v < C::V; ++v) {
-                            acc[v].x += q[r][v].x; acc[v].y += q[r][v].y; acc[v].z += q[r][v].z; acc[v].w += q[r][v].w;
-                        }
-                    }
-                }
-                if (p.acc_in) {
-#pragma unroll
-                    for (int v = 0; v < C::V; ++v)
-                        accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
-                }
-                if (l == 0) p.counters[sid] = 0;                    // self-cleaning for the next launch
-                do_epi = true;
-            }
-            __syncwarp();
+            if (spmm_split_finish<D, T>(p, split, row, b, sid, l, acc, accin)) do_epi = true;
         }
         spmm_epilogue<D, T>(p, do_epi, row, l, acc, accin);
     }
@@ -265,7 +338,8 @@ static int launch_vec(const SpmmParams& p, cudaStream_t stream) {
     }
     const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
     const int per_block = 8 * (32 / T);
-    int64_t grid = (n_work + per_block - 1) / per_block;
+    int64_t grid = (n_work - p.n_heavy + per_block - 1) / per_block;
+    if (grid < p.n_heavy) grid = p.n_heavy;
     const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     if (grid > cap) grid = cap;
     if (grid < 1) return MMREC_OK;
@@ -297,7 +371,8 @@ extern "C" int mmrec_spmm_set_lanes(int lanes_per_row) {
 }
 
 extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32_t* rowptr, const int32_t* colidx,
-                              const float* vals, const int32_t* tasks, int64_t n_tasks, const int32_t* split_rows,
+                              const float* vals, const int32_t* tasks, int64_t n_tasks, int64_t n_cta_tasks,
+                              const int32_t* split_rows,
                               int32_t* counters, float* partial, const float* X, int64_t ldx, float* Y, int64_t ldy,
                               const float* acc_in, float* acc_out, int64_t ldacc, float acc_div, const float* gate_ref,
                               int64_t ldgate, void* stream_) {
@@ -307,10 +382,11 @@ extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32
     MMREC_CHECK_ARG(rowptr && X && (Y || acc_out), "spmm: null pointer");
     MMREC_CHECK_ARG(ldx >= d && (!Y || ldy >= d) && (!acc_out || ldacc >= d) && (!gate_ref || ldgate >= d), "spmm: leading dimension < d");
     MMREC_CHECK_ARG(acc_div != 0.0f, "spmm: acc_div == 0");
-    MMREC_CHECK_ARG(!tasks || (n_tasks >= 0 && split_rows && counters && partial), "spmm: plan pointers missing");
+    MMREC_CHECK_ARG(!tasks || (n_tasks >= 0 && n_cta_tasks >= 0 && n_cta_tasks <= n_tasks && split_rows && counters && partial),
+                    "spmm: plan pointers missing");
     SpmmParams p;
     p.n_rows = n_rows; p.n_cols = n_cols; p.rowptr = rowptr; p.colidx = colidx; p.vals = vals;
-    p.tasks = (const int4*)tasks; p.n_tasks = n_tasks; p.split_rows = (const int4*)split_rows;
+    p.tasks = (const int4*)tasks; p.n_tasks = n_tasks; p.n_heavy = tasks ? n_cta_tasks : 0; p.split_rows = (const int4*)split_rows;
     p.counters = counters; p.partial = partial; p.X = X; p.ldx = ldx; p.Y = Y; p.ldy = ldy;
     p.acc_in = acc_in; p.acc_out = acc_out; p.ldacc = ldacc; p.acc_div = acc_div; p.gate_ref = gate_ref;
     p.ldgate = ldgate; p.d = d;

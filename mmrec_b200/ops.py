@@ -16,7 +16,8 @@ from ._lib import MMRecError, check
 
 _ws_cache: dict = {}
 import os as _os
-SEG = int(_os.environ.get("MMREC_SPMM_SEG", "64"))   # non-zeros per SpMM task (rows longer than this are split)
+SEG = int(_os.environ.get("MMREC_SPMM_SEG", "512"))        # non-zeros per SpMM task (rows longer than this are split)
+LIGHT_MAX = int(_os.environ.get("MMREC_SPMM_LIGHT", "16"))  # tasks longer than this are run by a whole CTA
 LAUNCHES = 0       # kernels of this library launched so far (bench.py's gpu_launches)
 
 
@@ -65,11 +66,12 @@ class CSR:
     coalesce + COO->CSR conversion ATen performs inside every `torch.sparse.mm` call.
     """
 
-    def __init__(self, n_rows, n_cols, rowptr, colidx, vals, nnz, symmetric=False, seg=SEG):
+    def __init__(self, n_rows, n_cols, rowptr, colidx, vals, nnz, symmetric=False, seg=None, light_max=None):
         self.n_rows, self.n_cols, self.nnz = int(n_rows), int(n_cols), int(nnz)
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
         self.symmetric = symmetric
-        self.seg = seg
+        self.seg = SEG if seg is None else seg
+        self.light_max = LIGHT_MAX if light_max is None else light_max
         self._t: Optional["CSR"] = None
         self._partial = {}
         self._plan()
@@ -77,7 +79,7 @@ class CSR:
     # -- construction ------------------------------------------------------------------------------
     @staticmethod
     def from_coo(row: torch.Tensor, col: torch.Tensor, val: Optional[torch.Tensor], n_rows: int, n_cols: int,
-                 sum_duplicates: bool = True, symmetric: bool = False, seg: int = SEG) -> "CSR":
+                 sum_duplicates: bool = True, symmetric: bool = False, seg=None, light_max=None) -> "CSR":
         _lib.require_device()
         _need_cuda(row, col, val)
         lib = _lib.load()
@@ -96,7 +98,7 @@ class CSR:
                                      _stream()), "mmrec_csr_from_coo")
         _count(6)
         n = int(nnz_out.item())
-        return CSR(n_rows, n_cols, rowptr, colidx[:max(n, 1)], vals[:max(n, 1)], n, symmetric, seg)
+        return CSR(n_rows, n_cols, rowptr, colidx[:max(n, 1)], vals[:max(n, 1)], n, symmetric, seg, light_max)
 
     @staticmethod
     def from_torch_sparse(t: torch.Tensor, symmetric: bool = False) -> "CSR":
@@ -111,13 +113,14 @@ class CSR:
         max_split = self.nnz // self.seg + 1
         tasks = torch.empty(4 * max_tasks, dtype=torch.int32, device=dev)
         split = torch.empty(4 * max_split, dtype=torch.int32, device=dev)
-        counts = torch.zeros(4, dtype=torch.int64, device=dev)
+        counts = torch.zeros(8, dtype=torch.int64, device=dev)
         ws = _ws("plan", lib.mmrec_spmm_plan_workspace_bytes(self.n_rows, max_tasks), dev)
-        check(lib.mmrec_spmm_plan(self.n_rows, _ptr(self.rowptr), self.seg, max_tasks, _ptr(tasks), _ptr(split),
+        check(lib.mmrec_spmm_plan(self.n_rows, _ptr(self.rowptr), self.seg, self.light_max, max_tasks, _ptr(tasks), _ptr(split),
                                   _ptr(counts), _ptr(ws), ws.numel(), _stream()), "mmrec_spmm_plan")
         _count(8)
         c = counts.tolist()
         self.n_tasks, self.n_split, self.n_slots, self.longest_row = int(c[0]), int(c[1]), int(c[2]), int(c[3])
+        self.n_cta_tasks = int(c[4])
         self.tasks = tasks[:4 * max(self.n_tasks, 1)]
         self.split_rows = split[:4 * max(self.n_split, 1)]
         self.counters = torch.zeros(max(self.n_split, 1), dtype=torch.int32, device=dev)
@@ -142,7 +145,7 @@ class CSR:
             return self
         if self._t is None:
             r, c, v = self.coo()
-            self._t = CSR.from_coo(c, r, v, self.n_cols, self.n_rows, False, False, self.seg)
+            self._t = CSR.from_coo(c, r, v, self.n_cols, self.n_rows, False, False, self.seg, self.light_max)
             self._t._t = self
         return self._t
 
@@ -178,7 +181,7 @@ def spmm_raw(A: CSR, X: torch.Tensor, Y: Optional[torch.Tensor] = None, acc_in: 
         raise MMRecError("spmm: nothing to write")
     plan = use_plan and A.n_tasks > 0
     check(lib.mmrec_spmm_f32(A.n_rows, A.n_cols, d, _ptr(A.rowptr), _ptr(A.colidx), _ptr(A.vals),
-                             _ptr(A.tasks) if plan else None, A.n_tasks if plan else 0,
+                             _ptr(A.tasks) if plan else None, A.n_tasks if plan else 0, A.n_cta_tasks if plan else 0,
                              _ptr(A.split_rows) if plan else None, _ptr(A.counters) if plan else None,
                              _ptr(A.partial(d)) if plan else None,
                              _ptr(X), X.stride(0), _ptr(Y), d, _ptr(acc_in), _ptr(acc_out), d, float(acc_div),

@@ -36,7 +36,7 @@ def test_argument_errors_without_a_gpu():
     """Argument validation happens before any CUDA call, so it is testable on a CPU box."""
     from mmrec_b200 import _lib
     lib = _lib.load()
-    assert lib.mmrec_spmm_f32(-1, 0, 64, None, None, None, None, 0, None, None, None, None, 0, None, 0, None, None, 0,
+    assert lib.mmrec_spmm_f32(-1, 0, 64, None, None, None, None, 0, 0, None, None, None, None, 0, None, 0, None, None, 0,
                               1.0, None, 0, None) == -1
     assert b"spmm" in lib.mmrec_last_error()
     assert lib.mmrec_topk_rows_f32(4, 10, None, 10, 11, 0, None, None, None) == -1     # k > n_items

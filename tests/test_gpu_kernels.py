@@ -62,11 +62,13 @@ def test_csr_transpose_and_plan(dev):
     r, c, v = rand_coo(500, 300, 8000, seed=3, dup_frac=0)
     # one very long row so that the plan must split it
     r = torch.cat([r, torch.full((3000,), 7)]); c = torch.cat([c, torch.randint(0, 300, (3000,))]); v = torch.cat([v, torch.rand(3000)])
-    A = CSR.from_coo(r.to(dev), c.to(dev), v.to(dev), 500, 300)
+    A = CSR.from_coo(r.to(dev), c.to(dev), v.to(dev), 500, 300, seg=128)
     assert A.longest_row >= 290 and A.n_split >= 1 and A.n_tasks > 500 and A.n_slots >= 2
     t = A.tasks.cpu().numpy().reshape(-1, 4)
     lens = t[:, 2] - t[:, 1]
     assert lens.max() <= A.seg and lens.sum() == A.nnz
+    assert np.all(np.diff(lens) <= 0)                       # sorted longest first ...
+    assert A.n_cta_tasks == int((lens > A.light_max).sum())   # ... so the CTA-run tasks are a prefix
     At = A.t()
     np.testing.assert_allclose(At.to_dense().cpu().numpy(), A.to_dense().cpu().numpy().T, rtol=0, atol=0)
 

@@ -25,9 +25,9 @@ else:
     tu, ti = g.train
 n = U + I
 rows_, cols_, vals_ = graph.norm_adj_entries(tu, ti, U, I)
-def build(seg):
+def build(seg, light=None):
     return ops.CSR.from_coo(torch.from_numpy(rows_).to(dev), torch.from_numpy(cols_).to(dev), torch.from_numpy(vals_).to(dev),
-                            n, n, sum_duplicates=False, symmetric=True, seg=seg)
+                            n, n, sum_duplicates=False, symmetric=True, seg=seg, light_max=light)
 adj = build(ops.SEG)
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.isfile("MEASURED_PEAKS.json") else 6650.0
 ego = torch.randn(n, d, device=dev) * 0.1
@@ -35,10 +35,10 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 lib = _lib.load()
 print(f"graph {a.workload}: N={n} nnz={adj.nnz} d={d} tasks={adj.n_tasks} split_rows={adj.n_split} longest={adj.longest_row} "
       f"bytes/layer={adj.algorithmic_bytes(d)/1e6:.2f} MB")
-for seg, lanes in [(s_, l_) for s_ in (32, 64, 128, 254) for l_ in (4, 8, 16, 32)]:
+for seg, light, lanes in [(s_, lt_, l_) for s_ in (256, 512, 1024) for lt_ in (8, 16, 32) for l_ in (8, 16)]:
     if lanes and (d % (4 * lanes) or d // (4 * lanes) > 4):
         continue
-    adj = build(seg)
+    adj = build(seg, light)
     lib.mmrec_spmm_set_lanes(lanes)
     for plan in (True,):
         out = None
@@ -58,7 +58,7 @@ for seg, lanes in [(s_, l_) for s_ in (32, 64, 128, 254) for l_ in (4, 8, 16, 32
             if r >= 3: ts.append(e0.elapsed_time(e1) * 1e3 / a.layers)
         us = float(np.median(ts))
         gbs = adj.algorithmic_bytes(d) / us / 1e3
-        print(f"seg={seg:3d} tasks={adj.n_tasks:6d} lanes={lanes:2d} plan={int(plan)}  {us:8.2f} us/layer  {gbs:8.1f} GB/s  frac={gbs/peak:.3f}  edges/s={adj.nnz/us*1e6:.3e}")
+        print(f"seg={seg:4d} light<={light:2d} tasks={adj.n_tasks:6d} cta_tasks={adj.n_cta_tasks:5d} lanes={lanes:2d} plan={int(plan)}  {us:8.2f} us/layer  {gbs:8.1f} GB/s  frac={gbs/peak:.3f}  edges/s={adj.nnz/us*1e6:.3e}")
 lib.mmrec_spmm_set_lanes(0)
 adj = build(ops.SEG)
 # graph replay (no host launch gaps)
