@@ -257,7 +257,7 @@ def run_ours(args):
                   "scored_items_per_sec": score_items / (msC * 1e-3),
                   "projected_rows_per_sec": 2 * I / (msB * 1e-3),
                   "edges_per_step": edges, "scored_items_per_step": score_items,
-                  "wall_s_timed_region": wall, "score_path": os.environ.get("MMREC_SCORE_PATH", "tc")},
+                  "wall_s_timed_region": wall, "score_path": os.environ.get("MMREC_SCORE_PATH", "auto")},
         "roofline": {"kernel": "spmm_vec_kernel<64> (4 launches: 3 x A_hat + mm_adj)", "bound": "hbm",
                      "achieved": spmm_bytes / (msA * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": spmm_bytes / (msA * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],

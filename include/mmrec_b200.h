@@ -97,7 +97,7 @@ int mmrec_bipartite_norm_f32(int64_t n_edges, const int64_t* users, const int64_
  * fp32[n_slots * d]); tasks == NULL selects one warp per row.  Summation order is fixed, so the
  * result is bit-reproducible run to run.
  * ------------------------------------------------------------------------------------------- */
-/* tuning knob: lanes that cooperate on one row (0 = default d/8; a power of two, d/(4*lanes) float4 per lane) */
+/* tuning knob: lanes that cooperate on one row (0 = default min(32, d/4); a power of two, d/(4*lanes) float4 per lane) */
 int mmrec_spmm_set_lanes(int lanes_per_row);
 int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d,
                    const int32_t* rowptr, const int32_t* colidx, const float* vals,
@@ -138,9 +138,11 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
  * mmrec_topk_merge:   merge `parts` sorted lists per user ([parts, B, k] values + indices) into
  *                     one (the per-user top-k reduction across item shards).
  * ------------------------------------------------------------------------------------------- */
-/* arithmetic path of mmrec_score_f32 / mmrec_score_topk_f32: 2 = tcgen05 3xTF32 with the top-k fused into the
- * GEMM epilogue (default), 1 = tcgen05 3xTF32 + separate mask/top-k kernels, 0 = exact fp32 on CUDA cores.
- * env MMREC_SCORE_PATH = simt | tc | fused sets the initial value. */
+/* path of mmrec_score_f32 / mmrec_score_topk_f32 (env MMREC_SCORE_PATH = simt | tc | auto | fused sets the start value):
+ *   0 simt   exact fp32 on CUDA cores
+ *   1 tc     tcgen05 3xTF32 GEMM into an L2-resident score block, then mask + streaming top-k kernels
+ *   2 auto   (default) tc for catalogues up to 64k items, fused beyond (the score block would leave L2)
+ *   3 fused  tcgen05 3xTF32 GEMM with the threshold-filter top-k fused into its epilogue, no score matrix */
 int mmrec_score_set_path(int path);
 size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d);
 int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu,

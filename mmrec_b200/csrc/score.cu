@@ -27,19 +27,26 @@ size_t score_fused_workspace_bytes(int64_t B, int64_t n_items, int d, int k, int
 int mask_apply(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int64_t row0, int64_t B,
                int64_t n_items, int64_t item_offset, float* S, int64_t ldS, cudaStream_t stream);
 
-static int g_score_path = -1;   // -1 unset, 0 simt, 1 tensor cores (unfused top-k), 2 tensor cores + fused top-k
+// -1 unset | 0 simt: exact fp32 CUDA cores | 1 tc: tcgen05 GEMM -> L2-resident score block -> mask -> streaming top-k
+//  2 auto (default): tc while a useful score block stays L2-resident (catalogues up to 64k items), fused beyond
+//  3 fused: tcgen05 GEMM with the threshold-filter top-k in its epilogue (no score matrix at all)
+static int g_score_path = -1;
 static int score_path() {
     if (g_score_path < 0) {
         const char* e = getenv("MMREC_SCORE_PATH");
-        g_score_path = (e && strcmp(e, "simt") == 0) ? 0 : ((e && strcmp(e, "tc") == 0) ? 1 : 2);
+        g_score_path = 2;
+        if (e && strcmp(e, "simt") == 0) g_score_path = 0;
+        if (e && strcmp(e, "tc") == 0) g_score_path = 1;
+        if (e && strcmp(e, "fused") == 0) g_score_path = 3;
     }
     return g_score_path;
 }
+static bool want_fused(int64_t n_items) { return score_path() == 3 || (score_path() == 2 && n_items > 65536); }
 }  // namespace mmrec
 
 using namespace mmrec;
 
-extern "C" int mmrec_score_set_path(int path) { g_score_path = path < 0 ? 0 : (path > 2 ? 2 : path); return MMREC_OK; }
+extern "C" int mmrec_score_set_path(int path) { g_score_path = path < 0 ? 0 : (path > 3 ? 3 : path); return MMREC_OK; }
 
 extern "C" size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d) {
     return score_tc_workspace_bytes(B, n_items, d) + 256;
@@ -91,7 +98,7 @@ extern "C" int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float
         set_error("score_topk: workspace %zu < %zu", ws_bytes, need);
         return MMREC_EWORKSPACE;
     }
-    if (score_path() == 2 && score_fused_workspace_bytes(B, n_items, d, k, mask_nnz) <= ws_bytes) {
+    if (want_fused(n_items) && score_fused_workspace_bytes(B, n_items, d, k, mask_nnz) <= ws_bytes) {
         int r = score_fused(B, users, Ue, ldu, n_items, Ie, ldi, d, mask_nnz, mask_rows, mask_cols, k, item_offset, out_idx,
                             out_val, ws, ws_bytes, (cudaStream_t)stream_);
         if (r != 0) return r < 0 ? r : MMREC_OK;

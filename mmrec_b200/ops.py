@@ -17,7 +17,7 @@ from ._lib import MMRecError, check
 _ws_cache: dict = {}
 import os as _os
 SEG = int(_os.environ.get("MMREC_SPMM_SEG", "512"))        # non-zeros per SpMM task (rows longer than this are split)
-LIGHT_MAX = int(_os.environ.get("MMREC_SPMM_LIGHT", "16"))  # tasks longer than this are run by a whole CTA
+LIGHT_MAX = int(_os.environ.get("MMREC_SPMM_LIGHT", "32"))  # tasks longer than this are run by a whole CTA
 LAUNCHES = 0       # kernels of this library launched so far (bench.py's gpu_launches)
 
 
@@ -324,12 +324,10 @@ def project(table, weight, bias=None, idx=None, l2_normalize=False) -> torch.Ten
 # K3: scoring, mask, top-k
 # ------------------------------------------------------------------------------------------------
 def set_score_path(path):
-    """0 / "simt": exact fp32 CUDA cores; 1 / "tc": tcgen05 3xTF32, unfused top-k; 2 / "fused" (default): tcgen05
-    with the top-k fused into the epilogue.  True/False are accepted as 2/0."""
+    """"simt" (0): exact fp32 CUDA cores; "tc" (1): tcgen05 3xTF32 + mask + streaming top-k kernels; "auto" (2,
+    default): tc up to 64k items, fused beyond; "fused" (3): tcgen05 with the top-k fused into the GEMM epilogue."""
     if isinstance(path, str):
-        path = {"simt": 0, "tc": 1, "fused": 2}[path]
-    elif isinstance(path, bool):
-        path = 2 if path else 0
+        path = {"simt": 0, "tc": 1, "auto": 2, "fused": 3}[path]
     _lib.load().mmrec_score_set_path(int(path))
 
 

@@ -258,7 +258,7 @@ def test_score_and_fused_topk(dev, B, U, I, d, k, path):
             assert gap < 4e-6 * scale, f"row {b}: non-tie mismatch, gap {gap}"
         assert len(bad) <= max(2, B // 20)
     finally:
-        ops.set_score_path("fused")
+        ops.set_score_path("auto")
 
 
 def _ref_topk(ue, ie, users, mask, k):
@@ -277,7 +277,7 @@ def _check_near_tie(idx, ref, ri, scale):
 
 
 def test_fused_topk_edge_cases(dev):
-    """The fused tcgen05 path: heavy users (more masked items than the candidate list holds -> exact kernel),
+    """The fused tcgen05 path (forced): heavy users (more masked items than the candidate list holds -> exact kernel),
     unsorted mask, degenerate (all-equal) scores, ragged sizes, d = 32 / 128."""
     from mmrec_b200 import ops
     ops.set_score_path("fused")
@@ -306,6 +306,7 @@ def test_fused_topk_edge_cases(dev):
     val, idx = ops.score_topk(ue.to(dev), ie.to(dev), None, mask.to(dev), 50)
     ref, (rv, ri) = _ref_topk(ue, ie, torch.arange(130), mask, 50)
     _check_near_tie(idx, ref, ri, ref[ref > -1e9].abs().max().item())
+    ops.set_score_path("auto")
 
 
 def test_score_without_user_index_and_strided_inputs(dev):
@@ -370,8 +371,8 @@ def test_full_size_properties_baby(dev):
     assert not hit.gather(1, idx).any()                                       # masked train positives never returned
     val2, idx2 = ops.score_topk(ue, ie, users, mask, 50)
     assert torch.equal(idx, idx2) and torch.equal(val, val2)                  # idempotent / deterministic
-    ops.set_score_path("tc")                                                  # fused == unfused on the same arithmetic
+    ops.set_score_path("fused")                                               # fused == unfused on the same arithmetic
     val3, idx3 = ops.score_topk(ue, ie, users, mask, 50)
-    ops.set_score_path("fused")
+    ops.set_score_path("auto")
     same = (idx3 == idx).all(dim=1).float().mean().item()
     assert same > 0.99 and (val3 - val).abs().max().item() < 1e-5 * val.abs().max().item() + 1e-9

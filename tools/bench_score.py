@@ -9,7 +9,7 @@ import bench as B
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="baby"); ap.add_argument("--batch", type=int, default=4096)
-ap.add_argument("--reps", type=int, default=10); ap.add_argument("--paths", default="fused,tc,simt")
+ap.add_argument("--reps", type=int, default=10); ap.add_argument("--paths", default="auto,fused,tc,simt")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 wl = B.Workload(a.workload)
@@ -35,4 +35,4 @@ for path in a.paths.split(","):
     agree = "" if ref is None else f" rows identical to {refname}: {(idx == ref).all(dim=1).float().mean().item():.4f}"
     if ref is None: ref, refname = idx, path
     print(f"{path:6s} {us:9.1f} us/batch  {nb*wl.I/us/1e3:8.2f} G items/s  {flops/us/1e6:7.2f} TFLOP/s useful  frac={flops/us/1e6/peak:.3f}  fallback_rows={fb}{agree}")
-ops.set_score_path("fused")
+ops.set_score_path("auto")

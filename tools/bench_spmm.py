@@ -10,6 +10,7 @@ from mmrec_b200.utils import synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="baby"); ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--reps", type=int, default=20); ap.add_argument("--d", type=int, default=0)
+ap.add_argument("--flush", default="write", choices=["none", "write", "read", "write+read"])
 ap.add_argument("--uniform", action="store_true", help="uniform item popularity (no heavy rows): isolates the cost of the power-law tail")
 ap.add_argument("--users", type=int, default=0); ap.add_argument("--items", type=int, default=0); ap.add_argument("--edges", type=int, default=0)
 a = ap.parse_args()
@@ -31,11 +32,17 @@ def build(seg, light=None):
 adj = build(ops.SEG)
 peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"] if os.path.isfile("MEASURED_PEAKS.json") else 6650.0
 ego = torch.randn(n, d, device=dev) * 0.1
-flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+_fbuf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+_rbuf = torch.ones(64 << 20, dtype=torch.float32, device=dev)
+class _Flush:
+    def zero_(self):
+        if "write" in a.flush: _fbuf.zero_()
+        if "read" in a.flush: _rbuf.sum()
+flush = _Flush()
 lib = _lib.load()
 print(f"graph {a.workload}: N={n} nnz={adj.nnz} d={d} tasks={adj.n_tasks} split_rows={adj.n_split} longest={adj.longest_row} "
       f"bytes/layer={adj.algorithmic_bytes(d)/1e6:.2f} MB")
-for seg, light, lanes in [(s_, lt_, l_) for s_ in (256, 512, 1024) for lt_ in (8, 16, 32) for l_ in (8, 16)]:
+for seg, light, lanes in [(s_, lt_, l_) for s_ in (512,) for lt_ in (16, 32) for l_ in (8, 16)]:
     if lanes and (d % (4 * lanes) or d // (4 * lanes) > 4):
         continue
     adj = build(seg, light)
