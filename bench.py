@@ -185,31 +185,53 @@ def run_ours(args):
     tA = tB = tC = 0.0
     sampler = ClockSampler(local)
     torch.cuda.synchronize()
-    launches0 = 0
+
+    # The three sections are captured once into CUDA graphs (static inputs, outputs in the graphs' pool) and replayed:
+    # the kernels of this path run 5-70 us each, shorter than the host's per-op Python/ctypes cost.
+    def sec_a():
+        return propagate()
+
+    def sec_b():
+        return ops.project(vf, Wv, bv), ops.project(tf, Wt, bt)
+
+    state = {}
+
+    def sec_c():
+        return [ops.score_topk(state["u"], state["i"], users, mask, TOPK) for users, mask in batches_dev]
+
+    graphs, n_launch = {}, {}
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(2):                                           # warm every lazy init (occupancy queries, workspaces)
+            state["u"], state["i"] = sec_a(); sec_b(); sec_c()
+        torch.cuda.synchronize()
+        for name, fn in (("a", sec_a), ("b", sec_b), ("c", sec_c)):
+            l0 = ops.LAUNCHES
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=side):
+                out = fn()
+            graphs[name], n_launch[name] = gph, ops.LAUNCHES - l0
+            if name == "a":
+                state["u"], state["i"] = out
+            state["out_" + name] = out
+    torch.cuda.synchronize()
+    launches_per_step = sum(n_launch.values())
     with torch.no_grad():
         for step in range(args.warmup + args.steps):
             if step == args.warmup:
                 torch.cuda.synchronize()
                 sampler.start()
-                launches0 = ops.LAUNCHES
                 wall0 = time.perf_counter()
             flush.zero_()                                            # evict L2 (126 MB) between steps
             e = [ev() for _ in range(6)]
-            e[0].record()
-            u_g, i_g = propagate()
-            e[1].record()
-            e[2].record()
-            pv = ops.project(vf, Wv, bv)
-            pt = ops.project(tf, Wt, bt)
-            e[3].record()
-            e[4].record()
-            outs = [ops.score_topk(u_g, i_g, users, mask, TOPK) for users, mask in batches_dev]
-            e[5].record()
+            e[0].record(); graphs["a"].replay(); e[1].record()
+            e[2].record(); graphs["b"].replay(); e[3].record()
+            e[4].record(); graphs["c"].replay(); e[5].record()
             torch.cuda.synchronize()
             if step >= args.warmup:
                 tA += e[0].elapsed_time(e[1]); tB += e[2].elapsed_time(e[3]); tC += e[4].elapsed_time(e[5])
     wall = time.perf_counter() - wall0
-    launches = ops.LAUNCHES - launches0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop()
     K = args.steps
     msA, msB, msC = tA / K, tB / K, tC / K
@@ -252,20 +274,21 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"FREEDOM synthetic {wl.name}: {U} users, {I} items, {len(wl.tr_u)} train edges, d={d}, "
                                f"{wl.n_layers} UI layers + 1 mm layer, top-{TOPK} over all users, eval batch {EVAL_BATCH}",
-                   "l2": "flushed (512 MiB write) before every step", "parallelism": "1 GPU"},
+                   "l2": "flushed (512 MiB write) before every step", "launch": "each section replayed from a CUDA graph",
+                   "parallelism": "1 GPU"},
         "extra": {"prop_ms": msA, "proj_ms": msB, "score_topk_ms": msC,
                   "scored_items_per_sec": score_items / (msC * 1e-3),
                   "projected_rows_per_sec": 2 * I / (msB * 1e-3),
                   "edges_per_step": edges, "scored_items_per_step": score_items,
                   "wall_s_timed_region": wall, "score_path": os.environ.get("MMREC_SCORE_PATH", "auto")},
-        "roofline": {"kernel": "spmm_vec_kernel<64> (4 launches: 3 x A_hat + mm_adj)", "bound": "hbm",
+        "roofline": {"kernel": "spmm_vec_kernel<64,16> (4 launches: 3 x A_hat + mm_adj)", "bound": "hbm",
                      "achieved": spmm_bytes / (msA * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": spmm_bytes / (msA * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
                      "algorithmic_bytes_per_launch_ui": ui_bytes},
-        "roofline_projection": {"kernel": "gemm_nt_kernel<32,64,2,4> (2 launches)", "bound": "hbm",
+        "roofline_projection": {"kernel": "project_tc_kernel + project_reduce_kernel (2 modalities)", "bound": "hbm",
                                 "achieved": proj_bytes / (msB * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                 "frac": proj_bytes / (msB * 1e-3) / 1e9 / pk["hbm_gbs"], "tflops": proj_flops / (msB * 1e-3) / 1e12},
-        "roofline_scoring": {"kernel": "score + mask + topk_rows", "bound": "tensor",
+        "roofline_scoring": {"kernel": "score_tc_kernel + mask_kernel + topk_stream_kernel (auto path)", "bound": "tensor",
                              "achieved": score_flops / (msC * 1e-3) / 1e12, "peak": pk["bf16_tflops"] / 2, "unit": "TFLOP/s",
                              "frac": score_flops / (msC * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
                              "note": "peak = measured bf16 dense / 2 (TF32 rate); useful flops 2*B*I*d"},

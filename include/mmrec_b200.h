@@ -115,10 +115,15 @@ int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d,
  * bm3.py:102-104, mgcn.py:148-150) and `F.normalize(MLP(features))` (mmgcn.py:165-168).
  *   Y[n,:] = table[idx ? idx[n] : n, :] @ W^T + bias      table [n_table, F], W [d, F], bias [d]|NULL
  *   l2_normalize: Y[n,:] /= max(||Y[n,:]||_2, 1e-12)
+ * Two arithmetic paths: tcgen05 3xTF32 with the table split in-kernel (default when ws is given and d <= 256;
+ * ws from mmrec_project_workspace_bytes holds the re-tiled weights and the K-split partials) and exact fp32 on CUDA
+ * cores (ws == NULL, or mmrec_project_set_path(0) / env MMREC_PROJECT_PATH=simt).
  * ------------------------------------------------------------------------------------------- */
+int mmrec_project_set_path(int tensor_core);
+size_t mmrec_project_workspace_bytes(int64_t n_out, int64_t F, int d);
 int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int64_t n_table, int64_t F,
                       const float* W, const float* bias, int d, int l2_normalize,
-                      float* Y, int64_t ldy, void* stream);
+                      float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  full-catalog scoring, train-positive mask and per-user top-k.   Replaces
@@ -140,8 +145,8 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
  * ------------------------------------------------------------------------------------------- */
 /* path of mmrec_score_f32 / mmrec_score_topk_f32 (env MMREC_SCORE_PATH = simt | tc | auto | fused sets the start value):
  *   0 simt   exact fp32 on CUDA cores
- *   1 tc     tcgen05 3xTF32 GEMM into an L2-resident score block, then mask + streaming top-k kernels
- *   2 auto   (default) tc for catalogues up to 64k items, fused beyond (the score block would leave L2)
+ *   1 tc     tcgen05 3xTF32 GEMM into an L2-resident score block, then mask + radix-select top-k kernels
+ *   2 auto   (default) fused wherever its shape rules allow (n_items >= 8k + 512, k <= 256, d <= 128), else tc
  *   3 fused  tcgen05 3xTF32 GEMM with the threshold-filter top-k fused into its epilogue, no score matrix */
 int mmrec_score_set_path(int path);
 size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d);

@@ -282,10 +282,16 @@ def project_raw(table, weight, bias, idx=None, l2_normalize=False) -> torch.Tens
     if table.shape[1] != F:
         raise MMRecError(f"project: table has {table.shape[1]} features, weight expects {F}")
     out = torch.empty(n_out, d, dtype=torch.float32, device=table.device)
+    ws = _ws("project", lib.mmrec_project_workspace_bytes(n_out, F, d), table.device)
     check(lib.mmrec_project_f32(n_out, _ptr(idx), _ptr(table), table.shape[0], F, _ptr(weight), _ptr(bias), d,
-                                int(l2_normalize), _ptr(out), d, _stream()), "mmrec_project_f32")
-    _count()
+                                int(l2_normalize), _ptr(out), d, _ptr(ws), ws.numel(), _stream()), "mmrec_project_f32")
+    _count(3)
     return out
+
+
+def set_project_path(tensor_core: bool):
+    """True (default): tcgen05 3xTF32 projection kernel; False: exact fp32 CUDA-core kernel."""
+    _lib.load().mmrec_project_set_path(int(bool(tensor_core)))
 
 
 class _ProjectFn(torch.autograd.Function):
@@ -324,8 +330,8 @@ def project(table, weight, bias=None, idx=None, l2_normalize=False) -> torch.Ten
 # K3: scoring, mask, top-k
 # ------------------------------------------------------------------------------------------------
 def set_score_path(path):
-    """"simt" (0): exact fp32 CUDA cores; "tc" (1): tcgen05 3xTF32 + mask + streaming top-k kernels; "auto" (2,
-    default): tc up to 64k items, fused beyond; "fused" (3): tcgen05 with the top-k fused into the GEMM epilogue."""
+    """"simt" (0): exact fp32 CUDA cores; "tc" (1): tcgen05 3xTF32 + mask + radix top-k kernels; "auto" (2, default):
+    fused where its shape rules allow, else tc; "fused" (3): tcgen05 with the top-k fused into the GEMM epilogue."""
     if isinstance(path, str):
         path = {"simt": 0, "tc": 1, "auto": 2, "fused": 3}[path]
     _lib.load().mmrec_score_set_path(int(path))

@@ -154,11 +154,38 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             torch.cuda.synchronize()
             if step >= args.warmup:
                 tA += e[0].elapsed_time(e[1]); tC += e[2].elapsed_time(e[3])
+    launches1 = ops.LAUNCHES
     dist.barrier()
-    t = torch.tensor([tA, tC], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)                         # max over ranks, device-timed
-    e_all = torch.tensor([float(edges_local)], device=dev, dtype=torch.float64)
-    dist.all_reduce(e_all, op=dist.ReduceOp.SUM)
+    # ---- e2e: the same calls with pinned HOST buffers, copies inside the timed region
+    ue_h = torch.from_numpy(wl.user_emb).pin_memory()
+    ie_h = torch.from_numpy(wl.item_emb[shard.local_items]).pin_memory()
+    out_u = torch.empty(U, d).pin_memory(); out_i = torch.empty(shard.n_local, d).pin_memory()
+    users_h = [b[0].cpu().pin_memory() for b in batches]
+    masks_h = [b[1].cpu().pin_memory() for b in batches]
+    out_idx = [torch.empty(b[0].numel(), TOPK, dtype=torch.int64).pin_memory() for b in batches]
+    eA = eC = 0.0
+    with torch.no_grad():
+        for step in range(args.warmup + args.steps):
+            flush.zero_()
+            dist.barrier()
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            ue_d, ie_d = ue_h.to(dev, non_blocking=True), ie_h.to(dev, non_blocking=True)
+            u_g, i_g = propagate_mean_sharded(a_ui, a_iu, ue_d, ie_d, wl.n_layers)
+            out_u.copy_(u_g, non_blocking=True); out_i.copy_(i_g, non_blocking=True)
+            e[1].record()
+            e[2].record()
+            for uh, mh, oh in zip(users_h, masks_h, out_idx):
+                _, idx = score_topk_sharded(shard, u_g, i_g, uh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True), TOPK)
+                oh.copy_(idx, non_blocking=True)
+            e[3].record()
+            torch.cuda.synchronize()
+            if step >= args.warmup:
+                eA += e[0].elapsed_time(e[1]); eC += e[2].elapsed_time(e[3])
+    dist.barrier()
+    h2d = (ue_h.numel() + ie_h.numel()) * 4 + sum(u.numel() * 8 + m.numel() * 8 for u, m in zip(users_h, masks_h))
+    d2h = (out_u.numel() + out_i.numel()) * 4 + sum(o.numel() * 8 for o in out_idx)
+    t = torch.tensor([tA, tC, eA, eC], device=dev, dtype=torch.float64)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         K = args.steps
@@ -180,7 +207,9 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
                          "achieved": algo_bytes / (msA * 1e-3) / 1e9 / world, "peak": pk["hbm_gbs"], "unit": "GB/s per GPU",
                          "frac": algo_bytes / (msA * 1e-3) / 1e9 / world / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
                          "note": "includes the per-layer NCCL all-reduce of the [U,d] user partials"},
-            "gpu_launches": int(ops.LAUNCHES - launches0), "clocks": clocks,
-            "e2e": None,
+            "gpu_launches": int(launches1 - launches0), "clocks": clocks,
+            "e2e": {"value": edges / (t[2].item() / K * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(h2d) * world,
+                    "d2h_bytes_per_step": int(d2h) * world, "prop_ms": t[2].item() / K, "score_topk_ms": t[3].item() / K,
+                    "scored_items_per_sec": U * I / (t[3].item() / K * 1e-3)},
         }))
     dist.destroy_process_group()

@@ -40,7 +40,7 @@ def test_argument_errors_without_a_gpu():
                               1.0, None, 0, None) == -1
     assert b"spmm" in lib.mmrec_last_error()
     assert lib.mmrec_topk_rows_f32(4, 10, None, 10, 11, 0, None, None, None) == -1     # k > n_items
-    assert lib.mmrec_project_f32(-5, None, None, 0, 0, None, None, 0, 0, None, 0, None) == -1
+    assert lib.mmrec_project_f32(-5, None, None, 0, 0, None, None, 0, 0, None, 0, None, 0, None) == -1
     assert lib.mmrec_topk_merge(100, 4, 50, None, None, None, None, None) == -1        # parts * k > 4096
 
 

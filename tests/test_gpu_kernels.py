@@ -177,8 +177,10 @@ def test_bipartite_norm_and_pruning_vs_reference(dev, golden):
 # ------------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("n,F,d", [(700, 256, 64), (1000, 4096, 64), (333, 130, 64), (257, 384, 32), (300, 512, 128),
                                    (129, 200, 256), (64, 77, 96), (50, 64, 300)])
-def test_project_matches_oracle(dev, n, F, d):
+@pytest.mark.parametrize("path", ["tc", "simt"])
+def test_project_matches_oracle(dev, n, F, d, path):
     from mmrec_b200 import ops
+    ops.set_project_path(path == "tc")
     g = torch.Generator().manual_seed(n + F)
     X = torch.randn(n, F, generator=g); W = torch.randn(d, F, generator=g) / F ** 0.5; b = torch.randn(d, generator=g)
     idx = torch.randint(0, n, (n // 2 + 3,), generator=g)
@@ -194,6 +196,7 @@ def test_project_matches_oracle(dev, n, F, d):
     (ops.project(X1, W1, b1, idx=idx.to(dev)) * w.to(dev)).sum().backward()
     (O.project(X2, W2, b2, idx=idx) * w).sum().backward()
     assert rel(X1.grad, X2.grad) < 1e-5 and rel(W1.grad, W2.grad) < 1e-5 and rel(b1.grad, b2.grad) < 1e-5
+    ops.set_project_path(True)
 
 
 # ------------------------------------------------------------------------------------------------ K3
