@@ -45,7 +45,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the first warm-up step to the end of the timed
+    regions (the device-only region of this workload lasts tens of milliseconds, shorter than one sampling period,
+    so the window also covers the warm-up and the e2e region, all of them under the same load)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -54,7 +56,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -218,9 +220,10 @@ def run_ours(args):
     launches_per_step = sum(n_launch.values())
     with torch.no_grad():
         for step in range(args.warmup + args.steps):
+            if step == 0:
+                sampler.start()
             if step == args.warmup:
                 torch.cuda.synchronize()
-                sampler.start()
                 wall0 = time.perf_counter()
             flush.zero_()                                            # evict L2 (126 MB) between steps
             e = [ev() for _ in range(6)]
@@ -232,7 +235,6 @@ def run_ours(args):
                 tA += e[0].elapsed_time(e[1]); tB += e[2].elapsed_time(e[3]); tC += e[4].elapsed_time(e[5])
     wall = time.perf_counter() - wall0
     launches = launches_per_step * args.steps
-    clocks = sampler.stop()
     K = args.steps
     msA, msB, msC = tA / K, tB / K, tC / K
 
@@ -261,6 +263,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             if step >= args.warmup:
                 e2e_A += e[0].elapsed_time(e[1]); e2e_C += e[2].elapsed_time(e[3])
+    clocks = sampler.stop()
     h2d = ego_h.numel() * 4 + sum(uh.numel() * 8 + b[2].numel() * 8 for uh, b in zip(users_h, batches))
     d2h = (out_u.numel() + out_i.numel()) * 4 + sum(o.numel() * 8 for o in out_idx)
     e2e_msA, e2e_msC = e2e_A / K, e2e_C / K

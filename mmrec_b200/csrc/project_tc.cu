@@ -3,13 +3,13 @@
 //
 // The feature table is the big operand (115 MB at 7k x 4096) and is read from HBM exactly once, as fp32, so its hi/lo
 // split happens IN the kernel:
-//   converter warps (4)  coalesced 16-byte loads of the gathered rows (2 stages of loads in flight per thread), split
+//   converter warps (8)  coalesced 16-byte loads of the gathered rows (4 K chunks = 64 KB per SM in flight), split
 //                        each value into tf32 hi + lo, store both into shared memory directly in the UMMA canonical
 //                        K-major layout (8 x 16 B core matrices; K stride padded to 2064 B so the stores are
 //                        conflict-free), fence.proxy.async, arrive on the stage's mbarrier;
 //   producer warp        cp.async.bulk of the pre-split, pre-tiled weight slab (hi and lo) of the same K chunk;
 //   MMA warp             12 x tcgen05.mma M128 N{64,128,256} K8 per 32-wide K chunk: hi.hi + lo.hi + hi.lo;
-//   epilogue             the converter warps read the accumulator (tcgen05.ld) and write one fp32 partial per K split.
+//   epilogue             four of the converter warps read the accumulator (tcgen05.ld) and write one fp32 partial per K split.
 // Grid = row tiles x K splits <= SM count (one wave); project_reduce_kernel adds the K splits, the bias and applies
 // the row normalisation.  Per launch the kernel moves 4 n F (+ weights) bytes for 2 n F d useful flops -> HBM-bound.
 #include "tc_common.cuh"
@@ -22,7 +22,9 @@ constexpr int PJ_M = 128;                 // rows per CTA tile
 constexpr int PJ_KC = 32;                 // k per stage
 constexpr int PJ_LBO_A = 2064;            // 16 row groups x 128 B + 16 B pad: K-adjacent core matrices land on different banks
 constexpr int PJ_A_BYTES = (PJ_KC / 4) * PJ_LBO_A;            // one of hi / lo for one stage = 16512 B
-constexpr int PJ_THREADS = 192;           // warp 0 weight producer, warp 1 MMA, warps 2..5 converters + epilogue
+constexpr int PJ_CONV = 256;              // converter threads (8 warps); the first 4 of them also run the epilogue
+constexpr int PJ_DEPTH = 4;               // chunks of table reads in flight per converter thread (64 KB per SM)
+constexpr int PJ_THREADS = 64 + PJ_CONV;  // warp 0 weight producer, warp 1 MMA, warps 2..9 converters
 
 struct ProjParams {
     const float* table; int64_t F; const int64_t* idx; int64_t n_out;
@@ -46,7 +48,7 @@ __host__ __device__ inline PjSmem pj_smem(int N, int stages) {
     L.total = L.tmem_ptr + 16;
     return L;
 }
-// barriers: a_full[s] = 0..7 (128 arrivals) | b_full[s] = 8..15 (tx) | empty[s] = 16..23 (1, tcgen05.commit) | acc_full = 24
+// barriers: a_full[s] = 0..7 (PJ_CONV arrivals) | b_full[s] = 8..15 (tx) | empty[s] = 16..23 (1, tcgen05.commit) | acc_full = 24
 
 __global__ void __launch_bounds__(PJ_THREADS, 1) project_tc_kernel(const ProjParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) project_tc_kernel(const ProjPar
     const uint32_t bar = sbase + L.bars;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 8; ++s) { mbar_init(bar + s * 8, 128); mbar_init(bar + (8 + s) * 8, 1); mbar_init(bar + (16 + s) * 8, 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(bar + s * 8, PJ_CONV); mbar_init(bar + (8 + s) * 8, 1); mbar_init(bar + (16 + s) * 8, 1); }
         mbar_init(bar + 24 * 8, 1);
         mbar_fence_init();
     }
@@ -109,21 +111,22 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) project_tc_kernel(const ProjPar
             mma_commit(bar + 24 * 8);
         }
     } else {
-        // ---------------- converters: thread t owns kblk t % 8 of rows t / 8 + 16 i, i = 0..7
+        // ---------------- converters: thread t owns kblk t % 8 of rows t / 8 + 32 i, i = 0..3; PJ_DEPTH chunks of its
+        // 16-byte reads are in flight at any time (registers are the staging buffer: 256 thr x 4 x 4 x 16 B = 64 KB per SM)
         const int t = threadIdx.x - 64;
         const int kb = t & 7;
-        const float* rowp[8];
+        const float* rowp[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int64_t r = (int64_t)tile * PJ_M + (t >> 3) + 16 * i;
+        for (int i = 0; i < 4; ++i) {
+            const int64_t r = (int64_t)tile * PJ_M + (t >> 3) + 32 * i;
             rowp[i] = r < p.n_out ? p.table + (p.idx ? p.idx[r] : r) * p.F : nullptr;
         }
-        auto load_chunk = [&](int c, float4 (&x)[8]) {
+        auto load_chunk = [&](int c, float4 (&x)[4]) {
             const int64_t k = (int64_t)(c0 + c) * PJ_KC + kb * 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rowp[i]) {
+                if (rowp[i] && c < n_my) {
                     if (p.vec_ok && k + 3 < p.F) v = __ldg(reinterpret_cast<const float4*>(rowp[i] + k));
                     else {
                         if (k + 0 < p.F) v.x = __ldg(rowp[i] + k + 0);
@@ -135,30 +138,35 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) project_tc_kernel(const ProjPar
                 x[i] = v;
             }
         };
-        float4 cur[8], nxt[8];
-        if (n_my > 0) load_chunk(0, cur);
-        for (int c = 0; c < n_my; ++c) {
-            const int s = c % p.stages, use = c / p.stages;
-            if (c + 1 < n_my) load_chunk(c + 1, nxt);                 // next chunk's HBM reads fly during the conversion
-            mbar_wait(bar + (16 + s) * 8, (use & 1) ^ 1);
-            uint8_t* st = smem + s * L.stage_bytes;
+        float4 ring[PJ_DEPTH][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = (t >> 3) + 16 * i;
-                const uint32_t off = kb * PJ_LBO_A + (r >> 3) * 128 + (r & 7) * 16;
-                float4 h, l;
-                split_tf32(cur[i].x, h.x, l.x); split_tf32(cur[i].y, h.y, l.y);
-                split_tf32(cur[i].z, h.z, l.z); split_tf32(cur[i].w, h.w, l.w);
-                *reinterpret_cast<float4*>(st + L.a0 + off) = h;
-                *reinterpret_cast<float4*>(st + L.a0 + PJ_A_BYTES + off) = l;
+        for (int q = 0; q < PJ_DEPTH; ++q) load_chunk(q, ring[q]);
+        for (int cb = 0; cb < n_my; cb += PJ_DEPTH) {
+#pragma unroll
+            for (int q = 0; q < PJ_DEPTH; ++q) {                      // static ring index: stays in registers
+                const int c = cb + q;
+                if (c < n_my) {
+                    const int s = c % p.stages, use = c / p.stages;
+                    mbar_wait(bar + (16 + s) * 8, (use & 1) ^ 1);
+                    uint8_t* st = smem + s * L.stage_bytes;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = (t >> 3) + 32 * i;
+                        const uint32_t off = kb * PJ_LBO_A + (r >> 3) * 128 + (r & 7) * 16;
+                        float4 h, l;
+                        split_tf32(ring[q][i].x, h.x, l.x); split_tf32(ring[q][i].y, h.y, l.y);
+                        split_tf32(ring[q][i].z, h.z, l.z); split_tf32(ring[q][i].w, h.w, l.w);
+                        *reinterpret_cast<float4*>(st + L.a0 + off) = h;
+                        *reinterpret_cast<float4*>(st + L.a0 + PJ_A_BYTES + off) = l;
+                    }
+                    fence_proxy_async();                              // generic-proxy stores -> visible to the MMA's async reads
+                    mbar_arrive(bar + s * 8);
+                    load_chunk(c + PJ_DEPTH, ring[q]);                // refill this ring slot
+                }
             }
-            fence_proxy_async();                                      // generic-proxy stores -> visible to the MMA's async reads
-            mbar_arrive(bar + s * 8);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
         }
         // ---------------- epilogue: partial tile of this K split
-        if (n_my > 0) {
+        if (n_my > 0 && warp < 6) {
             mbar_wait(bar + 24 * 8, 0);
             fence_after_sync();
             const int q = warp & 3;

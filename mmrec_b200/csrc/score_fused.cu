@@ -22,7 +22,6 @@ namespace mmrec {
 using namespace tc;
 
 constexpr int FZ_NB = 32;               // histogram bins per row
-constexpr int FZ_MAXFINAL = 2048;       // finalists the select kernel can sort per row
 
 struct FusedParams {
     const float *Uhi, *Ulo, *Ihi, *Ilo;
@@ -315,46 +314,58 @@ __device__ void fz_bitonic_desc(uint64_t* a, int n) {
     __syncthreads();
 }
 
+constexpr int FZ_WFIN = 512;            // finalists one warp can rank per row (typical: 60-150)
+
+// One warp per row, four rows per CTA.
 __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_splits, int cap, int k, int64_t item_offset,
                                                            const float2* __restrict__ cand, const int32_t* __restrict__ cnt,
                                                            const float* __restrict__ thr, const int32_t* __restrict__ mask_ptr,
                                                            const int32_t* __restrict__ mask_items, int32_t* __restrict__ flags,
                                                            int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
-    __shared__ uint64_t fin[FZ_MAXFINAL];
-    __shared__ int n_fin, over;
-    const int64_t row = blockIdx.x;
-    if (flags[row]) return;                                          // already condemned to the exact kernel
-    if (threadIdx.x == 0) { n_fin = 0; over = 0; }
-    __syncthreads();
+    __shared__ uint64_t fin_all[4][FZ_WFIN];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 4 + warp;
+    if (row >= B || flags[row]) return;                              // (flagged: already condemned to the exact kernel)
+    uint64_t* fin = fin_all[warp];
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
     // Certificate: every split's list holds ALL of its items with value >= its own final threshold, hence all items
     // >= T = max over splits.  If at least k unmasked items clear T, the global top-k is among them.
     float T = -INFINITY;
     for (int s = 0; s < n_splits; ++s) T = fmaxf(T, thr[row * n_splits + s]);
+    int n = 0;
+    bool over = false;
     for (int s = 0; s < n_splits; ++s) {
-        const int n = cnt[row * n_splits + s];
-        const float th = T;
+        const int ns = cnt[row * n_splits + s];
         const float2* cs = cand + (row * n_splits + s) * cap;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            const float2 c = cs[j];
-            if (!(c.x >= th)) continue;
-            const int item = __float_as_int(c.y);
-            bool masked = false;
-            for (int q = m0; q < m1; ++q) masked |= (mask_items[q] == item);
-            if (masked) continue;
-            const int pos = atomicAdd(&n_fin, 1);
-            if (pos < FZ_MAXFINAL) fin[pos] = ((uint64_t)float_key(c.x) << 32) | (uint32_t)(~(uint32_t)item);
-            else over = 1;
+        for (int j0 = 0; j0 < ns; j0 += 32) {
+            const int j = j0 + lane;
+            bool keep = false;
+            float2 c = make_float2(0.f, 0.f);
+            if (j < ns) {
+                c = cs[j];
+                keep = c.x >= T;
+                if (keep) {
+                    const int item = __float_as_int(c.y);
+                    for (int q = m0; q < m1; ++q) keep &= (mask_items[q] != item);
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int pos = n + __popc(bal & ((1u << lane) - 1u));
+            if (keep) {
+                if (pos < FZ_WFIN) fin[pos] = ((uint64_t)float_key(c.x) << 32) | (uint32_t)(~(uint32_t)__float_as_int(c.y));
+                else over = true;
+            }
+            n += __popc(bal);
         }
     }
-    __syncthreads();
-    const int n = n_fin;
+    over = __any_sync(0xffffffffu, over);
     if (over || n < k) {                                             // cannot certify this row: exact kernel takes it
-        if (threadIdx.x == 0) flags[row] = 1;
+        if (lane == 0) flags[row] = 1;
         return;
     }
+    __syncwarp();
     // composites are unique (item index in the low word): rank = number of larger composites = output position
-    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    for (int t = lane; t < n; t += 32) {
         const uint64_t me = fin[t];
         int rank = 0;
         for (int u = 0; u < n; ++u) rank += fin[u] > me;
@@ -395,30 +406,33 @@ __global__ void __launch_bounds__(256) exact_keys_kernel(const int64_t* __restri
                                                          const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
                                                          const int32_t* __restrict__ counter, const int32_t* __restrict__ row_of_slot,
                                                          int tile_rows, unsigned* __restrict__ keys) {
-    extern __shared__ float ex_sm[];                                 // urow[d] | tile[tile_rows][d + 1]
+    // One warp per item: the 32 lanes read the item's row coalesced, multiply by the user's row (held in registers) and
+    // tree-reduce with shuffles -- fp32 throughout; the summation tree differs from the fmaf chain of the CUDA-core
+    // GEMM by rounding only (these rows are compared under the near-tie rule like every other).
+    (void)tile_rows;
     const int sl = blockIdx.x;
     if (sl >= *counter) return;
     const int64_t row = row_of_slot[sl];
-    const int tid = threadIdx.x;
-    float* urow = ex_sm;
-    float* tile = ex_sm + d;
-    const int ldt = d + 1;
+    const int lane = threadIdx.x & 31;
     const float* u = Ue + (users ? users[row] : row) * ldu;
-    for (int c = tid; c < d; c += 256) urow[c] = u[c];
+    float ur[8];                                                     // d <= 256
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ur[i] = (lane + 32 * i < d) ? u[lane + 32 * i] : 0.f;
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
     unsigned* out = keys + (int64_t)sl * n_items;
-    for (int64_t i0 = (int64_t)blockIdx.y * tile_rows; i0 < n_items; i0 += (int64_t)gridDim.y * tile_rows) {
-        __syncthreads();
-        const int nt = (int)((n_items - i0) < tile_rows ? (n_items - i0) : tile_rows);
-        for (int e = tid; e < nt * d; e += 256) tile[(e / d) * ldt + (e % d)] = __ldg(Ie + (i0 + e / d) * ldi + (e % d));
-        __syncthreads();
-        if (tid < nt) {
-            float acc = 0.f;
-            for (int c = 0; c < d; ++c) acc = fmaf(urow[c], tile[tid * ldt + c], acc);
-            const int32_t item = (int32_t)(i0 + tid);
+    const int64_t w = (int64_t)blockIdx.y * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.y * 8;
+    for (int64_t i = w; i < n_items; i += nw) {
+        const float* v = Ie + i * ldi;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (lane + 32 * q < d) acc = fmaf(ur[q], __ldg(v + lane + 32 * q), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const int32_t item = (int32_t)i;
             for (int q = m0; q < m1; ++q)
                 if (mask_items[q] == item) acc = -1e10f;
-            out[i0 + tid] = float_key(acc);
+            out[i] = float_key(acc);
         }
     }
 }
@@ -461,26 +475,47 @@ __global__ void __launch_bounds__(256) exact_select_kernel(int64_t n_items, int 
         __syncthreads();
     }
     const unsigned kth = prefix;
-    if (tid == 0) { s_count = 0; s_base = 0; }
+    __shared__ unsigned tie_idx[1024];
+    __shared__ unsigned n_ties;
+    if (tid == 0) { s_count = 0; s_base = 0; n_ties = 0; }
     __syncthreads();
     const unsigned n_gt = (unsigned)k - need;
-    for (int64_t i0 = 0; i0 < n_items; i0 += 256) {
-        const int64_t i = i0 + tid;
-        const unsigned key = i < n_items ? keys[i] : 0u;
-        if (i < n_items && key > kth) { unsigned pos = atomicAdd(&s_count, 1u); sel[pos] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)i); }
-        const bool eq = i < n_items && key == kth;
-        const unsigned bal = __ballot_sync(0xffffffffu, eq);
-        const int lane = tid & 31, wid = tid >> 5;
-        if (lane == 0) warp_tot[wid] = __popc(bal);
-        __syncthreads();
-        unsigned off = s_base;
-        for (int w = 0; w < wid; ++w) off += warp_tot[w];
-        const unsigned rank = off + __popc(bal & ((1u << lane) - 1u));
-        if (eq && rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~(uint32_t)i);
-        __syncthreads();
-        if (tid == 0) { unsigned tot = 0; for (int w = 0; w < 8; ++w) tot += warp_tot[w]; s_base += tot; }
-        __syncthreads();
+    // strictly greater keys in any order; the indices of the keys equal to the k-th are collected and the `need` lowest
+    // of them taken (normally there is exactly one)
+    for (int64_t i = tid; i < n_items; i += 256) {
+        const unsigned key = keys[i];
+        if (key > kth) { unsigned pos = atomicAdd(&s_count, 1u); sel[pos] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)i); }
+        else if (key == kth) { unsigned pos = atomicAdd(&n_ties, 1u); if (pos < 1024u) tie_idx[pos] = (unsigned)i; }
     }
+    __syncthreads();
+    if (n_ties <= 1024u) {
+        const unsigned nt = n_ties;
+        for (unsigned t = tid; t < nt; t += 256) {
+            const unsigned me = tie_idx[t];
+            unsigned rank = 0;
+            for (unsigned u = 0; u < nt; ++u) rank += tie_idx[u] < me;
+            if (rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~me);
+        }
+    } else {
+        // degenerate row (thousands of equal scores): ordered sweep, 256 items at a time
+        for (int64_t i0 = 0; i0 < n_items; i0 += 256) {
+            const int64_t i = i0 + tid;
+            const bool eq = i < n_items && keys[i] == kth;
+            const unsigned bal = __ballot_sync(0xffffffffu, eq);
+            const int lane = tid & 31, wid = tid >> 5;
+            if (lane == 0) warp_tot[wid] = __popc(bal);
+            __syncthreads();
+            unsigned off = s_base;
+            for (int w = 0; w < wid; ++w) off += warp_tot[w];
+            const unsigned rank = off + __popc(bal & ((1u << lane) - 1u));
+            if (eq && rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~(uint32_t)i);
+            __syncthreads();
+            if (tid == 0) { unsigned tot = 0; for (int w = 0; w < 8; ++w) tot += warp_tot[w]; s_base += tot; }
+            __syncthreads();
+            if (s_base >= need) break;
+        }
+    }
+    __syncthreads();
     int n2 = 1;
     while (n2 < k) n2 <<= 1;
     for (int t = k + tid; t < n2; t += 256) sel[t] = 0;
@@ -696,7 +731,6 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
     const FzSmem L = fz_smem(P.KP);
     static bool attr_set = false;
     if (!attr_set) {
-        MMREC_CUDA(cudaFuncSetAttribute(exact_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         MMREC_CUDA(cudaFuncSetAttribute(exact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         MMREC_CUDA(cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -717,7 +751,7 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         p.flags = (int32_t*)(base + P.off_flags);
         score_fused_kernel<<<(unsigned)(n_ut * P.splits), TC_THREADS, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
-        fused_select_kernel<<<(unsigned)nb, 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,
+        fused_select_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,
                                                               mitems, p.flags, out_idx + r0 * k, out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
         // rows the filter could not certify: exact fp32 recompute (normally none or a handful per block)
@@ -730,10 +764,9 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
             exact_slots_kernel<<<(unsigned)((nb + T - 1) / T), T, 0, stream>>>(nb, p.flags, slot, counter, row_of_slot);
             MMREC_LAUNCH_CHECK();
             const int tile_rows = d <= 64 ? 256 : 128;
-            const size_t ex_smem = (size_t)(d + tile_rows * (d + 1)) * sizeof(float);
             const int64_t* ub = users ? users + r0 : nullptr;
             const float* ue = users ? Ue : Ue + r0 * ldu;
-            exact_keys_kernel<<<dim3(EX_SLOTS, EX_SPLIT), 256, ex_smem, stream>>>(ub, ue, ldu, n_items, Ie, ldi, d, p.mask_ptr, mitems,
+            exact_keys_kernel<<<dim3(EX_SLOTS, EX_SPLIT), 256, 0, stream>>>(ub, ue, ldu, n_items, Ie, ldi, d, p.mask_ptr, mitems,
                                                                                  counter, row_of_slot, tile_rows, keys);
             MMREC_LAUNCH_CHECK();
             exact_select_kernel<<<EX_SLOTS, 256, 0, stream>>>(n_items, k, item_offset, counter, row_of_slot, keys, out_idx + r0 * k,

@@ -137,10 +137,10 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     launches0 = 0
     with torch.no_grad():
         for step in range(args.warmup + args.steps):
+            if step == 0 and rank == 0:
+                sampler.start()
             if step == args.warmup:
                 torch.cuda.synchronize(); dist.barrier()
-                if rank == 0:
-                    sampler.start()
                 launches0 = ops.LAUNCHES
             flush.zero_()
             dist.barrier()
