@@ -266,6 +266,20 @@ def mmgcn_mean_aggregate(edge_index: torch.Tensor, x: torch.Tensor) -> torch.Ten
     return out / cnt.clamp(min=1).unsqueeze(1)
 
 
+def mmgcn_gcn_forward(p, prefix, edge_index, features, id_embedding, preference, dim_latent, concate=True, has_id=True):
+    """PARITY UNPINNED.  One modality tower, `src/models/mmgcn.py:163-188` (`concate = 'False'` is truthy, `:31`):
+    `p` maps parameter names (`<prefix>.MLP.weight`, `<prefix>.conv_embed_1.weight`, ...) to tensors."""
+    g = lambda name: p[prefix + "." + name]
+    lin = lambda x, name: F.linear(x, g(name + ".weight"), g(name + ".bias"))
+    temp = lin(features, "MLP") if dim_latent else features
+    x = F.normalize(torch.cat((preference, temp), dim=0))
+    for li in (1, 2, 3):
+        h = F.leaky_relu(mmgcn_mean_aggregate(edge_index, torch.matmul(x, g(f"conv_embed_{li}.weight"))))
+        x_hat = F.leaky_relu(lin(x, f"linear_layer{li}")) + id_embedding if has_id else F.leaky_relu(lin(x, f"linear_layer{li}"))
+        x = F.leaky_relu(lin(torch.cat((h, x_hat), dim=1), f"g_layer{li}")) if concate else F.leaky_relu(lin(h, f"g_layer{li}") + x_hat)
+    return x
+
+
 # --------------------------------------------------------------------------------------
 # a5: modality projection
 # --------------------------------------------------------------------------------------

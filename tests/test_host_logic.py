@@ -139,7 +139,7 @@ def test_early_stopping_and_plugin_loader():
     assert (best, step, stop, upd) == (0.5, 0, False, True)
     best, step, stop, upd = early_stopping(0.3, 0.5, 5, max_step=5, bigger=True)
     assert (best, step, stop, upd) == (0.5, 6, True, False)
-    for name in ("FREEDOM", "BM3", "MGCN", "LightGCN", "LayerGCN"):
+    for name in ("FREEDOM", "BM3", "MGCN", "LightGCN", "LayerGCN", "MMGCN"):
         cls = get_model(name)
         assert cls.__name__ == name
         for meth in ("calculate_loss", "full_sort_predict", "forward", "pre_epoch_processing", "post_epoch_processing"):
