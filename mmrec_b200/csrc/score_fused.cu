@@ -13,6 +13,9 @@
 //     items dropped, and a bitonic sort on (value desc, item asc) emits the top-k -- the contract of topk.cu.
 // Anything the filter cannot certify (candidate overflow, a degenerate histogram, NaNs) raises a per-row flag and
 // the row is recomputed by the exact fp32 kernel at the end of this file; no host round trip.
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
 #include "tc_common.cuh"
@@ -21,7 +24,10 @@ namespace mmrec {
 
 using namespace tc;
 
-constexpr int FZ_NB = 32;               // histogram bins per row
+constexpr int FZ_NB = 32;               // histogram bins per row (two 16-bit counters per shared-memory word)
+constexpr int FZ_CH = 16;               // accumulator columns an epilogue warp reads per tcgen05.ld
+constexpr int FZ_HALF = TC_N / 2;       // columns of a tile owned by one epilogue set
+constexpr int FZ_MAX_THREADS = 64 + 128 * 4;
 
 struct FusedParams {
     const float *Uhi, *Ulo, *Ihi, *Ilo;
@@ -32,25 +38,46 @@ struct FusedParams {
     int32_t* cnt;                       // [B][n_splits]
     float* thr;                         // [B][n_splits]
     int32_t* flags;                     // [B] fallback flags
+    uint32_t* gthr;                     // [B] highest certified threshold of any split (order-preserving key), zeroed per launch
 };
 
-constexpr int FZ_SCRATCH_BYTES = 4 * 32 * 32 * 4;   // per epilogue warp: one 32 x 32 chunk, thread-private columns
-
+// Shared memory: user tile (hi | lo) | item slab ring | row state | histogram | per-warp chunk scratch | barriers.
+// Epilogue sets (4 warps = 128 rows each): a set owns one column half of the tiles of one parity.  KP <= 64 runs four
+// sets (both halves x both TMEM buffers in flight), KP = 128 has room for two (both halves, tiles in turn).
 struct FzSmem {
-    uint32_t u_hi, u_lo, slab0, hist, scratch, bars, tmem_ptr, total;
-    int stages;
+    uint32_t u_hi, u_lo, slab0, rowst, hist, scratch, bars, tmem_ptr, total;
+    int stages, parities, nsets;
 };
 __host__ __device__ inline FzSmem fz_smem(int KP) {
     FzSmem L;
     const uint32_t u_bytes = TC_M * KP * 4;
-    L.stages = KP >= 128 ? 2 : 4;
+    L.stages = KP >= 128 ? 2 : 3;
+    L.parities = KP >= 128 ? 1 : 2;
+    L.nsets = 2 * L.parities;
     L.u_hi = 0; L.u_lo = u_bytes; L.slab0 = 2 * u_bytes;
-    L.hist = L.slab0 + L.stages * TC_SLAB_BYTES;
-    L.scratch = L.hist + FZ_NB * TC_M * 2;
-    L.bars = L.scratch + FZ_SCRATCH_BYTES;
+    L.rowst = L.slab0 + L.stages * TC_SLAB_BYTES;                    // 8 words per row, field-major
+    L.hist = L.rowst + 8 * TC_M * 4;                                 // [16 bin pairs][128 rows] u32
+    L.scratch = L.hist + (FZ_NB / 2) * TC_M * 4;
+    L.bars = L.scratch + L.nsets * 4 * (FZ_CH * 32 * 4);
     L.tmem_ptr = L.bars + 16 * 8;
     L.total = L.tmem_ptr + 16;
     return L;
+}
+enum { RS_THR = 0, RS_CNT = 1, RS_LO = 2, RS_SCALE = 3, RS_WIDTH = 4, RS_BAD = 5 };
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // producer / MMA issuer: identical protocol to score_tc.cu (barrier slots: 0 u_full | 1..4 full | 5..8 empty |
@@ -110,7 +137,181 @@ __device__ __forceinline__ void fz_mma(const FusedParams& p, const FzSmem& L, ui
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedParams p) {
+// Epilogue.  The four lane quarters of a set cover the 128 rows of the tile; thread (set, row) filters its set's column
+// half of its set's tiles against the ROW's threshold, which all sets of the CTA share in shared memory together with
+// the candidate count and the histogram (shared-memory atomics: hits are rare).  Certified thresholds are also
+// published per row in global memory, so the other item splits of the row stop collecting what cannot make the top-k.
+__device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& L, uint8_t* smem, uint32_t sbase, uint32_t tmem_base,
+                                            int ut, int sp, int it0, int it1, int warp, int lane) {
+    const uint32_t bar = sbase + L.bars;
+    const int e = warp - 2;
+    const int set = e >> 2;
+    const int q = warp & 3;                                          // the TMEM lane quarter this warp can read
+    const int half = set & 1, par = set >> 1;
+    const int rl = q * 32 + lane;                                    // row inside the tile = TMEM lane
+    const int64_t row = (int64_t)ut * TC_M + rl;
+    const bool live = row < p.B;
+    const int n_epi = 128 * L.nsets;
+    const int n_tiles = it1 - it0;
+    uint32_t* rs = reinterpret_cast<uint32_t*>(smem + L.rowst) + rl;           // field f of this row: rs[f * TC_M]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L.hist) + rl;          // bin pair b2 of this row: hist[b2 * TC_M]
+    float* sc = reinterpret_cast<float*>(smem + L.scratch) + e * (FZ_CH * 32) + lane;   // value j of the chunk: sc[j * 32]
+    int need = p.k;
+    if (live && p.mask_ptr) need += p.mask_ptr[row + 1] - p.mask_ptr[row];
+    float2* cand = p.cand + ((int64_t)(live ? row : 0) * p.n_splits + sp) * p.cap;
+    const int n_items32 = (int)p.n_items;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    if (set == 0) {
+        // Seed from the first half tile.  gm[] = maxima of its 16 groups of 8 columns; thr0 = the r-th largest of them,
+        // so about r of the 128 scores pass.  r aims at ~2.5x the share the row finally needs (need / n_items) and is
+        // at least 8 (~6 %): the seed is the one threshold nothing certifies, so it has to be safe -- the row threshold
+        // (max over splits) must still leave k unmasked items above it -- and the certified thresholds take over from
+        // it after a tile or two anyway.
+        mbar_wait(bar + 9 * 8, 0);
+        fence_after_sync();
+        const int n_valid = n_items32 - it0 * TC_N;
+        float gm[16];
+#pragma unroll
+        for (int c = 0; c < FZ_HALF / FZ_CH; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x16(lane_base + c * FZ_CH, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float x = (c * FZ_CH + g * 8 + j < n_valid) ? __uint_as_float(v[g * 8 + j]) : -INFINITY;
+                    m = fmaxf(m, x);
+                }
+                gm[c * 2 + g] = m;
+            }
+        }
+        float gmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gmax = fmaxf(gmax, gm[j]);
+        int r = (int)ceilf(2.5f * (float)need * (float)FZ_HALF / (float)p.n_items);
+        r = r < 8 ? 8 : (r > 16 ? 16 : r);
+        float cur = gmax;
+        for (int i = 1; i < r; ++i) {                                // peel off the i-th largest (one instance at a time)
+            float nxt = -INFINITY;
+            bool removed = false;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (!removed && gm[j] == cur) { gm[j] = -INFINITY; removed = true; }
+                nxt = fmaxf(nxt, gm[j]);
+            }
+            cur = nxt;
+        }
+        float width = (gmax - cur) * (1.0f / 16.f), lo = cur, thr = cur;
+        uint32_t bad = 0;
+        if (!(width > 0.f) || !(cur > -INFINITY) || !(gmax < INFINITY)) { bad = 1; width = 1.f; lo = 0.f; thr = INFINITY; }
+        if (!live) thr = INFINITY;                                   // padding rows: nothing passes, nothing is written
+        rs[RS_THR * TC_M] = float_key(thr);
+        rs[RS_CNT * TC_M] = 0;
+        rs[RS_LO * TC_M] = __float_as_uint(lo);
+        rs[RS_SCALE * TC_M] = __float_as_uint(1.0f / width);
+        rs[RS_WIDTH * TC_M] = __float_as_uint(width);
+        rs[RS_BAD * TC_M] = bad;
+#pragma unroll
+        for (int b = 0; b < FZ_NB / 2; ++b) hist[b * TC_M] = 0;
+    }
+    epi_bar_sync(n_epi);                                             // row state visible to every set
+    const float lo = __uint_as_float(rs[RS_LO * TC_M]), scale = __uint_as_float(rs[RS_SCALE * TC_M]);
+    const float width = __uint_as_float(rs[RS_WIDTH * TC_M]);
+    volatile uint32_t* thr_key = rs + RS_THR * TC_M;
+
+    for (int t = par; t < n_tiles; t += L.parities) {
+        const uint32_t buf = t & 1;
+        mbar_wait(bar + (9 + buf) * 8, (t >> 1) & 1);
+        fence_after_sync();
+        const uint32_t foreign = live ? ld_relaxed_u32(p.gthr + row) : 0u;   // consumed after the tile
+        const uint32_t tbase = lane_base + buf * TC_N + half * FZ_HALF;
+        const int col_base = (it0 + t) * TC_N + half * FZ_HALF;
+        const int n_valid = n_items32 - col_base;                    // columns of this half tile inside the catalogue
+#pragma unroll 1
+        for (int c = 0; c < FZ_HALF / FZ_CH; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x16(tbase + c * FZ_CH, v);
+            tmem_ld_wait();
+            if (n_valid < FZ_HALF) {                                 // last, partial tile only
+#pragma unroll
+                for (int j = 0; j < FZ_CH; ++j)
+                    if (c * FZ_CH + j >= n_valid) v[j] = 0xff800000u;   // -inf
+            }
+            const float thr = key_float(*thr_key);
+            // Branch-free filter: one bit per value.  Rows (= lanes) hit at different columns, so a per-value branch
+            // would run its body for almost every column; instead the hits are walked per lane afterwards.
+            uint32_t hits = 0;
+#pragma unroll
+            for (int j = 0; j < FZ_CH; ++j) hits |= (__uint_as_float(v[j]) >= thr ? 1u : 0u) << j;
+            if (__any_sync(0xffffffffu, hits != 0)) {
+#pragma unroll
+                for (int j = 0; j < FZ_CH; ++j) sc[j * 32] = __uint_as_float(v[j]);   // own column only: no sync needed
+                const int nmax = __reduce_max_sync(0xffffffffu, __popc(hits));
+#pragma unroll 2
+                for (int h = 0; h < nmax; ++h) {                     // warp-uniform trip count, predicated body
+                    const bool on = hits != 0;
+                    const int j = on ? __ffs(hits) - 1 : 0;
+                    hits &= hits - 1;
+                    const float x = sc[j * 32];
+                    if (on) {
+                        const uint32_t pos = atomicAdd(rs + RS_CNT * TC_M, 1u);
+                        if (pos < (uint32_t)p.cap) {
+                            cand[pos] = make_float2(x, __int_as_float(col_base + c * FZ_CH + j));
+                            int b = (int)((x - lo) * scale);
+                            b = b < 0 ? 0 : (b > FZ_NB - 1 ? FZ_NB - 1 : b);
+                            atomicAdd(hist + (b >> 1) * TC_M, (b & 1) ? 65536u : 1u);   // after the append: counted => listed
+                        }
+                    }
+                }
+            }
+        }
+        // accumulator drained: hand the TMEM buffer back before the (SMEM-only) threshold update
+        fence_before_sync();
+        mbar_arrive(bar + (11 + buf) * 8);
+        // Raise the row threshold to the highest bin edge that keeps `need` counted candidates above it.  Counters of
+        // other sets may be moving: any snapshot is a lower bound, so what it certifies stays certified.
+        int cnum = 0, b = FZ_NB - 1;
+        for (; b >= 0; --b) {
+            const uint32_t w = hist[(b >> 1) * TC_M];
+            cnum += (b & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
+            if (cnum >= need) break;
+        }
+        uint32_t mine = 0;
+        if (b >= 0 && live) {
+            float cert = lo;                                         // b == 0: everything counted is >= thr0
+            if (b > 0) {
+                const float edge = lo + (float)b * width;
+                cert = edge - 2e-6f * fmaxf(fmaxf(fabsf(edge), fabsf(lo)), width);   // slack for the bin index rounding
+            }
+            mine = float_key(cert);
+            if (mine > *thr_key) {
+                atomicMax(rs + RS_THR * TC_M, mine);
+                atomicMax(p.gthr + row, mine);
+            }
+        }
+        if (foreign > *thr_key) atomicMax(rs + RS_THR * TC_M, foreign);
+    }
+    epi_bar_sync(n_epi);                                             // every set is done with the row state
+    if (set == 0 && live) {
+        if (n_tiles > 0) {
+            const uint32_t cnt = rs[RS_CNT * TC_M];
+            p.cnt[row * p.n_splits + sp] = cnt < (uint32_t)p.cap ? (int32_t)cnt : p.cap;
+            p.thr[row * p.n_splits + sp] = key_float(rs[RS_THR * TC_M]);
+            // (a split that never collected `need` candidates keeps a low threshold; the select kernel certifies the
+            // row globally, see there)
+            if (rs[RS_BAD * TC_M]) atomicOr(p.flags + row, 1);                // degenerate seed (NaN / inf / constant scores)
+            if (cnt > (uint32_t)p.cap) atomicOr(p.flags + row, 2);           // candidate list overflow
+        } else {
+            p.cnt[row * p.n_splits + sp] = 0;
+            p.thr[row * p.n_splits + sp] = -INFINITY;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FZ_MAX_THREADS, 1) score_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const FzSmem L = fz_smem(p.KP);
     const uint32_t sbase = smem_u32(smem);
@@ -118,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
     const uint32_t bar = sbase + L.bars;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 11; ++i) mbar_init(bar + i * 8, 1);
-        mbar_init(bar + 11 * 8, 128); mbar_init(bar + 12 * 8, 128);
+        mbar_init(bar + 11 * 8, 256); mbar_init(bar + 12 * 8, 256);   // both column halves release a TMEM buffer
         mbar_fence_init();
     }
     if (warp == 1) { tmem_alloc(sbase + L.tmem_ptr, 512); tmem_relinquish(); }
@@ -135,146 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) score_fused_kernel(const FusedP
     } else if (warp == 1) {
         if (lane == 0 && it0 < it1) fz_mma(p, L, sbase, tmem_base, it0, it1);
     } else {
-        const int q = warp & 3;
-        const int rl = q * 32 + lane;                               // row inside the tile = TMEM lane
-        const int64_t row = (int64_t)ut * TC_M + rl;
-        const bool live = row < p.B;
-        uint16_t* hist = reinterpret_cast<uint16_t*>(smem + L.hist);   // [bin][row]
-        // this thread's column of its warp's chunk scratch: sc[j * 32] is value j of the current chunk (dynamic index)
-        float* sc = reinterpret_cast<float*>(smem + L.scratch) + (warp & 3) * 1024 + lane;
-        int need = p.k;
-        if (live && p.mask_ptr) need += p.mask_ptr[row + 1] - p.mask_ptr[row];
-        float2* cand = p.cand + ((int64_t)(live ? row : 0) * p.n_splits + sp) * p.cap;
-        float thr = INFINITY, lo = 0.f, scale = 0.f, width = 1.f;
-        int cnt = 0, bad = 0;
-        const int n_items32 = (int)p.n_items;
-
-        auto bin_of = [&](float v) -> int {
-            int b = (int)((v - lo) * scale);
-            return b < 0 ? 0 : (b > FZ_NB - 1 ? FZ_NB - 1 : b);
-        };
-
-        for (int it = it0, t = 0; it < it1; ++it, ++t) {
-            const uint32_t buf = t & 1;
-            mbar_wait(bar + (9 + buf) * 8, (t >> 1) & 1);
-            fence_after_sync();
-            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TC_N;
-            const int col_base = it * TC_N;
-            const int n_valid = n_items32 - col_base;                // columns of this tile inside the catalogue (>= 256: all)
-            if (t == 0) {
-                // Seed.  gm[] = maxima of the 32 groups of 8 columns; thr0 = the r-th largest of them, so about r of the
-                // 256 scores of this tile pass.  r aims at ~2.5x the share the row finally needs (need / n_items) and is
-                // at least 8: with 4-5 item splits the row threshold (max over splits) then still leaves >= need items
-                // above it in all but a fraction of a percent of the rows (those go to the exact kernel).
-                float gm[32];
-#pragma unroll 1
-                for (int c8 = 0; c8 < TC_N / 32; ++c8) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(tbase + c8 * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
-                        float m = -INFINITY;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float x = (c8 * 32 + gq * 8 + j < n_valid) ? __uint_as_float(v[gq * 8 + j]) : -INFINITY;
-                            m = fmaxf(m, x);
-                        }
-#pragma unroll
-                        for (int s2 = 0; s2 < 8; ++s2)               // static register index: gm[c8*4+gq] = m
-                            if (s2 == c8) gm[s2 * 4 + gq] = m;
-                    }
-                }
-                float gmax = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) gmax = fmaxf(gmax, gm[j]);
-                int r = (int)ceilf(2.5f * (float)need * 256.f / (float)p.n_items);
-                r = r < 8 ? 8 : (r > 32 ? 32 : r);
-                float cur = gmax;
-                for (int i = 1; i < r; ++i) {                        // peel off the i-th largest (one instance at a time)
-                    float nxt = -INFINITY;
-                    bool removed = false;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (!removed && gm[j] == cur) { gm[j] = -INFINITY; removed = true; }
-                        nxt = fmaxf(nxt, gm[j]);
-                    }
-                    cur = nxt;
-                }
-                thr = lo = cur;
-                width = (gmax - cur) * (1.0f / 16.f);
-                if (!(width > 0.f) || !(cur > -INFINITY) || !(gmax < INFINITY)) { bad = 1; width = 1.f; lo = 0.f; thr = INFINITY; }
-                if (!live) thr = INFINITY;                          // padding rows: nothing passes, nothing is written
-                scale = 1.0f / width;
-#pragma unroll
-                for (int b = 0; b < FZ_NB; ++b) hist[b * TC_M + rl] = 0;
-            }
-#pragma unroll 1
-            for (int c8 = 0; c8 < TC_N / 32; ++c8) {
-                uint32_t v[32];
-                tmem_ld_32x32(tbase + c8 * 32, v);
-                tmem_ld_wait();
-                if (n_valid < TC_N) {                                // last, partial tile only
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c8 * 32 + j >= n_valid) v[j] = 0xff800000u;   // -inf
-                }
-                // Branch-free filter: one bit per value.  Rows (= lanes) hit at different columns, so a per-value branch
-                // would run its body for almost every column; instead the hits are walked per lane afterwards.
-                uint32_t hits = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) hits |= (__uint_as_float(v[j]) >= thr ? 1u : 0u) << j;
-                if (__any_sync(0xffffffffu, hits != 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sc[j * 32] = __uint_as_float(v[j]);   // own column only: no sync needed
-                    while (hits) {
-                        const int j = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const float x = sc[j * 32];
-                        if (cnt < p.cap) cand[cnt] = make_float2(x, __int_as_float(col_base + c8 * 32 + j));
-                        ++cnt;
-                        uint16_t& h = hist[bin_of(x) * TC_M + rl];
-                        if (h < 0xffff) ++h;
-                    }
-                }
-            }
-            // accumulator drained: hand the TMEM buffer back before the (SMEM-only) threshold update
-            fence_before_sync();
-            mbar_arrive(bar + (11 + buf) * 8);
-            if (cnt > p.cap) bad = 1;
-            // raise the threshold to the highest bin edge that keeps `need` counted candidates above it
-            int c = 0, b = FZ_NB - 1;
-            for (; b >= 0; --b) {
-                c += hist[b * TC_M + rl];
-                if (c >= need) break;
-            }
-            if (b > 0) {
-                const float edge = lo + (float)b * width;
-                const float safe = edge - 2e-6f * fmaxf(fmaxf(fabsf(edge), fabsf(lo)), width);   // bin_of() rounding slack
-                if (safe > thr) thr = safe;
-                if (b == FZ_NB - 1 && !bad) {
-                    // everything needed sits in the clamped top bin: slide the window up and recount the survivors
-                    lo = safe;
-#pragma unroll
-                    for (int bb = 0; bb < FZ_NB; ++bb) hist[bb * TC_M + rl] = 0;
-                    const int n = cnt < p.cap ? cnt : p.cap;
-                    for (int j = 0; j < n; ++j) {
-                        const float x = cand[j].x;
-                        if (x >= thr) { uint16_t& h = hist[bin_of(x) * TC_M + rl]; if (h < 0xffff) ++h; }
-                    }
-                }
-            }
-        }
-        if (live && it0 < it1) {
-            p.cnt[row * p.n_splits + sp] = cnt < p.cap ? cnt : p.cap;
-            p.thr[row * p.n_splits + sp] = thr;
-            // (a split that never collected `need` candidates keeps a low threshold; the select kernel certifies the
-            // row globally, see there)
-            if (bad) atomicOr(p.flags + row, 1);
-        } else if (live) {
-            p.cnt[row * p.n_splits + sp] = 0;
-            p.thr[row * p.n_splits + sp] = -INFINITY;
-        }
+        fz_epilogue(p, L, smem, sbase, tmem_base, ut, sp, it0, it1, warp, lane);
     }
     fence_before_sync();
     __syncthreads();
@@ -323,6 +385,7 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
                                                            const int32_t* __restrict__ mask_items, int32_t* __restrict__ flags,
                                                            int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
     __shared__ uint64_t fin_all[4][FZ_WFIN];
+    __shared__ uint32_t hist_all[4][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * 4 + warp;
     if (row >= B || flags[row]) return;                              // (flagged: already condemned to the exact kernel)
@@ -330,29 +393,33 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
     // Certificate: every split's list holds ALL of its items with value >= its own final threshold, hence all items
     // >= T = max over splits.  If at least k unmasked items clear T, the global top-k is among them.
-    float T = -INFINITY;
-    for (int s = 0; s < n_splits; ++s) T = fmaxf(T, thr[row * n_splits + s]);
+    // (lane s holds split s's count and threshold, lane q the q-th masked item: one round trip to memory for all of them)
+    const int my_cnt = lane < n_splits ? cnt[row * n_splits + lane] : 0;
+    float T = lane < n_splits ? thr[row * n_splits + lane] : -INFINITY;
+    for (int s = 32 + lane; s < n_splits; s += 32) T = fmaxf(T, thr[row * n_splits + s]);
+    const int mlen = m1 - m0;
+    const int my_mask = lane < mlen ? mask_items[m0 + lane] : INT_MIN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) T = fmaxf(T, __shfl_xor_sync(0xffffffffu, T, o));
+    const int mreg = mlen < 32 ? mlen : 32;
     int n = 0;
     bool over = false;
     for (int s = 0; s < n_splits; ++s) {
-        const int ns = cnt[row * n_splits + s];
+        const int ns = s < 32 ? __shfl_sync(0xffffffffu, my_cnt, s) : cnt[row * n_splits + s];
         const float2* cs = cand + (row * n_splits + s) * cap;
         for (int j0 = 0; j0 < ns; j0 += 32) {
             const int j = j0 + lane;
-            bool keep = false;
-            float2 c = make_float2(0.f, 0.f);
-            if (j < ns) {
-                c = cs[j];
-                keep = c.x >= T;
-                if (keep) {
-                    const int item = __float_as_int(c.y);
-                    for (int q = m0; q < m1; ++q) keep &= (mask_items[q] != item);
-                }
-            }
+            float2 c = make_float2(-INFINITY, 0.f);
+            if (j < ns) c = cs[j];
+            bool keep = j < ns && c.x >= T;
+            const int item = __float_as_int(c.y);
+            for (int q = 0; q < mreg; ++q) keep &= (__shfl_sync(0xffffffffu, my_mask, q) != item);
+            if (keep)
+                for (int q = m0 + 32; q < m1; ++q) keep &= (mask_items[q] != item);
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             const int pos = n + __popc(bal & ((1u << lane) - 1u));
             if (keep) {
-                if (pos < FZ_WFIN) fin[pos] = ((uint64_t)float_key(c.x) << 32) | (uint32_t)(~(uint32_t)__float_as_int(c.y));
+                if (pos < FZ_WFIN) fin[pos] = ((uint64_t)float_key(c.x) << 32) | (uint32_t)(~(uint32_t)item);
                 else over = true;
             }
             n += __popc(bal);
@@ -360,15 +427,68 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
     }
     over = __any_sync(0xffffffffu, over);
     if (over || n < k) {                                             // cannot certify this row: exact kernel takes it
-        if (lane == 0) flags[row] = 1;
+        if (lane == 0) flags[row] = over ? 4 : 8;
         return;
     }
     __syncwarp();
-    // composites are unique (item index in the low word): rank = number of larger composites = output position
-    for (int t = lane; t < n; t += 32) {
+    // k-th largest 32-bit key by a warp radix select (4 x 8 bits, per-warp histogram in shared memory) ...
+    uint32_t* hist = hist_all[warp];
+    uint32_t prefix = 0;
+    int need = k;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int b = lane; b < 256; b += 32) hist[b] = 0;
+        __syncwarp();
+        for (int t = lane; t < n; t += 32) {
+            const uint32_t key = (uint32_t)(fin[t] >> 32);
+            if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        // lane l owns bins [8l, 8l+8); `above` = keys in the bins owned by higher lanes (exclusive suffix sum)
+        uint32_t mine[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mine[j] = hist[lane * 8 + j]; tot += mine[j]; }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += v;
+        }
+        uint32_t cum = incl - tot;
+        int dgt = -1;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            if (dgt < 0) {
+                if (cum + mine[j] >= (uint32_t)need) dgt = lane * 8 + j;
+                else cum += mine[j];
+            }
+        }
+        // the highest lane that found a digit wins (the bins above it hold fewer than `need` keys)
+        const unsigned found = __ballot_sync(0xffffffffu, dgt >= 0);
+        const int win = 31 - __clz(found);
+        dgt = __shfl_sync(0xffffffffu, dgt, win);
+        cum = __shfl_sync(0xffffffffu, cum, win);
+        prefix |= (uint32_t)dgt << shift;
+        need -= (int)cum;
+        __syncwarp();
+    }
+    // ... then only the composites with key >= that key (k of them plus ties) are ranked against each other.
+    // Composites are unique (item index in the low word): rank = number of larger composites = output position.
+    int m = 0;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        const uint64_t c = t < n ? fin[t] : 0;
+        const bool keep = t < n && (uint32_t)(c >> 32) >= prefix;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) fin[m + __popc(bal & ((1u << lane) - 1u))] = c;     // in place: writes never pass the reads
+        m += __popc(bal);
+        __syncwarp();
+    }
+    for (int t = lane; t < m; t += 32) {
         const uint64_t me = fin[t];
         int rank = 0;
-        for (int u = 0; u < n; ++u) rank += fin[u] > me;
+        for (int u = 0; u < m; ++u) rank += fin[u] > me;
         if (rank < k) {
             out_idx[row * k + rank] = (int64_t)(uint32_t)(~(uint32_t)me) + item_offset;
             out_val[row * k + rank] = key_float((uint32_t)(me >> 32));
@@ -421,20 +541,63 @@ __global__ void __launch_bounds__(256) exact_keys_kernel(const int64_t* __restri
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
     unsigned* out = keys + (int64_t)sl * n_items;
     const int64_t w = (int64_t)blockIdx.y * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.y * 8;
-    for (int64_t i = w; i < n_items; i += nw) {
-        const float* v = Ie + i * ldi;
-        float acc = 0.f;
+    for (int64_t i0 = w; i0 < n_items; i0 += 4 * nw) {                // 4 items in flight per warp
+        float acc[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (lane + 32 * q < d) acc = fmaf(ur[q], __ldg(v + lane + 32 * q), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const int32_t item = (int32_t)i;
-            for (int q = m0; q < m1; ++q)
-                if (mask_items[q] == item) acc = -1e10f;
-            out[i] = float_key(acc);
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i0 + e * nw;
+            acc[e] = 0.f;
+            if (i < n_items) {
+                const float* v = Ie + i * ldi;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (lane + 32 * q < d) acc[e] = fmaf(ur[q], __ldg(v + lane + 32 * q), acc[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = i0 + e * nw;
+            const float r = warp_sum(acc[e]);
+            if (lane == 0 && i < n_items) out[i] = float_key(r);
         }
     }
+    // mask: every CTA overwrites the keys of the masked items its own warps produced (item i belongs to warp i % nw)
+    __syncthreads();
+    for (int q = m0 + (int)threadIdx.x; q < m1; q += (int)blockDim.x) {
+        const int64_t item = mask_items[q];
+        if (item >= 0 && item < n_items && (item % nw) / 8 == (int64_t)blockIdx.y) out[item] = float_key(-1e10f);
+    }
+}
+
+// Warp 0 of a CTA: the highest digit whose suffix count reaches `need` (lane l owns bins [8l, 8l+8)).
+__device__ __forceinline__ void pick_digit_warp(const unsigned* hist, unsigned need, unsigned prefix, int shift, unsigned* s_prefix,
+                                                unsigned* s_need) {
+    const int lane = threadIdx.x & 31;
+    unsigned mine[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mine[j] = hist[lane * 8 + j]; tot += mine[j]; }
+    unsigned incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += v;
+    }
+    unsigned cum = incl - tot;
+    int dgt = -1;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+        if (dgt < 0) {
+            if (cum + mine[j] >= need) dgt = lane * 8 + j;
+            else cum += mine[j];
+        }
+    }
+    const unsigned found = __ballot_sync(0xffffffffu, dgt >= 0);
+    if (found == 0) {                                                // fewer than `need` keys in total: digit 0 (cannot happen for k <= n)
+        if (lane == 0) { *s_prefix = prefix; *s_need = need; }
+        return;
+    }
+    const int win = 31 - __clz(found);
+    if (lane == win) { *s_prefix = prefix | ((unsigned)dgt << shift); *s_need = need - cum; }
 }
 
 __global__ void __launch_bounds__(256) exact_select_kernel(int64_t n_items, int k, int64_t item_offset, const int32_t* __restrict__ counter,
@@ -460,16 +623,7 @@ __global__ void __launch_bounds__(256) exact_select_kernel(int64_t n_items, int 
             if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned cum = 0;
-            int dgt = 255;
-            for (; dgt > 0; --dgt) {
-                if (cum + hist[dgt] >= need) break;
-                cum += hist[dgt];
-            }
-            s_prefix = prefix | ((unsigned)dgt << shift);
-            s_need = need - cum;
-        }
+        if (tid < 32) pick_digit_warp(hist, need, prefix, shift, &s_prefix, &s_need);
         __syncthreads();
         prefix = s_prefix; need = s_need;
         __syncthreads();
@@ -563,8 +717,7 @@ __global__ void __launch_bounds__(256) exact_overflow_kernel(int64_t B, const in
     const float* u = Ue + (users ? users[row] : row) * ldu;
     for (int c = tid; c < d; c += 256) urow[c] = u[c];
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
-    // key of item i0 + tid: fmaf chain of the CUDA-core GEMM (k ascending); the 256 items of a tile are staged
-    // through shared memory so that the global reads are coalesced.  Returns 0 for tid beyond the catalogue.
+    // key of item i0 + tid; the items of a tile are staged through shared memory so that the global reads are coalesced.  Returns 0 for tid beyond the catalogue.
     auto tile_key = [&](int64_t i0, bool& valid) -> unsigned {
         __syncthreads();
         const int nt = (int)((n_items - i0) < EX_TILE ? (n_items - i0) : EX_TILE);
@@ -572,8 +725,25 @@ __global__ void __launch_bounds__(256) exact_overflow_kernel(int64_t B, const in
         __syncthreads();
         valid = tid < nt;
         if (!valid) return 0u;
-        float acc = 0.f;
-        for (int c = 0; c < d; ++c) acc = fmaf(urow[c], tile[tid * ldt + c], acc);
+        // the arithmetic of exact_keys_kernel, one thread playing the 32 lanes: lane L sums k = L, L+32, ... with fmaf,
+        // then the xor-butterfly of warp_sum (16, 8, 4, 2, 1) -- so a row gets the same bits whichever exact kernel ran it
+        float part[32];
+#pragma unroll
+        for (int L = 0; L < 32; ++L) part[L] = 0.f;
+        for (int q = 0; q * 32 < d; ++q) {
+#pragma unroll
+            for (int L = 0; L < 32; ++L) {
+                const int c = q * 32 + L;
+                if (c < d) part[L] = fmaf(urow[c], tile[tid * ldt + c], part[L]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int L = 0; L < 32; ++L)
+                if (L < o) part[L] = part[L] + part[L + o];
+        }
+        float acc = part[0];
         const int32_t item = (int32_t)(i0 + tid);
         for (int q = m0; q < m1; ++q)
             if (mask_items[q] == item) acc = -1e10f;
@@ -590,16 +760,7 @@ __global__ void __launch_bounds__(256) exact_overflow_kernel(int64_t B, const in
             if (valid && (key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned cum = 0;
-            int dgt = 255;
-            for (; dgt > 0; --dgt) {
-                if (cum + hist[dgt] >= need) break;
-                cum += hist[dgt];
-            }
-            s_prefix = prefix | ((unsigned)dgt << shift);
-            s_need = need - cum;
-        }
+        if (tid < 32) pick_digit_warp(hist, need, prefix, shift, &s_prefix, &s_need);
         __syncthreads();
         prefix = s_prefix; need = s_need;
         __syncthreads();
@@ -674,7 +835,7 @@ static FzPlan fz_plan(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz
     P.off_ihi = take((size_t)P.n_it * TC_N * P.KP * 4); P.off_ilo = take((size_t)P.n_it * TC_N * P.KP * 4);
     P.off_cand = take((size_t)P.rows_blk * P.splits * P.cap * 8);
     P.off_cnt = take((size_t)P.rows_blk * P.splits * 4); P.off_thr = take((size_t)P.rows_blk * P.splits * 4);
-    P.off_flags = take((size_t)P.rows_blk * 4);
+    P.off_flags = take((size_t)P.rows_blk * 8);                     // flags[rows_blk] | gthr[rows_blk]
     P.off_mptr = take((size_t)(B + 2) * 4); P.off_mcur = take((size_t)(B + 2) * 4);
     P.off_mitems = take((size_t)(mask_nnz > 0 ? mask_nnz : 1) * 4);
     size_t scan_bytes = 0;
@@ -742,14 +903,15 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         pack_split_kernel<TC_M><<<(unsigned)((tu + T - 1) / T), T, 0, stream>>>(nb, users ? users + r0 : nullptr,
                                                                                 users ? Ue : Ue + r0 * ldu, ldu, d, P.KP, Uhi, Ulo, n_ut);
         MMREC_LAUNCH_CHECK();
-        MMREC_CUDA(cudaMemsetAsync(base + P.off_flags, 0, (size_t)nb * 4, stream));
+        MMREC_CUDA(cudaMemsetAsync(base + P.off_flags, 0, (size_t)P.rows_blk * 8, stream));
         FusedParams p;
         p.Uhi = Uhi; p.Ulo = Ulo; p.Ihi = Ihi; p.Ilo = Ilo; p.KP = P.KP; p.n_itiles = (int)P.n_it;
         p.tiles_per_split = P.tiles_per_split; p.n_splits = P.splits; p.cap = P.cap; p.k = k; p.B = nb; p.n_items = n_items;
         p.mask_ptr = has_mask ? mptr + r0 : nullptr;
         p.cand = (float2*)(base + P.off_cand); p.cnt = (int32_t*)(base + P.off_cnt); p.thr = (float*)(base + P.off_thr);
         p.flags = (int32_t*)(base + P.off_flags);
-        score_fused_kernel<<<(unsigned)(n_ut * P.splits), TC_THREADS, L.total, stream>>>(p);
+        p.gthr = (uint32_t*)(base + P.off_flags) + P.rows_blk;
+        score_fused_kernel<<<(unsigned)(n_ut * P.splits), 64 + 128 * L.nsets, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
         fused_select_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,
                                                               mitems, p.flags, out_idx + r0 * k, out_val + r0 * k);
@@ -792,8 +954,14 @@ extern "C" int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, in
     const int64_t nb = B % P.rows_blk ? B % P.rows_blk : P.rows_blk;
     int32_t* h = (int32_t*)malloc((size_t)nb * 4);
     if (!h || cudaMemcpy(h, base + P.off_flags, (size_t)nb * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { free(h); return -1; }
-    int64_t n = 0;
-    for (int64_t i = 0; i < nb; ++i) n += h[i] != 0;
+    int64_t n = 0, why[4] = {0, 0, 0, 0};
+    for (int64_t i = 0; i < nb; ++i) {
+        n += h[i] != 0;
+        for (int b = 0; b < 4; ++b) why[b] += (h[i] >> b) & 1;
+    }
     free(h);
+    if (getenv("MMREC_DEBUG"))
+        fprintf(stderr, "mmrec: fused fallback rows %lld of %lld (degenerate seed %lld, list overflow %lld, > %d finalists %lld, < k certified %lld)\n",
+                (long long)n, (long long)nb, (long long)why[0], (long long)why[1], FZ_WFIN, (long long)why[2], (long long)why[3]);
     return n;
 }

@@ -28,11 +28,21 @@ struct SpmmParams {
     const float* acc_in; float* acc_out; int64_t ldacc; float acc_div;
     const float* gate_ref; int64_t ldgate;
     int d;
+    uint32_t sx, sy, sacc, sgate;      // the leading dimensions as byte strides (vector kernel: one IMAD.WIDE per row address)
 };
 
 // T lanes cooperate on one task (row or row segment); a warp runs 32/T tasks at once.  Fewer lanes per row
 // means more rows in flight per SM -- the kernel is bound by dependent-load latency (task descriptor -> column
 // indices -> rows of X), not by bytes, so rows in flight is what buys throughput at Amazon-scale graphs.
+
+// Row `r`, float4 number `f4` of a matrix with byte stride `stride`: 32 x 32 -> 64-bit multiply-add, one instruction.
+__device__ __forceinline__ const float4* row_f4(const float* base, uint32_t stride, int r, int f4) {
+    return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(base) + (uint64_t)(uint32_t)r * stride) + f4;
+}
+__device__ __forceinline__ float4* row_f4(float* base, uint32_t stride, int r, int f4) {
+    return reinterpret_cast<float4*>(reinterpret_cast<char*>(base) + (uint64_t)(uint32_t)r * stride) + f4;
+}
+
 template <int D, int T>
 struct VecCfg {
     static_assert(D % (4 * T) == 0, "row must split into float4 per lane");
@@ -52,7 +62,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, bool on, int 
         if (on) {
 #pragma unroll
             for (int v = 0; v < C::V; ++v) {
-                float4 r = ldg4(p.gate_ref + (int64_t)row * p.ldgate + (v * T + l) * 4);
+                float4 r = __ldg(row_f4(p.gate_ref, p.sgate, row, v * T + l));
                 dot += y[v].x * r.x + y[v].y * r.y + y[v].z * r.z + y[v].w * r.w;
                 ny += y[v].x * y[v].x + y[v].y * y[v].y + y[v].z * y[v].z + y[v].w * y[v].w;
                 nr += r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
@@ -73,7 +83,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, bool on, int 
     if (p.Y) {
 #pragma unroll
         for (int v = 0; v < C::V; ++v)
-            *reinterpret_cast<float4*>(p.Y + (int64_t)row * p.ldy + (v * T + l) * 4) = y[v];
+            *row_f4(p.Y, p.sy, row, v * T + l) = y[v];
     }
     if (p.acc_out) {
 #pragma unroll
@@ -84,7 +94,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, bool on, int 
                 a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
                 a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
             }
-            *reinterpret_cast<float4*>(p.acc_out + (int64_t)row * p.ldacc + (v * T + l) * 4) = a;
+            *row_f4(p.acc_out, p.sacc, row, v * T + l) = a;
         }
     }
 }
@@ -95,20 +105,23 @@ template <int D, int T>
 __device__ __forceinline__ void spmm_gather(const SpmmParams& p, int b, int len, int maxlen, int l, float4 (&acc)[VecCfg<D, T>::V]) {
     using C = VecCfg<D, T>;
     int cj[C::UNR]; float wj[C::UNR];
+    const int32_t* cp = p.colidx + b;                                // walked with immediate offsets: no per-load address math
+    const float* vp = p.vals + b;
+    const float* xl = p.X + l * 4;
 #pragma unroll
     for (int u = 0; u < C::UNR; ++u) {
         const bool ok = u < len;
-        cj[u] = ok ? __ldg(p.colidx + b + u) : 0;
-        wj[u] = ok ? __ldg(p.vals + b + u) : 0.f;
+        cj[u] = ok ? __ldg(cp + u) : 0;
+        wj[u] = ok ? __ldg(vp + u) : 0.f;
     }
-    for (int j0 = 0; j0 < maxlen; j0 += C::UNR) {
+    for (int j0 = 0; j0 < maxlen; j0 += C::UNR, cp += C::UNR, vp += C::UNR) {
         float4 x[C::UNR][C::V];
 #pragma unroll
         for (int u = 0; u < C::UNR; ++u) {
             const bool ok = j0 + u < len;
 #pragma unroll
             for (int v = 0; v < C::V; ++v)
-                x[u][v] = ok ? ldg4(p.X + (int64_t)cj[u] * p.ldx + (v * T + l) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[u][v] = ok ? __ldg(row_f4(xl, p.sx, cj[u], v * T)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float wc[C::UNR];
 #pragma unroll
@@ -116,8 +129,8 @@ __device__ __forceinline__ void spmm_gather(const SpmmParams& p, int b, int len,
 #pragma unroll
         for (int u = 0; u < C::UNR; ++u) {
             const bool ok = j0 + C::UNR + u < len;
-            cj[u] = ok ? __ldg(p.colidx + b + j0 + C::UNR + u) : 0;
-            wj[u] = ok ? __ldg(p.vals + b + j0 + C::UNR + u) : 0.f;
+            cj[u] = ok ? __ldg(cp + C::UNR + u) : 0;
+            wj[u] = ok ? __ldg(vp + C::UNR + u) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < C::UNR; ++u) {
@@ -179,7 +192,7 @@ __device__ __forceinline__ bool spmm_split_finish(const SpmmParams& p, bool spli
         if (p.acc_in) {
 #pragma unroll
             for (int v = 0; v < C::V; ++v)
-                accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
+                accin[v] = *row_f4(p.acc_in, p.sacc, row, v * T + l);
         }
         if (l == 0) p.counters[sid] = 0;                    // self-cleaning for the next launch
         last = true;
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
         if (warp == 0 && g == 0 && p.acc_in && sid < 0) {
 #pragma unroll
             for (int v = 0; v < C::V; ++v)
-                accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
+                accin[v] = *row_f4(p.acc_in, p.sacc, row, v * T + l);
         }
         float4 acc[C::V];
 #pragma unroll
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
         if (valid && p.acc_in && sid < 0) {                         // epilogue operand does not depend on the gather
 #pragma unroll
             for (int v = 0; v < C::V; ++v)
-                accin[v] = *reinterpret_cast<const float4*>(p.acc_in + (int64_t)row * p.ldacc + (v * T + l) * 4);
+                accin[v] = *row_f4(p.acc_in, p.sacc, row, v * T + l);
         }
         float4 acc[C::V];
 #pragma unroll
@@ -390,6 +403,9 @@ extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32
     p.counters = counters; p.partial = partial; p.X = X; p.ldx = ldx; p.Y = Y; p.ldy = ldy;
     p.acc_in = acc_in; p.acc_out = acc_out; p.ldacc = ldacc; p.acc_div = acc_div; p.gate_ref = gate_ref;
     p.ldgate = ldgate; p.d = d;
+    MMREC_CHECK_ARG(ldx < (1ll << 30) && ldy < (1ll << 30) && ldacc < (1ll << 30) && ldgate < (1ll << 30) && n_cols < (1ll << 31) &&
+                    n_rows < (1ll << 31), "spmm: leading dimension / size out of range");
+    p.sx = (uint32_t)(ldx * 4); p.sy = (uint32_t)(ldy * 4); p.sacc = (uint32_t)(ldacc * 4); p.sgate = (uint32_t)(ldgate * 4);
     auto al16 = [](const void* q, int64_t ld) { return q == nullptr || ((((uintptr_t)q) & 15) == 0 && (ld & 3) == 0); };
     const bool vec_ok = al16(X, ldx) && al16(Y, ldy) && al16(acc_in, ldacc) && al16(acc_out, ldacc) &&
                         al16(gate_ref, ldgate) && al16(partial, 4);

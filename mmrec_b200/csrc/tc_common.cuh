@@ -122,6 +122,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = __uint_as_float(l);
 }
 
+// Cheaper split for streamed operands (2 instructions instead of 9): hi = x with the low 13 mantissa bits cleared, lo = x - hi
+// exactly (< 2^-10 |x|); the tensor core reads the top 19 bits of lo.  x = hi + lo to ~2^-20 |x|: enough for the 1e-4
+// bar of the projections, not for ranking scores (those use split_tf32).
+__device__ __forceinline__ void split_tf32_trunc(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = x - hi;
+}
+
 }  // namespace tc
 
 // ---- tile geometry shared by the tensor-core kernels ---------------------------------------------------------
