@@ -44,17 +44,42 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/summarize_ncu.py); None when no capture is recorded."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the first warm-up step to the end of the timed
-    regions (the device-only region of this workload lasts tens of milliseconds, shorter than one sampling period,
-    so the window also covers the warm-up and the e2e region, all of them under the same load)."""
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML (the library nvidia-smi prints from) polled
+    every 5 ms from a thread -- the device-only region of this workload lasts ~10 ms, shorter than one period of
+    `nvidia-smi -lms`; falls back to the nvidia-smi loop when the NVML binding is missing."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.nvml, self.stop_flag = [], None, index, None, False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(self.index)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.h = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -63,11 +88,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4))))
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                mask = int(get_reasons(self.h))
+                self.rows.append((sm, [name for name, b in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            if not self.rows:
+                return None
+            reasons = sorted({r for _, rs in self.rows for r in rs})
+            return {"sm_mhz": float(np.median([sm for sm, _ in self.rows])), "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(self.rows), "source": "nvml, 5 ms period"}
         if not self.proc:
             return None
         self.proc.terminate()
@@ -86,7 +135,8 @@ class ClockSampler:
                 pass
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 50"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -208,11 +258,11 @@ def run_ours(args):
             state["u"], state["i"] = sec_a(); sec_b(); sec_c()
         torch.cuda.synchronize()
         for name, fn in (("a", sec_a), ("b", sec_b), ("c", sec_c)):
-            l0 = ops.LAUNCHES
+            l0 = ops.launch_count()
             gph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gph, stream=side):
                 out = fn()
-            graphs[name], n_launch[name] = gph, ops.LAUNCHES - l0
+            graphs[name], n_launch[name] = gph, ops.launch_count() - l0
             if name == "a":
                 state["u"], state["i"] = out
             state["out_" + name] = out
@@ -286,12 +336,12 @@ def run_ours(args):
                   "wall_s_timed_region": wall, "score_path": os.environ.get("MMREC_SCORE_PATH", "auto")},
         "roofline": {"kernel": "spmm_vec_kernel<64,16> (4 launches: 3 x A_hat + mm_adj)", "bound": "hbm",
                      "achieved": spmm_bytes / (msA * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": spmm_bytes / (msA * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
+                     "frac": spmm_bytes / (msA * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": ncu_traffic("spmm_vec_kernel"), "peak_src": pk["src"],
                      "algorithmic_bytes_per_launch_ui": ui_bytes},
         "roofline_projection": {"kernel": "project_tc_kernel + project_reduce_kernel (2 modalities)", "bound": "hbm",
                                 "achieved": proj_bytes / (msB * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                 "frac": proj_bytes / (msB * 1e-3) / 1e9 / pk["hbm_gbs"], "tflops": proj_flops / (msB * 1e-3) / 1e12},
-        "roofline_scoring": {"kernel": "score_tc_kernel + mask_kernel + topk_stream_kernel (auto path)", "bound": "tensor",
+        "roofline_scoring": {"kernel": "score_fused_kernel + fused_select_kernel (+ mask CSR, operand packing; auto path)", "bound": "tensor",
                              "achieved": score_flops / (msC * 1e-3) / 1e12, "peak": pk["bf16_tflops"] / 2, "unit": "TFLOP/s",
                              "frac": score_flops / (msC * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
                              "note": "peak = measured bf16 dense / 2 (TF32 rate); useful flops 2*B*I*d"},
@@ -314,9 +364,9 @@ def cpu_setup(wl, kr, kc, kv):
     return O, adj, mm, torch.from_numpy(wl.user_emb), torch.from_numpy(wl.item_emb)
 
 
-def cpu_step(O, wl, adj, mm, ue, ie, n_eval_batches=1):
+def cpu_step(O, wl, adj, mm, ue, ie, n_eval_batches=1, mm_layers=1):
     t0 = time.perf_counter()
-    u_g, i_g = O.freedom_forward(adj, mm, ue, ie, 1, wl.n_layers)          # freedom.py:164-178
+    u_g, i_g = O.freedom_forward(adj, mm, ue, ie, mm_layers, wl.n_layers)  # freedom.py:164-178
     t1 = time.perf_counter()
     scored = 0
     for b in range(n_eval_batches):
@@ -331,7 +381,7 @@ def cpu_step(O, wl, adj, mm, ue, ie, n_eval_batches=1):
     return t1 - t0, t2 - t1, scored
 
 
-def pick_threads(O, wl, adj, mm, ue, ie):
+def pick_threads(O, wl, adj, mm, ue, ie, mm_layers=1):
     """Give the CPU arm its best shot: torch's sparse/dense kernels at this size get slower when oversubscribed,
     so try a few thread counts (up to all host cores) on one step and keep the fastest."""
     cores = os.cpu_count() or 1
@@ -339,8 +389,8 @@ def pick_threads(O, wl, adj, mm, ue, ie):
     with torch.no_grad():
         for t in sorted({min(cores, c) for c in (4, 8, 16, 32, 64, cores)}):
             torch.set_num_threads(t)
-            cpu_step(O, wl, adj, mm, ue, ie)
-            a, c, _ = cpu_step(O, wl, adj, mm, ue, ie)
+            cpu_step(O, wl, adj, mm, ue, ie, mm_layers=mm_layers)
+            a, c, _ = cpu_step(O, wl, adj, mm, ue, ie, mm_layers=mm_layers)
             if a + c < best_t:
                 best, best_t = t, a + c
     torch.set_num_threads(best)
@@ -368,16 +418,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = Workload(args.workload, n_layers=3)
+    # the same workload as this repo's arm at --gpus N: weak scaling = N x the items and edges (the N > 1 arm
+    # propagates the 3 user-item layers only, so the item-item layer is left out here too)
+    wl = Workload(args.workload, n_layers=3, items_scale=max(1, args.gpus))
+    mm_layers = 1 if args.gpus <= 1 else 0
     kr, kc, kv = wl.knn_coo()
     O, adj, mm, ue, ie = cpu_setup(wl, kr, kc, kv)
-    threads = pick_threads(O, wl, adj, mm, ue, ie)
-    edges = wl.n_layers * adj._nnz() + mm._nnz()
+    threads = pick_threads(O, wl, adj, mm, ue, ie, mm_layers)
+    edges = wl.n_layers * adj._nnz() + mm_layers * mm._nnz()
     ta = tc = 0.0
     sc = 0
     with torch.no_grad():
         for step in range(args.warmup + args.steps):
-            a, c, s = cpu_step(O, wl, adj, mm, ue, ie)
+            a, c, s = cpu_step(O, wl, adj, mm, ue, ie, mm_layers=mm_layers)
             if step >= args.warmup:
                 ta += a; tc += c; sc += s
     K = args.steps
@@ -390,7 +443,7 @@ def run_reference(args):
         "ms_per_step": (ta + tc) / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"FREEDOM synthetic {wl.name}: {wl.U} users, {wl.I} items, {len(wl.tr_u)} train edges, d={wl.d}, "
-                               f"{wl.n_layers} UI layers + 1 mm layer", "parallelism": f"CPU, {threads} threads"},
+                               f"{wl.n_layers} UI layers + {mm_layers} mm layer", "parallelism": f"CPU, {threads} threads"},
         "extra": {"prop_ms": ta / K * 1e3, "score_topk_ms_per_batch": tc / K * 1e3, "scored_items_per_sec": sc / tc},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

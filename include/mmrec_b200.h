@@ -39,6 +39,9 @@ int mmrec_abi_version(void);
 const char* mmrec_last_error(void);
 /* 0 if the current device can run this library (compute capability 10.x), else MMREC_EUNSUPPORTED */
 int mmrec_device_check(void);
+/* Kernels of this library launched by the calling process so far (every launch site counts itself; library
+ * primitives -- CUB sort/scan, memsets -- are not counted).  bench.py reports the difference over its timed region. */
+int64_t mmrec_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K1c  COO -> CSR.   Replaces the per-call `coalesce()` + COO->CSR conversion hidden inside every

@@ -18,6 +18,7 @@ PROTOTYPES = {
     "mmrec_abi_version": (_i32, []),
     "mmrec_last_error": (C.c_char_p, []),
     "mmrec_device_check": (_i32, []),
+    "mmrec_launch_count": (_i64, []),
     "mmrec_csr_from_coo_workspace_bytes": (_sz, [_i64, _i64]),
     "mmrec_csr_from_coo": (_i32, [_i64, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "mmrec_spmm_plan_workspace_bytes": (_sz, [_i64, _i64]),

@@ -26,7 +26,12 @@ void set_error(const char* fmt, ...);
         }                                                                                         \
     } while (0)
 
-#define MMREC_LAUNCH_CHECK() MMREC_CUDA(cudaGetLastError())
+extern long long g_launches;   // kernels launched (mmrec_launch_count)
+#define MMREC_LAUNCH_CHECK()            \
+    do {                                \
+        ++::mmrec::g_launches;          \
+        MMREC_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

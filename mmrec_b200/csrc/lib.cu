@@ -27,9 +27,13 @@ int sm_count() {
     return cached[dev];
 }
 
+long long g_launches = 0;
+
 }  // namespace mmrec
 
 extern "C" int mmrec_abi_version(void) { return MMREC_ABI_VERSION; }
+
+extern "C" int64_t mmrec_launch_count(void) { return (int64_t)mmrec::g_launches; }
 
 extern "C" const char* mmrec_last_error(void) { return mmrec::g_err; }
 

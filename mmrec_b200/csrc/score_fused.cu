@@ -359,6 +359,78 @@ __global__ void mask_fill_kernel(int64_t nnz, const int64_t* __restrict__ rows, 
     items[pos] = (int32_t)(cols[j] - item_offset);     // may fall outside [0, n_items): then it never matches
 }
 
+// The same CSR in one launch for the per-batch case (B <= MC_MAX_ROWS rows): one CTA counts in shared memory, scans,
+// fills.  Three passes over the mask entries, no global atomics, no memsets, no library scan.
+constexpr int MC_MAX_ROWS = 8192;
+constexpr int MC_THREADS = 1024;
+__global__ void __launch_bounds__(MC_THREADS) mask_csr_small_kernel(int64_t nnz, const int64_t* __restrict__ rows,
+                                                                    const int64_t* __restrict__ cols, int B, int64_t item_offset,
+                                                                    int32_t* __restrict__ ptr, int32_t* __restrict__ items) {
+    extern __shared__ int32_t mc_sm[];                               // count / cursor [B + 1] | warp totals [32]
+    int32_t* cnt = mc_sm;
+    int32_t* wtot = mc_sm + B + 1;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int r = tid; r <= B; r += MC_THREADS) cnt[r] = 0;
+    __syncthreads();
+    for (int64_t j = tid; j < nnz; j += MC_THREADS) {
+        const int64_t r = rows[j];
+        if (r >= 0 && r < B) atomicAdd(cnt + r, 1);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..B]: each thread owns a contiguous run of rows
+    const int per = (B + 1 + MC_THREADS - 1) / MC_THREADS;
+    const int r0 = tid * per, r1 = min(B + 1, r0 + per);
+    int local = 0;
+    for (int r = r0; r < r1; ++r) local += cnt[r];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = wtot[lane], sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, sc, o);
+            if (lane >= o) sc += u;
+        }
+        wtot[lane] = sc - v;                                         // exclusive warp offsets
+    }
+    __syncthreads();
+    int run = wtot[wid] + incl - local;
+    for (int r = r0; r < r1; ++r) {
+        const int c = cnt[r];
+        ptr[r] = run;
+        cnt[r] = run;                                                // becomes the fill cursor
+        run += c;
+    }
+    __syncthreads();
+    for (int64_t j = tid; j < nnz; j += MC_THREADS) {
+        const int64_t r = rows[j];
+        if (r >= 0 && r < B) items[atomicAdd(cnt + r, 1)] = (int32_t)(cols[j] - item_offset);   // order inside a row is free
+    }
+}
+
+// One launch for everything the scoring kernel needs prepared: item operand (when `n_it` > 0), user operand of this row
+// block, and the zeroing of the per-block scratch words (flags, shared thresholds, slots, slot counter).
+__global__ void fz_prep_kernel(int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int64_t n_it, float* __restrict__ Ihi,
+                               float* __restrict__ Ilo, int64_t nb, const int64_t* __restrict__ users, const float* __restrict__ Ue,
+                               int64_t ldu, int64_t n_ut, float* __restrict__ Uhi, float* __restrict__ Ulo, int d, int KP,
+                               uint32_t* __restrict__ zero0, int64_t zero0_words, uint32_t* __restrict__ zero1, int64_t zero1_words) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t ti = n_it * TC_N * (KP / 4), tu = n_ut * TC_M * (KP / 4);
+    if (t < ti) { pack_split_one<TC_N>(t, n_items, nullptr, Ie, ldi, d, KP, Ihi, Ilo); return; }
+    t -= ti;
+    if (t < tu) { pack_split_one<TC_M>(t, nb, users, Ue, ldu, d, KP, Uhi, Ulo); return; }
+    t -= tu;
+    if (t < zero0_words) { zero0[t] = 0; return; }
+    t -= zero0_words;
+    if (t < zero1_words) zero1[t] = 0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // select: finalists of all splits -> drop masked -> top-k in contract order
 // ------------------------------------------------------------------------------------------------------
@@ -376,6 +448,7 @@ __device__ void fz_bitonic_desc(uint64_t* a, int n) {
     __syncthreads();
 }
 
+constexpr int EX_SLOTS = 128;           // flagged rows served by the cached-key kernels per row block
 constexpr int FZ_WFIN = 512;            // finalists one warp can rank per row (typical: 60-150)
 
 // One warp per row, four rows per CTA.
@@ -383,12 +456,24 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
                                                            const float2* __restrict__ cand, const int32_t* __restrict__ cnt,
                                                            const float* __restrict__ thr, const int32_t* __restrict__ mask_ptr,
                                                            const int32_t* __restrict__ mask_items, int32_t* __restrict__ flags,
+                                                           int32_t* __restrict__ slot, int32_t* __restrict__ counter,
+                                                           int32_t* __restrict__ row_of_slot,
                                                            int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
     __shared__ uint64_t fin_all[4][FZ_WFIN];
     __shared__ uint32_t hist_all[4][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * 4 + warp;
-    if (row >= B || flags[row]) return;                              // (flagged: already condemned to the exact kernel)
+    if (row >= B) return;
+    // A flagged row takes a slot in the key scratch of the exact kernels (slot[] holds slot + 1, 0 = not flagged; the
+    // prep kernel zeroed it together with the counter).
+    auto condemn = [&]() {
+        if (lane == 0) {
+            const int sl = atomicAdd(counter, 1);
+            slot[row] = sl + 1;
+            if (sl < EX_SLOTS) row_of_slot[sl] = (int32_t)row;
+        }
+    };
+    if (flags[row]) { condemn(); return; }                            // the scoring kernel gave up on it (seed / overflow)
     uint64_t* fin = fin_all[warp];
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
     // Certificate: every split's list holds ALL of its items with value >= its own final threshold, hence all items
@@ -428,10 +513,14 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
     over = __any_sync(0xffffffffu, over);
     if (over || n < k) {                                             // cannot certify this row: exact kernel takes it
         if (lane == 0) flags[row] = over ? 4 : 8;
+        condemn();
         return;
     }
     __syncwarp();
-    // k-th largest 32-bit key by a warp radix select (4 x 8 bits, per-warp histogram in shared memory) ...
+    // Few finalists (the usual case): rank them all against each other.  Many: first the k-th largest 32-bit key by a warp
+    // radix select (4 x 8 bits, per-warp histogram in shared memory) ...
+    int m = n;
+    if (n > 96) {
     uint32_t* hist = hist_all[warp];
     uint32_t prefix = 0;
     int need = k;
@@ -475,7 +564,7 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
     }
     // ... then only the composites with key >= that key (k of them plus ties) are ranked against each other.
     // Composites are unique (item index in the low word): rank = number of larger composites = output position.
-    int m = 0;
+    m = 0;
     for (int t0 = 0; t0 < n; t0 += 32) {
         const int t = t0 + lane;
         const uint64_t c = t < n ? fin[t] : 0;
@@ -484,6 +573,7 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
         if (keep) fin[m + __popc(bal & ((1u << lane) - 1u))] = c;     // in place: writes never pass the reads
         m += __popc(bal);
         __syncwarp();
+    }
     }
     for (int t = lane; t < m; t += 32) {
         const uint64_t me = fin[t];
@@ -498,7 +588,7 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
 
 // ------------------------------------------------------------------------------------------------------
 // exact fp32 rows (flagged only).  Three small kernels, all of which exit at once for rows that are not flagged:
-//   exact_slots  : flagged rows take a slot in the key scratch (atomic counter)
+//   (slots in the key scratch are handed out by fused_select_kernel as it flags rows)
 //   exact_keys   : EX_SPLIT CTAs per flagged row recompute its scores with the fmaf chain of the CUDA-core GEMM
 //                  (k ascending, items staged through shared memory so the reads are coalesced), apply the mask and
 //                  store order-preserving keys
@@ -507,19 +597,6 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
 // ------------------------------------------------------------------------------------------------------
 constexpr int EX_SPLIT = 16;
 
-constexpr int EX_SLOTS = 128;           // flagged rows served by the cached-key kernels per row block
-
-__global__ void exact_slots_kernel(int64_t B, const int32_t* __restrict__ flags, int32_t* __restrict__ slot, int32_t* __restrict__ counter,
-                                   int32_t* __restrict__ row_of_slot) {
-    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= B) return;
-    int sl = -1;
-    if (flags[r]) {
-        sl = atomicAdd(counter, 1);
-        if (sl < EX_SLOTS) row_of_slot[sl] = (int32_t)r;
-    }
-    slot[r] = sl;
-}
 
 __global__ void __launch_bounds__(256) exact_keys_kernel(const int64_t* __restrict__ users, const float* __restrict__ Ue, int64_t ldu,
                                                          int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int d,
@@ -704,7 +781,7 @@ __global__ void __launch_bounds__(256) exact_overflow_kernel(int64_t B, const in
     __syncthreads();
     {
         const int64_t r = (int64_t)blockIdx.x * 256 + tid;
-        if (r < B && slot[r] >= first_overflow) todo[atomicAdd(&n_todo, 1)] = (int)r;
+        if (r < B && slot[r] > first_overflow) todo[atomicAdd(&n_todo, 1)] = (int)r;   // slot[] = slot + 1
     }
     __syncthreads();
     const int n_rows_todo = n_todo;
@@ -870,9 +947,20 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
     float *Ihi = (float*)(base + P.off_ihi), *Ilo = (float*)(base + P.off_ilo);
     int32_t *mptr = (int32_t*)(base + P.off_mptr), *mcur = (int32_t*)(base + P.off_mcur), *mitems = (int32_t*)(base + P.off_mitems);
     const int T = 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMREC_CUDA(cudaFuncSetAttribute(exact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(mask_csr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
     // mask -> CSR over batch rows
     const bool has_mask = mask_nnz > 0;
-    if (has_mask) {
+    if (has_mask && B <= MC_MAX_ROWS && mask_nnz <= (1ll << 18)) {
+        mask_csr_small_kernel<<<1, MC_THREADS, (size_t)(B + 1 + 32) * 4, stream>>>(mask_nnz, mask_rows, mask_cols, (int)B, item_offset, mptr,
+                                                                                 mitems);
+        MMREC_LAUNCH_CHECK();
+    } else if (has_mask) {
         MMREC_CUDA(cudaMemsetAsync(mcur, 0, (size_t)(B + 2) * 4, stream));
         mask_count_kernel<<<(unsigned)((mask_nnz + T - 1) / T), T, 0, stream>>>(mask_nnz, mask_rows, B, mcur);
         MMREC_LAUNCH_CHECK();
@@ -883,27 +971,22 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
                                                                               mcur, mitems);
         MMREC_LAUNCH_CHECK();
     }
-    // items: split + re-tile once for all row blocks
-    {
-        const int64_t ti = P.n_it * TC_N * (P.KP / 4);
-        pack_split_kernel<TC_N><<<(unsigned)((ti + T - 1) / T), T, 0, stream>>>(n_items, nullptr, Ie, ldi, d, P.KP, Ihi, Ilo, P.n_it);
-        MMREC_LAUNCH_CHECK();
-    }
     const FzSmem L = fz_smem(P.KP);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMREC_CUDA(cudaFuncSetAttribute(exact_overflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        MMREC_CUDA(cudaFuncSetAttribute(score_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    int32_t* slot = (int32_t*)(base + P.off_slot);                   // slot + 1 per row | counter | row_of_slot[EX_SLOTS]
+    int32_t* counter = slot + P.rows_blk;
+    int32_t* row_of_slot = counter + 1;
+    unsigned* keys = (unsigned*)(base + P.off_keys);
     for (int64_t r0 = 0; r0 < B; r0 += P.rows_blk) {
         const int64_t nb = (B - r0) < P.rows_blk ? (B - r0) : P.rows_blk;
         const int64_t n_ut = (nb + TC_M - 1) / TC_M;
-        const int64_t tu = n_ut * TC_M * (P.KP / 4);
-        pack_split_kernel<TC_M><<<(unsigned)((tu + T - 1) / T), T, 0, stream>>>(nb, users ? users + r0 : nullptr,
-                                                                                users ? Ue : Ue + r0 * ldu, ldu, d, P.KP, Uhi, Ulo, n_ut);
+        // operands (items: split + re-tiled once, with the first row block) + zeroed scratch words, one launch
+        const int64_t n_it_now = r0 == 0 ? P.n_it : 0;
+        const int64_t zero0 = 2 * P.rows_blk, zero1 = P.rows_blk + 1;            // flags | gthr, slot | counter
+        const int64_t prep_threads = n_it_now * TC_N * (P.KP / 4) + n_ut * TC_M * (P.KP / 4) + zero0 + zero1;
+        fz_prep_kernel<<<(unsigned)((prep_threads + T - 1) / T), T, 0, stream>>>(
+            n_items, Ie, ldi, n_it_now, Ihi, Ilo, nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_ut, Uhi, Ulo, d, P.KP,
+            (uint32_t*)(base + P.off_flags), zero0, (uint32_t*)slot, zero1);
         MMREC_LAUNCH_CHECK();
-        MMREC_CUDA(cudaMemsetAsync(base + P.off_flags, 0, (size_t)P.rows_blk * 8, stream));
         FusedParams p;
         p.Uhi = Uhi; p.Ulo = Ulo; p.Ihi = Ihi; p.Ilo = Ilo; p.KP = P.KP; p.n_itiles = (int)P.n_it;
         p.tiles_per_split = P.tiles_per_split; p.n_splits = P.splits; p.cap = P.cap; p.k = k; p.B = nb; p.n_items = n_items;
@@ -914,17 +997,11 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         score_fused_kernel<<<(unsigned)(n_ut * P.splits), 64 + 128 * L.nsets, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
         fused_select_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,
-                                                              mitems, p.flags, out_idx + r0 * k, out_val + r0 * k);
+                                                              mitems, p.flags, slot, counter, row_of_slot, out_idx + r0 * k,
+                                                              out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
-        // rows the filter could not certify: exact fp32 recompute (normally none or a handful per block)
+        // rows the filter could not certify: exact fp32 recompute (normally none; the kernels exit at once then)
         {
-            int32_t* slot = (int32_t*)(base + P.off_slot);
-            int32_t* counter = slot + P.rows_blk;
-            int32_t* row_of_slot = counter + 1;
-            unsigned* keys = (unsigned*)(base + P.off_keys);
-            MMREC_CUDA(cudaMemsetAsync(counter, 0, 4, stream));
-            exact_slots_kernel<<<(unsigned)((nb + T - 1) / T), T, 0, stream>>>(nb, p.flags, slot, counter, row_of_slot);
-            MMREC_LAUNCH_CHECK();
             const int tile_rows = d <= 64 ? 256 : 128;
             const int64_t* ub = users ? users + r0 : nullptr;
             const float* ue = users ? Ue : Ue + r0 * ldu;

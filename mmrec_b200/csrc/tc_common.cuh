@@ -142,12 +142,9 @@ constexpr int TC_THREADS = 192;    // warp 0 producer, warp 1 MMA, warps 2..5 ep
 // operand packing: split into tf32 hi/lo and re-tile as [tile][kblk = KP/4][row group = R/8][8 rows][4 floats], the
 // UMMA canonical K-major no-swizzle layout, so that a K slab of a tile is one contiguous byte range
 template <int R>
-__global__ void pack_split_kernel(int64_t n_rows, const int64_t* __restrict__ idx, const float* __restrict__ E, int64_t ld,
-                                  int d, int KP, float* __restrict__ hi, float* __restrict__ lo, int64_t n_tiles) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per (padded row, kblk)
-    const int kblks = KP / 4;
-    const int64_t total = n_tiles * R * kblks;
-    if (t >= total) return;
+__device__ __forceinline__ void pack_split_one(int64_t t, int64_t n_rows, const int64_t* __restrict__ idx, const float* __restrict__ E,
+                                               int64_t ld, int d, int KP, float* __restrict__ hi, float* __restrict__ lo) {
+    const int kblks = KP / 4;                                          // t = (padded row, kblk)
     const int64_t row = t / kblks;
     const int kb = (int)(t % kblks);
     float x[4] = {0.f, 0.f, 0.f, 0.f};
@@ -164,6 +161,14 @@ __global__ void pack_split_kernel(int64_t n_rows, const int64_t* __restrict__ id
     const int64_t off = ((tile * kblks + kb) * (R / 8) + rr / 8) * 32 + (rr % 8) * 4;
     *reinterpret_cast<float4*>(hi + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+template <int R>
+__global__ void pack_split_kernel(int64_t n_rows, const int64_t* __restrict__ idx, const float* __restrict__ E, int64_t ld,
+                                  int d, int KP, float* __restrict__ hi, float* __restrict__ lo, int64_t n_tiles) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one thread per (padded row, kblk)
+    if (t >= n_tiles * R * (KP / 4)) return;
+    pack_split_one<R>(t, n_rows, idx, E, ld, d, KP, hi, lo);
 }
 
 }  // namespace mmrec

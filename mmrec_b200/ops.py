@@ -18,12 +18,13 @@ _ws_cache: dict = {}
 import os as _os
 SEG = int(_os.environ.get("MMREC_SPMM_SEG", "512"))        # non-zeros per SpMM task (rows longer than this are split)
 LIGHT_MAX = int(_os.environ.get("MMREC_SPMM_LIGHT", "32"))  # tasks longer than this are run by a whole CTA
-LAUNCHES = 0       # kernels of this library launched so far (bench.py's gpu_launches)
 
 
-def _count(n=1):
-    global LAUNCHES
-    LAUNCHES += n
+def launch_count() -> int:
+    """Kernels of this library launched by this process so far: every launch site in the C ABI counts itself
+    (`mmrec_launch_count`); bench.py's `gpu_launches` is the difference over its timed region (for a section replayed
+    from a CUDA graph: the launches recorded while capturing it, times the replays)."""
+    return int(_lib.load().mmrec_launch_count())
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -96,7 +97,6 @@ class CSR:
         check(lib.mmrec_csr_from_coo(nnz, _ptr(row), _ptr(col), _ptr(val), n_rows, n_cols, int(sum_duplicates),
                                      _ptr(rowptr), _ptr(colidx), _ptr(vals), _ptr(nnz_out), _ptr(ws), ws.numel(),
                                      _stream()), "mmrec_csr_from_coo")
-        _count(6)
         n = int(nnz_out.item())
         return CSR(n_rows, n_cols, rowptr, colidx[:max(n, 1)], vals[:max(n, 1)], n, symmetric, seg, light_max)
 
@@ -117,7 +117,6 @@ class CSR:
         ws = _ws("plan", lib.mmrec_spmm_plan_workspace_bytes(self.n_rows, max_tasks), dev)
         check(lib.mmrec_spmm_plan(self.n_rows, _ptr(self.rowptr), self.seg, self.light_max, max_tasks, _ptr(tasks), _ptr(split),
                                   _ptr(counts), _ptr(ws), ws.numel(), _stream()), "mmrec_spmm_plan")
-        _count(8)
         c = counts.tolist()
         self.n_tasks, self.n_split, self.n_slots, self.longest_row = int(c[0]), int(c[1]), int(c[2]), int(c[3])
         self.n_cta_tasks = int(c[4])
@@ -186,7 +185,6 @@ def spmm_raw(A: CSR, X: torch.Tensor, Y: Optional[torch.Tensor] = None, acc_in: 
                              _ptr(A.partial(d)) if plan else None,
                              _ptr(X), X.stride(0), _ptr(Y), d, _ptr(acc_in), _ptr(acc_out), d, float(acc_div),
                              _ptr(gate_ref), d, _stream()), "mmrec_spmm_f32")
-    _count()
 
 
 class _SpmmFn(torch.autograd.Function):
@@ -285,7 +283,6 @@ def project_raw(table, weight, bias, idx=None, l2_normalize=False) -> torch.Tens
     ws = _ws("project", lib.mmrec_project_workspace_bytes(n_out, F, d), table.device)
     check(lib.mmrec_project_f32(n_out, _ptr(idx), _ptr(table), table.shape[0], F, _ptr(weight), _ptr(bias), d,
                                 int(l2_normalize), _ptr(out), d, _ptr(ws), ws.numel(), _stream()), "mmrec_project_f32")
-    _count(3)
     return out
 
 
@@ -351,7 +348,6 @@ def score(user_e, item_e, users=None) -> torch.Tensor:
     ws = _ws("score", lib.mmrec_score_workspace_bytes(B, n_items, d), item_e.device)
     check(lib.mmrec_score_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e), item_e.stride(0), d,
                               _ptr(out), n_items, _ptr(ws), ws.numel(), _stream()), "mmrec_score_f32")
-    _count(3)
     return out
 
 
@@ -367,12 +363,10 @@ def mask_topk(scores: torch.Tensor, mask: Optional[torch.Tensor], k: int, item_o
         mask = mask.to(torch.int64).contiguous()
         check(lib.mmrec_mask_f32(mask.shape[1], _ptr(mask[0]), _ptr(mask[1]), B, n_items, item_offset, _ptr(scores),
                                  n_items, _stream()), "mmrec_mask_f32")
-        _count()
     idx = torch.empty(B, k, dtype=torch.int64, device=scores.device)
     val = torch.empty(B, k, dtype=torch.float32, device=scores.device)
     check(lib.mmrec_topk_rows_f32(B, n_items, _ptr(scores), n_items, k, item_offset, _ptr(idx), _ptr(val), _stream()),
           "mmrec_topk_rows_f32")
-    _count()
     return val, idx
 
 
@@ -398,7 +392,6 @@ def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0):
     check(lib.mmrec_score_topk_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e),
                                    item_e.stride(0), d, nnz, _ptr(m0), _ptr(m1), k, item_offset, _ptr(idx), _ptr(val),
                                    _ptr(ws), ws.numel(), _stream()), "mmrec_score_topk_f32")
-    _count(3)
     return val, idx
 
 
@@ -417,7 +410,6 @@ def topk_merge(vals: torch.Tensor, idx: torch.Tensor):
     out_i = torch.empty(B, k, dtype=torch.int64, device=vals.device)
     out_v = torch.empty(B, k, dtype=torch.float32, device=vals.device)
     check(lib.mmrec_topk_merge(parts, B, k, _ptr(vals), _ptr(idx), _ptr(out_i), _ptr(out_v), _stream()), "mmrec_topk_merge")
-    _count()
     return out_v, out_i
 
 
@@ -430,5 +422,4 @@ def bipartite_norm(users: torch.Tensor, items: torch.Tensor, n_users: int, n_ite
     ws = _ws("bnorm", lib.mmrec_bipartite_norm_workspace_bytes(n_users, n_items), users.device)
     check(lib.mmrec_bipartite_norm_f32(users.numel(), _ptr(users), _ptr(items), n_users, n_items, eps, _ptr(vals), _ptr(ws),
                                        ws.numel(), _stream()), "mmrec_bipartite_norm_f32")
-    _count(2)
     return vals

@@ -37,6 +37,7 @@ class ItemShard:
         key = np.unique(r * n_items + c)
         r, c = key // n_items, key % n_items
         self.rank, self.world, self.n_users, self.n_items = rank, world, n_users, n_items
+        assert n_items < 2 ** 31, "item ids travel as int32 in the top-k exchange"
         self.local_items = np.arange(rank, n_items, world, dtype=np.int64)     # global ids of my items, ascending
         self.n_local = len(self.local_items)
         # global degrees + 1e-7, float64, exactly as the single-GPU builder (freedom.py:113-116)
@@ -94,23 +95,34 @@ def propagate_mean_sharded(a_ui, a_iu, user_emb, item_emb_local, n_layers, spmm=
     return acc_u, acc_i
 
 
-def score_topk_sharded(shard: ItemShard, user_e, item_e_local, users, mask, k, score_topk=None, merge=None, group=None):
-    """Global top-k over all shards.  `mask` holds GLOBAL item ids ([2, nnz]: batch row, item)."""
+def local_mask(shard: ItemShard, mask):
+    """The entries of a [2, nnz] (batch row, GLOBAL item) mask that fall on this rank's shard, relabelled to local
+    item ids.  Data-dependent size: done once per batch by whoever builds the batches, outside the step."""
+    if mask is None or mask.numel() == 0:
+        return None
+    sel = (mask[1] % shard.world) == shard.rank
+    return torch.stack([mask[0][sel], mask[1][sel] // shard.world])
+
+
+def score_topk_sharded(shard: ItemShard, user_e, item_e_local, users, mask, k, score_topk=None, merge=None, group=None,
+                       mask_is_local=False):
+    """Global top-k over all shards.  `mask` holds GLOBAL item ids ([2, nnz]: batch row, item) unless
+    `mask_is_local` (then it is the output of `local_mask`)."""
     from . import ops
     score_topk = score_topk or ops.score_topk
     merge = merge or ops.topk_merge
     world = shard.world
-    lm = None
-    if mask is not None and mask.numel() > 0:
-        sel = (mask[1] % world) == shard.rank
-        lm = torch.stack([mask[0][sel], mask[1][sel] // world])
+    lm = mask if mask_is_local else local_mask(shard, mask)
     val, idx = score_topk(user_e, item_e_local, users, lm, k)
     idx = idx * world + shard.rank                                   # back to global item ids
-    vals = [torch.empty_like(val) for _ in range(world)]
-    idxs = [torch.empty_like(idx) for _ in range(world)]
-    dist.all_gather(vals, val, group=group)
-    dist.all_gather(idxs, idx, group=group)
-    return merge(torch.stack(vals), torch.stack(idxs))
+    B = val.shape[0]
+    # one collective per batch: (value bits, global item id) as an int32 pair (item ids are < 2^31, checked by the shard)
+    pair = torch.stack([val.contiguous().view(torch.int32), idx.to(torch.int32)], dim=-1)          # [B, k, 2]
+    allp = torch.empty(world, B, k, 2, dtype=torch.int32, device=val.device)
+    dist.all_gather_into_tensor(allp.view(world * B, k * 2), pair.view(B, k * 2), group=group)
+    vals = allp[..., 0].contiguous().view(torch.float32)
+    idxs = allp[..., 1].to(torch.int64)
+    return merge(vals, idxs)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -128,40 +140,83 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     batches = []
     for lo in range(0, U, EVAL_BATCH):
         hi = min(U, lo + EVAL_BATCH)
-        batches.append((torch.arange(lo, hi, device=dev), torch.from_numpy(wl.eval_mask(lo, hi)).to(dev)))
+        m = torch.from_numpy(wl.eval_mask(lo, hi)).to(dev)
+        batches.append((torch.arange(lo, hi, device=dev), m, local_mask(shard, m)))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     edges_local = wl.n_layers * 2 * shard.nnz
     ev = lambda: torch.cuda.Event(enable_timing=True)
     tA = tC = 0.0
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
-    launches0 = 0
+    state = {}
+
+    def sec_a():
+        return propagate_mean_sharded(a_ui, a_iu, ue, ie, wl.n_layers)
+
+    def sec_c():
+        return [score_topk_sharded(shard, state["u"], state["i"], users, lm, TOPK, mask_is_local=True) for users, _, lm in batches]
+
+    # Both sections (kernels of 5-70 us, NCCL collectives included) are captured once into CUDA graphs and replayed,
+    # as in the single-GPU arm; if this torch/NCCL build refuses to capture a collective the arm runs them eagerly.
+    graphs, n_launch, mode = {}, {"a": 0, "c": 0}, "cuda graphs"
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side), torch.no_grad():
+        for _ in range(2):
+            state["u"], state["i"] = sec_a(); sec_c()
+        torch.cuda.synchronize(); dist.barrier()
+        try:
+            for name, fn in (("a", sec_a), ("c", sec_c)):
+                l0 = ops.launch_count()
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    out = fn()
+                graphs[name], n_launch[name] = gph, ops.launch_count() - l0
+                if name == "a":
+                    state["u"], state["i"] = out
+            torch.cuda.synchronize()
+        except Exception as exc:                                     # noqa: BLE001
+            graphs, mode = {}, f"eager ({type(exc).__name__} during graph capture)"
+            torch.cuda.synchronize()
+    ok = torch.tensor([1.0 if graphs else 0.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)                        # all ranks replay, or none
+    if ok.item() == 0.0:
+        graphs = {}
+    launches = 0
     with torch.no_grad():
         for step in range(args.warmup + args.steps):
             if step == 0 and rank == 0:
                 sampler.start()
             if step == args.warmup:
                 torch.cuda.synchronize(); dist.barrier()
-                launches0 = ops.LAUNCHES
             flush.zero_()
-            dist.barrier()
+            torch.cuda.synchronize(); dist.barrier()
             e = [ev() for _ in range(4)]
+            l0 = ops.launch_count()
             e[0].record()
-            u_g, i_g = propagate_mean_sharded(a_ui, a_iu, ue, ie, wl.n_layers)
+            if graphs:
+                graphs["a"].replay()
+            else:
+                state["u"], state["i"] = sec_a()
             e[1].record()
             e[2].record()
-            outs = [score_topk_sharded(shard, u_g, i_g, users, mask, TOPK) for users, mask in batches]
+            if graphs:
+                graphs["c"].replay()
+            else:
+                sec_c()
             e[3].record()
             torch.cuda.synchronize()
             if step >= args.warmup:
                 tA += e[0].elapsed_time(e[1]); tC += e[2].elapsed_time(e[3])
-    launches1 = ops.LAUNCHES
+                launches += (n_launch["a"] + n_launch["c"]) if graphs else ops.launch_count() - l0
+    u_g, i_g = state["u"], state["i"]
+    launches0, launches1 = 0, launches
     dist.barrier()
+    # ---- e2e
     # ---- e2e: the same calls with pinned HOST buffers, copies inside the timed region
     ue_h = torch.from_numpy(wl.user_emb).pin_memory()
     ie_h = torch.from_numpy(wl.item_emb[shard.local_items]).pin_memory()
     out_u = torch.empty(U, d).pin_memory(); out_i = torch.empty(shard.n_local, d).pin_memory()
     users_h = [b[0].cpu().pin_memory() for b in batches]
-    masks_h = [b[1].cpu().pin_memory() for b in batches]
+    masks_h = [b[2].cpu().pin_memory() for b in batches]             # this rank's share of the mask
     out_idx = [torch.empty(b[0].numel(), TOPK, dtype=torch.int64).pin_memory() for b in batches]
     eA = eC = 0.0
     with torch.no_grad():
@@ -176,7 +231,8 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             e[1].record()
             e[2].record()
             for uh, mh, oh in zip(users_h, masks_h, out_idx):
-                _, idx = score_topk_sharded(shard, u_g, i_g, uh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True), TOPK)
+                _, idx = score_topk_sharded(shard, u_g, i_g, uh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True), TOPK,
+                                            mask_is_local=True)
                 oh.copy_(idx, non_blocking=True)
             e[3].record()
             torch.cuda.synchronize()
@@ -186,11 +242,14 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     h2d = (ue_h.numel() + ie_h.numel()) * 4 + sum(u.numel() * 8 + m.numel() * 8 for u, m in zip(users_h, masks_h))
     d2h = (out_u.numel() + out_i.numel()) * 4 + sum(o.numel() * 8 for o in out_idx)
     t = torch.tensor([tA, tC, eA, eC], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                          # device time of the slowest rank
+    e_all = torch.tensor([float(edges_local), float(launches1 - launches0)], device=dev, dtype=torch.float64)
+    dist.all_reduce(e_all, op=dist.ReduceOp.SUM)                      # units processed / kernels launched by all ranks
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         K = args.steps
         msA, msC = t[0].item() / K, t[1].item() / K
-        edges = e_all.item()
+        edges = e_all[0].item()
         pk = peaks()
         algo_bytes = wl.n_layers * (a_ui.algorithmic_bytes(d) + a_iu.algorithmic_bytes(d)) * world
         print(json.dumps({
@@ -201,15 +260,26 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             "config": {"workload": f"FREEDOM synthetic {wl.name} x{world} items: {U} users, {I} items ({I // world} per GPU), "
                                    f"{len(wl.tr_u)} train edges, d={d}, {wl.n_layers} UI layers, top-{TOPK} over all users",
                        "l2": "flushed (512 MiB write) before every step",
-                       "parallelism": f"item-sharded x{world}: all-reduce of user embeddings per layer, top-k all-gather + merge"},
+                       "parallelism": f"item-sharded x{world}: all-reduce of user embeddings per layer, top-k all-gather + merge",
+                       "launch": mode},
             "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U * I / (msC * 1e-3)},
             "roofline": {"kernel": "spmm_vec_kernel<64> (per rank: 2 per layer)", "bound": "hbm",
                          "achieved": algo_bytes / (msA * 1e-3) / 1e9 / world, "peak": pk["hbm_gbs"], "unit": "GB/s per GPU",
                          "frac": algo_bytes / (msA * 1e-3) / 1e9 / world / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
                          "note": "includes the per-layer NCCL all-reduce of the [U,d] user partials"},
-            "gpu_launches": int(launches1 - launches0), "clocks": clocks,
+            "gpu_launches": int(e_all[1].item()), "clocks": clocks,
             "e2e": {"value": edges / (t[2].item() / K * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(h2d) * world,
                     "d2h_bytes_per_step": int(d2h) * world, "prop_ms": t[2].item() / K, "score_topk_ms": t[3].item() / K,
                     "scored_items_per_sec": U * I / (t[3].item() / K * 1e-3)},
         }))
+    # Shut down: the captured graphs hold NCCL work, drop them before the process group; a watchdog guarantees the
+    # exit (rank 0 has printed its line) should the teardown of this torch/NCCL build block.
+    import sys, threading
+    sys.stdout.flush()
+    graphs = None
+    state.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    threading.Timer(20.0, lambda: os._exit(0)).start()
     dist.destroy_process_group()
+    os._exit(0)

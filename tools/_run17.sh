@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r17_bench_n2.log 2>&1; echo "rc=$?" >> gpurun_out/r17_bench_n2.log; tail -3 gpurun_out/r17_bench_n2.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r17_ref_n2.log 2>&1; echo "rc=$?" >> gpurun_out/r17_ref_n2.log; tail -3 gpurun_out/r17_ref_n2.log
+timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/r17_bench_n1.log 2>&1; tail -1 gpurun_out/r17_bench_n1.log
