@@ -170,6 +170,24 @@ int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64
 int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz);
 int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, const int64_t* idx,
                      int64_t* out_idx, float* out_val, void* stream);
+/* the same merge over lists left where each rank wrote them (peer-mapped memory): vals[p] / idx[p] are host
+ * arrays of `parts` (<= 16) device pointers to [B, k] lists; an index becomes idx * idx_mul + p * idx_add
+ * (round-robin item shards: idx_mul = world, idx_add = 1).  The caller synchronises the ranks before the call. */
+int mmrec_topk_merge_peers(int parts, int64_t B, int k, const void* const* vals, const void* const* idx,
+                           int64_t idx_mul, int64_t idx_add, int64_t* out_idx, float* out_val, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  user-embedding exchange of the item-sharded propagation, over peer memory (no reference counterpart:
+ * the reference is single-GPU, src/utils/configurator.py:114-118; the sum it distributes is the user half of
+ * `torch.sparse.mm(adj, ego)`, src/models/freedom.py:172, plus the layer mean of freedom.py:175-176).
+ *   parts   host array of `world` device pointers, rank order: partial user sums R_g E_Ig, [n] floats each,
+ *           peer-mapped (CUDA IPC / symmetric memory) -- the caller synchronises the ranks before the call
+ *   sum_out = sum over ranks in rank order (identical bits on every rank), may be NULL
+ *   acc_out = (acc_in + sum) / acc_div, may be NULL (acc_in NULL = 0; in place allowed)
+ *   n % 4 == 0, all pointers 16-byte aligned, world <= 16.
+ */
+int mmrec_peer_sum_f32(int64_t n, int world, const void* const* parts, const float* acc_in,
+                       float* acc_out, float acc_div, float* sum_out, void* stream);
 
 #ifdef __cplusplus
 }

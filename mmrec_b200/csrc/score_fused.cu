@@ -39,6 +39,8 @@ struct FusedParams {
     float* thr;                         // [B][n_splits]
     int32_t* flags;                     // [B] fallback flags
     uint32_t* gthr;                     // [B] highest certified threshold of any split (order-preserving key), zeroed per launch
+    unsigned long long* gbins;          // [B] (lo, width) of the row's histogram window: the first split to seed sets it (0 = unset)
+    uint32_t* ghist;                    // [B][FZ_NB / 2] candidates counted per bin by ALL splits of the row (two 16-bit counters per word)
 };
 
 // Shared memory: user tile (hi | lo) | item slab ring | row state | histogram | per-warp chunk scratch | barriers.
@@ -56,8 +58,8 @@ __host__ __device__ inline FzSmem fz_smem(int KP) {
     L.nsets = 2 * L.parities;
     L.u_hi = 0; L.u_lo = u_bytes; L.slab0 = 2 * u_bytes;
     L.rowst = L.slab0 + L.stages * TC_SLAB_BYTES;                    // 8 words per row, field-major
-    L.hist = L.rowst + 8 * TC_M * 4;                                 // [16 bin pairs][128 rows] u32
-    L.scratch = L.hist + (FZ_NB / 2) * TC_M * 4;
+    L.hist = L.rowst + 8 * TC_M * 4;                                 // (unused: the histogram is row-global, in L2)
+    L.scratch = L.hist;
     L.bars = L.scratch + L.nsets * 4 * (FZ_CH * 32 * 4);
     L.tmem_ptr = L.bars + 16 * 8;
     L.total = L.tmem_ptr + 16;
@@ -154,7 +156,7 @@ __device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& 
     const int n_epi = 128 * L.nsets;
     const int n_tiles = it1 - it0;
     uint32_t* rs = reinterpret_cast<uint32_t*>(smem + L.rowst) + rl;           // field f of this row: rs[f * TC_M]
-    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L.hist) + rl;          // bin pair b2 of this row: hist[b2 * TC_M]
+    uint32_t* ghist = p.ghist + (live ? row : 0) * (FZ_NB / 2);                // the row's bins, shared with the other splits
     float* sc = reinterpret_cast<float*>(smem + L.scratch) + e * (FZ_CH * 32) + lane;   // value j of the chunk: sc[j * 32]
     int need = p.k;
     if (live && p.mask_ptr) need += p.mask_ptr[row + 1] - p.mask_ptr[row];
@@ -208,14 +210,23 @@ __device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& 
         uint32_t bad = 0;
         if (!(width > 0.f) || !(cur > -INFINITY) || !(gmax < INFINITY)) { bad = 1; width = 1.f; lo = 0.f; thr = INFINITY; }
         if (!live) thr = INFINITY;                                   // padding rows: nothing passes, nothing is written
+        if (live && !bad) {
+            // One histogram window per ROW: the first split to get here publishes its (lo, width), the others adopt it
+            // (and its seed), so that the candidates of all splits are counted on the same bin edges.
+            const unsigned long long mine = ((unsigned long long)__float_as_uint(lo) << 32) | __float_as_uint(width);
+            const unsigned long long old = atomicCAS(p.gbins + row, 0ull, mine);
+            if (old != 0ull) {
+                lo = __uint_as_float((uint32_t)(old >> 32));
+                width = __uint_as_float((uint32_t)old);
+                thr = lo;
+            }
+        }
         rs[RS_THR * TC_M] = float_key(thr);
         rs[RS_CNT * TC_M] = 0;
         rs[RS_LO * TC_M] = __float_as_uint(lo);
         rs[RS_SCALE * TC_M] = __float_as_uint(1.0f / width);
         rs[RS_WIDTH * TC_M] = __float_as_uint(width);
         rs[RS_BAD * TC_M] = bad;
-#pragma unroll
-        for (int b = 0; b < FZ_NB / 2; ++b) hist[b * TC_M] = 0;
     }
     epi_bar_sync(n_epi);                                             // row state visible to every set
     const float lo = __uint_as_float(rs[RS_LO * TC_M]), scale = __uint_as_float(rs[RS_SCALE * TC_M]);
@@ -227,6 +238,9 @@ __device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& 
         mbar_wait(bar + (9 + buf) * 8, (t >> 1) & 1);
         fence_after_sync();
         const uint32_t foreign = live ? ld_relaxed_u32(p.gthr + row) : 0u;   // consumed after the tile
+        // snapshot of the row's bin counters, requested two chunks before the end of the tile and read after it (a stale
+        // snapshot is still a lower bound); one of the two sets that share a tile does the walk, the other picks the threshold up from shared memory
+        uint4 hw[FZ_NB / 8];
         const uint32_t tbase = lane_base + buf * TC_N + half * FZ_HALF;
         const int col_base = (it0 + t) * TC_N + half * FZ_HALF;
         const int n_valid = n_items32 - col_base;                    // columns of this half tile inside the catalogue
@@ -234,6 +248,10 @@ __device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& 
         for (int c = 0; c < FZ_HALF / FZ_CH; ++c) {
             uint32_t v[16];
             tmem_ld_32x16(tbase + c * FZ_CH, v);
+            if (c == FZ_HALF / FZ_CH - 2 && half == 0) {
+#pragma unroll
+                for (int i = 0; i < FZ_NB / 8; ++i) hw[i] = __ldcg(reinterpret_cast<const uint4*>(ghist) + i);
+            }
             tmem_ld_wait();
             if (n_valid < FZ_HALF) {                                 // last, partial tile only
 #pragma unroll
@@ -262,7 +280,7 @@ __device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& 
                             cand[pos] = make_float2(x, __int_as_float(col_base + c * FZ_CH + j));
                             int b = (int)((x - lo) * scale);
                             b = b < 0 ? 0 : (b > FZ_NB - 1 ? FZ_NB - 1 : b);
-                            atomicAdd(hist + (b >> 1) * TC_M, (b & 1) ? 65536u : 1u);   // after the append: counted => listed
+                            atomicAdd(ghist + (b >> 1), (b & 1) ? 65536u : 1u);          // after the append: counted => listed
                         }
                     }
                 }
@@ -271,13 +289,25 @@ __device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& 
         // accumulator drained: hand the TMEM buffer back before the (SMEM-only) threshold update
         fence_before_sync();
         mbar_arrive(bar + (11 + buf) * 8);
-        // Raise the row threshold to the highest bin edge that keeps `need` counted candidates above it.  Counters of
-        // other sets may be moving: any snapshot is a lower bound, so what it certifies stays certified.
-        int cnum = 0, b = FZ_NB - 1;
-        for (; b >= 0; --b) {
-            const uint32_t w = hist[(b >> 1) * TC_M];
-            cnum += (b & 1) ? (int)(w >> 16) : (int)(w & 0xffffu);
-            if (cnum >= need) break;
+        // Raise the row threshold to the highest bin edge that keeps `need` counted candidates above it -- counted over the
+        // whole catalogue seen so far, by every split of the row.  The counters are moving: any snapshot is a lower
+        // bound, so what it certifies stays certified.
+        int cnum = 0, b = -1;
+        if (half == 0) {
+#pragma unroll
+            for (int i = FZ_NB / 8 - 1; i >= 0; --i) {
+                const uint32_t w4[4] = {hw[i].x, hw[i].y, hw[i].z, hw[i].w};
+#pragma unroll
+                for (int j = 3; j >= 0; --j) {
+#pragma unroll
+                    for (int h2 = 1; h2 >= 0; --h2) {
+                        if (b < 0) {
+                            cnum += (int)(h2 ? (w4[j] >> 16) : (w4[j] & 0xffffu));
+                            if (cnum >= need) b = (i * 4 + j) * 2 + h2;
+                        }
+                    }
+                }
+            }
         }
         uint32_t mine = 0;
         if (b >= 0 && live) {
@@ -359,22 +389,64 @@ __global__ void mask_fill_kernel(int64_t nnz, const int64_t* __restrict__ rows, 
     items[pos] = (int32_t)(cols[j] - item_offset);     // may fall outside [0, n_items): then it never matches
 }
 
-// The same CSR in one launch for the per-batch case (B <= MC_MAX_ROWS rows): one CTA counts in shared memory, scans,
-// fills.  Three passes over the mask entries, no global atomics, no memsets, no library scan.
+// Per-batch case (B <= MC_MAX_ROWS rows).  The reference's evaluation loader emits the mask row-major (batch row ascending:
+// src/utils/dataloader.py builds it user by user), so the common case is a sorted row array: mask_csr_sorted_kernel
+// writes the row pointers from the positions where the row changes and checks the order as it goes, one fully parallel
+// pass.  If any CTA saw a descent, mask_csr_small_kernel (one CTA: count in shared memory, scan, fill) redoes the job
+// for arbitrary order; otherwise it exits at once.  No global atomics, no memsets, no library scan.
+__global__ void __launch_bounds__(256) mask_csr_sorted_kernel(int64_t nnz, const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
+                                                              int B, int64_t item_offset, int32_t* __restrict__ ptr,
+                                                              int32_t* __restrict__ items, int32_t* __restrict__ unsorted) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // entry j, plus one sentinel thread j == nnz
+    int bad = 0;
+    if (j <= nnz) {
+        const int64_t rj = j < nnz ? rows[j] : (int64_t)B;
+        const int64_t rp = j > 0 ? rows[j - 1] : -1;
+        bad = j < nnz && rp > rj;
+        if (j < nnz) items[j] = (int32_t)(cols[j] - item_offset);
+        // rows (rp, rj] start at entry j (rows outside [0, B) own no pointer; clamped so that they delimit correctly)
+        const int64_t lo = rp < -1 ? -1 : (rp > B ? B : rp), hi = rj < -1 ? -1 : (rj > B ? B : rj);
+        for (int64_t r = lo + 1; r <= hi; ++r) ptr[r] = (int32_t)j;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) unsorted[blockIdx.x] = bad;
+}
+
+
 constexpr int MC_MAX_ROWS = 8192;
 constexpr int MC_THREADS = 1024;
 __global__ void __launch_bounds__(MC_THREADS) mask_csr_small_kernel(int64_t nnz, const int64_t* __restrict__ rows,
                                                                     const int64_t* __restrict__ cols, int B, int64_t item_offset,
-                                                                    int32_t* __restrict__ ptr, int32_t* __restrict__ items) {
+                                                                    int32_t* __restrict__ ptr, int32_t* __restrict__ items,
+                                                                    const int32_t* __restrict__ unsorted, int n_unsorted) {
     extern __shared__ int32_t mc_sm[];                               // count / cursor [B + 1] | warp totals [32]
+    {   // runs only when mask_csr_sorted_kernel found the rows out of order (it then left garbage behind)
+        int any = 0;
+        for (int i = threadIdx.x; i < n_unsorted; i += MC_THREADS) any |= unsorted[i];
+        if (!__syncthreads_or(any)) return;
+    }
     int32_t* cnt = mc_sm;
     int32_t* wtot = mc_sm + B + 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int r = tid; r <= B; r += MC_THREADS) cnt[r] = 0;
     __syncthreads();
-    for (int64_t j = tid; j < nnz; j += MC_THREADS) {
-        const int64_t r = rows[j];
-        if (r >= 0 && r < B) atomicAdd(cnt + r, 1);
+    constexpr int MC_U = 8;                                          // loads in flight per thread (the loop is latency-bound)
+    for (int64_t jb = 0; jb < nnz; jb += (int64_t)MC_U * MC_THREADS) {        // warp-uniform trip count (match / shfl below)
+        const int64_t j0 = jb + tid;
+        int64_t r[MC_U];
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            const int64_t j = j0 + (int64_t)u * MC_THREADS;
+            r[u] = j < nnz ? __ldg(rows + j) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            // batch rows arrive (mostly) sorted: the lanes of a warp hit a handful of counters.  One atomic per distinct
+            // row of the warp (same-address shared atomics serialise a full round trip each).
+            const int rr = (r[u] >= 0 && r[u] < B) ? (int)r[u] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, rr);
+            if (rr >= 0 && lane == __ffs(peers) - 1) atomicAdd(cnt + rr, __popc(peers));
+        }
     }
     __syncthreads();
     // exclusive scan of cnt[0..B]: each thread owns a contiguous run of rows
@@ -408,9 +480,25 @@ __global__ void __launch_bounds__(MC_THREADS) mask_csr_small_kernel(int64_t nnz,
         run += c;
     }
     __syncthreads();
-    for (int64_t j = tid; j < nnz; j += MC_THREADS) {
-        const int64_t r = rows[j];
-        if (r >= 0 && r < B) items[atomicAdd(cnt + r, 1)] = (int32_t)(cols[j] - item_offset);   // order inside a row is free
+    for (int64_t jb = 0; jb < nnz; jb += (int64_t)MC_U * MC_THREADS) {        // warp-uniform trip count (match / shfl below)
+        const int64_t j0 = jb + tid;
+        int64_t r[MC_U], c[MC_U];
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            const int64_t j = j0 + (int64_t)u * MC_THREADS;
+            r[u] = j < nnz ? __ldg(rows + j) : -1;
+            c[u] = j < nnz ? __ldg(cols + j) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            const int rr = (r[u] >= 0 && r[u] < B) ? (int)r[u] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, rr);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (rr >= 0 && lane == leader) base = atomicAdd(cnt + rr, __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (rr >= 0) items[base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)(c[u] - item_offset);   // order inside a row is free
+        }
     }
 }
 
@@ -489,8 +577,52 @@ __global__ void __launch_bounds__(128) fused_select_kernel(int64_t B, int n_spli
     const int mreg = mlen < 32 ? mlen : 32;
     int n = 0;
     bool over = false;
-    for (int s = 0; s < n_splits; ++s) {
-        const int ns = s < 32 ? __shfl_sync(0xffffffffu, my_cnt, s) : cnt[row * n_splits + s];
+    // Candidates of all splits as one flat list (exclusive prefix of the counts in lane s): slot t = lane + 32 i maps to
+    // (split, j).  The loads of up to SEL_U slots per lane are issued together -- the lists were written by other SMs,
+    // so every load is an L2 round trip, and one round trip per row instead of one per 32 candidates is the point.
+    int pre = my_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+    }
+    const int total32 = __shfl_sync(0xffffffffu, pre, 31);           // candidates in the first 32 splits
+    pre -= my_cnt;                                                   // exclusive
+    constexpr int SEL_U = 8;
+    const int nsp = n_splits < 32 ? n_splits : 32;
+    for (int t0 = 0; t0 < total32; t0 += 32 * SEL_U) {
+        float2 c[SEL_U];
+#pragma unroll
+        for (int i = 0; i < SEL_U; ++i) {
+            const int t = t0 + i * 32 + lane;
+            // split of slot t: the last lane whose exclusive prefix is <= t (empty splits are skipped); warp-uniform
+            // control flow, the result of lanes beyond the list is not used
+            int sp = 0;
+            for (int s2 = 1; s2 < nsp; ++s2)
+                if (__shfl_sync(0xffffffffu, pre, s2) <= t) sp = s2;
+            const int j = t - __shfl_sync(0xffffffffu, pre, sp);
+            c[i] = make_float2(-INFINITY, 0.f);
+            if (t < total32) c[i] = cand[(row * n_splits + sp) * cap + j];
+        }
+#pragma unroll
+        for (int i = 0; i < SEL_U; ++i) {
+            const int t = t0 + i * 32 + lane;
+            bool keep = t < total32 && c[i].x >= T;
+            const int item = __float_as_int(c[i].y);
+            for (int q = 0; q < mreg; ++q) keep &= (__shfl_sync(0xffffffffu, my_mask, q) != item);
+            if (keep)
+                for (int q = m0 + 32; q < m1; ++q) keep &= (mask_items[q] != item);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int pos = n + __popc(bal & ((1u << lane) - 1u));
+            if (keep) {
+                if (pos < FZ_WFIN) fin[pos] = ((uint64_t)float_key(c[i].x) << 32) | (uint32_t)(~(uint32_t)item);
+                else over = true;
+            }
+            n += __popc(bal);
+        }
+    }
+    for (int s = 32; s < n_splits; ++s) {                            // (more than 32 splits: tiny batches only)
+        const int ns = cnt[row * n_splits + s];
         const float2* cs = cand + (row * n_splits + s) * cap;
         for (int j0 = 0; j0 < ns; j0 += 32) {
             const int j = j0 + lane;
@@ -912,8 +1044,9 @@ static FzPlan fz_plan(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz
     P.off_ihi = take((size_t)P.n_it * TC_N * P.KP * 4); P.off_ilo = take((size_t)P.n_it * TC_N * P.KP * 4);
     P.off_cand = take((size_t)P.rows_blk * P.splits * P.cap * 8);
     P.off_cnt = take((size_t)P.rows_blk * P.splits * 4); P.off_thr = take((size_t)P.rows_blk * P.splits * 4);
-    P.off_flags = take((size_t)P.rows_blk * 8);                     // flags[rows_blk] | gthr[rows_blk]
-    P.off_mptr = take((size_t)(B + 2) * 4); P.off_mcur = take((size_t)(B + 2) * 4);
+    P.off_flags = take((size_t)P.rows_blk * (8 + 8 + 2 * FZ_NB));   // flags | gthr | gbins (u64) | ghist [rows_blk][FZ_NB / 2]
+    P.off_mptr = take((size_t)(B + 2) * 4);
+    P.off_mcur = take((size_t)(B + 2 > 1100 ? B + 2 : 1100) * 4);   // fill cursors, or the per-CTA order flags of the sorted-mask pass
     P.off_mitems = take((size_t)(mask_nnz > 0 ? mask_nnz : 1) * 4);
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int64_t)(B + 1));
@@ -957,8 +1090,11 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
     // mask -> CSR over batch rows
     const bool has_mask = mask_nnz > 0;
     if (has_mask && B <= MC_MAX_ROWS && mask_nnz <= (1ll << 18)) {
+        const int nblk = (int)((mask_nnz + 1 + T - 1) / T);          // <= 1025 words of mcur hold the per-CTA order flags
+        mask_csr_sorted_kernel<<<nblk, T, 0, stream>>>(mask_nnz, mask_rows, mask_cols, (int)B, item_offset, mptr, mitems, mcur);
+        MMREC_LAUNCH_CHECK();
         mask_csr_small_kernel<<<1, MC_THREADS, (size_t)(B + 1 + 32) * 4, stream>>>(mask_nnz, mask_rows, mask_cols, (int)B, item_offset, mptr,
-                                                                                 mitems);
+                                                                                 mitems, mcur, nblk);
         MMREC_LAUNCH_CHECK();
     } else if (has_mask) {
         MMREC_CUDA(cudaMemsetAsync(mcur, 0, (size_t)(B + 2) * 4, stream));
@@ -981,7 +1117,7 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         const int64_t n_ut = (nb + TC_M - 1) / TC_M;
         // operands (items: split + re-tiled once, with the first row block) + zeroed scratch words, one launch
         const int64_t n_it_now = r0 == 0 ? P.n_it : 0;
-        const int64_t zero0 = 2 * P.rows_blk, zero1 = P.rows_blk + 1;            // flags | gthr, slot | counter
+        const int64_t zero0 = (4 + FZ_NB / 2) * P.rows_blk, zero1 = P.rows_blk + 1;   // flags | gthr | gbins | ghist, slot | counter
         const int64_t prep_threads = n_it_now * TC_N * (P.KP / 4) + n_ut * TC_M * (P.KP / 4) + zero0 + zero1;
         fz_prep_kernel<<<(unsigned)((prep_threads + T - 1) / T), T, 0, stream>>>(
             n_items, Ie, ldi, n_it_now, Ihi, Ilo, nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_ut, Uhi, Ulo, d, P.KP,
@@ -994,6 +1130,8 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         p.cand = (float2*)(base + P.off_cand); p.cnt = (int32_t*)(base + P.off_cnt); p.thr = (float*)(base + P.off_thr);
         p.flags = (int32_t*)(base + P.off_flags);
         p.gthr = (uint32_t*)(base + P.off_flags) + P.rows_blk;
+        p.gbins = (unsigned long long*)((uint32_t*)(base + P.off_flags) + 2 * P.rows_blk);
+        p.ghist = (uint32_t*)(base + P.off_flags) + 4 * P.rows_blk;
         score_fused_kernel<<<(unsigned)(n_ut * P.splits), 64 + 128 * L.nsets, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
         fused_select_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,

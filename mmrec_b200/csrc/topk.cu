@@ -166,6 +166,51 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_merge_kernel(int parts, int
     }
 }
 
+// The same merge with the lists left where the ranks wrote them: list `p` is [B, k] behind vals[p] / idx[p] (peer-mapped
+// memory in the item-sharded evaluation), and a local item id becomes the global one as idx * idx_mul + p * idx_add
+// (round-robin shards: idx_mul = world, idx_add = 1; pass 1, 0 for ids that are global already).
+constexpr int MERGE_MAX_PEERS = 16;
+struct MergePeers { const float* v[MERGE_MAX_PEERS]; const int64_t* i[MERGE_MAX_PEERS]; };
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_merge_peers_kernel(int parts, int64_t B, int k, const MergePeers src, int64_t idx_mul,
+                                                                        int64_t idx_add, int64_t* __restrict__ out_idx,
+                                                                        float* __restrict__ out_val) {
+    extern __shared__ uint64_t cand[];   // n2 composites (value key, ~rank) + n2 int64 indices
+    __shared__ int slot_of_rank[MERGE_MAX_PEERS * TOPK_MAXK > 4096 ? 4096 : MERGE_MAX_PEERS * TOPK_MAXK];
+    const int n = parts * k;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    int64_t* cidx = reinterpret_cast<int64_t*>(cand + n2);
+    const int64_t b = blockIdx.x;
+    for (int t = threadIdx.x; t < n; t += TOPK_THREADS) {
+        const int part = t / k, j = t % k;
+        cidx[t] = src.i[part][b * k + j] * idx_mul + part * idx_add;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n2; t += TOPK_THREADS) {
+        if (t < n) {
+            const int part = t / k, j = t % k;
+            const float v = src.v[part][b * k + j];
+            const int64_t me = cidx[t];
+            unsigned rank = 0;
+            for (int u = 0; u < n; ++u) rank += (cidx[u] < me) || (cidx[u] == me && u < t);
+            cand[t] = ((uint64_t)float_key(v) << 32) | (uint32_t)(~rank);
+        } else {
+            cand[t] = 0;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += TOPK_THREADS) slot_of_rank[(uint32_t)(~(uint32_t)cand[t])] = t;
+    __syncthreads();
+    bitonic_desc(cand, n2);
+    for (int t = threadIdx.x; t < k; t += TOPK_THREADS) {
+        const uint64_t c = cand[t];
+        const int slot = slot_of_rank[(uint32_t)(~(uint32_t)c)];
+        out_idx[b * k + t] = cidx[slot];
+        out_val[b * k + t] = key_float((uint32_t)(c >> 32));
+    }
+}
+
 }  // namespace mmrec
 
 namespace mmrec {
@@ -213,6 +258,28 @@ extern "C" int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, 
     size_t smem = (size_t)n2 * 16;
     MMREC_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     topk_merge_kernel<<<(unsigned)B, TOPK_THREADS, smem, stream>>>(parts, B, k, vals, idx, out_idx, out_val);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}
+
+extern "C" int mmrec_topk_merge_peers(int parts, int64_t B, int k, const void* const* vals, const void* const* idx, int64_t idx_mul,
+                                      int64_t idx_add, int64_t* out_idx, float* out_val, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(parts >= 1 && parts <= MERGE_MAX_PEERS && B >= 0 && k >= 1 && (int64_t)parts * k <= 4096,
+                    "topk_merge_peers: need parts <= 16 and parts*k <= 4096");
+    if (B == 0) return MMREC_OK;
+    MMREC_CHECK_ARG(vals && idx && out_idx && out_val, "topk_merge_peers: null pointer");
+    MergePeers src;
+    for (int p = 0; p < MERGE_MAX_PEERS; ++p) { src.v[p] = nullptr; src.i[p] = nullptr; }
+    for (int p = 0; p < parts; ++p) {
+        MMREC_CHECK_ARG(vals[p] && idx[p], "topk_merge_peers: null list pointer");
+        src.v[p] = (const float*)vals[p]; src.i[p] = (const int64_t*)idx[p];
+    }
+    int n = parts * k, n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    const size_t smem = (size_t)n2 * 16;
+    MMREC_CUDA(cudaFuncSetAttribute(topk_merge_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    topk_merge_peers_kernel<<<(unsigned)B, TOPK_THREADS, smem, stream>>>(parts, B, k, src, idx_mul, idx_add, out_idx, out_val);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }

@@ -370,9 +370,10 @@ def mask_topk(scores: torch.Tensor, mask: Optional[torch.Tensor], k: int, item_o
     return val, idx
 
 
-def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0):
+def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0, out=None):
     """Fused `full_sort_predict` + mask + top-k (`src/models/freedom.py:216-220` + `src/common/trainer.py:304-309`)
-    without materialising the [B, n_items] score matrix in HBM.  Returns (values [B,k], indices int64 [B,k])."""
+    without materialising the [B, n_items] score matrix in HBM.  Returns (values [B,k], indices int64 [B,k]); `out` =
+    (values, indices) buffers to write into (e.g. peer-mapped memory in the sharded evaluation)."""
     _need_cuda(user_e, item_e, users, mask)
     lib = _lib.load()
     user_e, item_e = _f32c(user_e), _f32c(item_e)
@@ -380,8 +381,13 @@ def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0):
         users = users.to(torch.int64).contiguous()
     B = user_e.shape[0] if users is None else users.numel()
     n_items, d = item_e.shape
-    idx = torch.empty(B, k, dtype=torch.int64, device=item_e.device)
-    val = torch.empty(B, k, dtype=torch.float32, device=item_e.device)
+    if out is not None:
+        val, idx = out
+        assert val.shape == (B, k) and idx.shape == (B, k) and val.dtype == torch.float32 and idx.dtype == torch.int64 \
+            and val.is_contiguous() and idx.is_contiguous()
+    else:
+        idx = torch.empty(B, k, dtype=torch.int64, device=item_e.device)
+        val = torch.empty(B, k, dtype=torch.float32, device=item_e.device)
     m0 = m1 = None
     nnz = 0
     if mask is not None and mask.numel() > 0:
@@ -411,6 +417,32 @@ def topk_merge(vals: torch.Tensor, idx: torch.Tensor):
     out_v = torch.empty(B, k, dtype=torch.float32, device=vals.device)
     check(lib.mmrec_topk_merge(parts, B, k, _ptr(vals), _ptr(idx), _ptr(out_i), _ptr(out_v), _stream()), "mmrec_topk_merge")
     return out_v, out_i
+
+
+def topk_merge_peers(val_ptrs, idx_ptrs, B, k, device, idx_mul=1, idx_add=0):
+    """`topk_merge` over lists left where each rank wrote them: raw device addresses of `parts` [B, k] value (fp32) and
+    index (int64) lists, rank order; index -> idx * idx_mul + part * idx_add (round-robin shards: world, 1)."""
+    import ctypes
+    lib = _lib.load()
+    parts = len(val_ptrs)
+    va = (ctypes.c_void_p * parts)(*[int(x) for x in val_ptrs])
+    ia = (ctypes.c_void_p * parts)(*[int(x) for x in idx_ptrs])
+    out_i = torch.empty(B, k, dtype=torch.int64, device=device)
+    out_v = torch.empty(B, k, dtype=torch.float32, device=device)
+    check(lib.mmrec_topk_merge_peers(parts, B, k, ctypes.cast(va, ctypes.c_void_p), ctypes.cast(ia, ctypes.c_void_p), int(idx_mul),
+                                     int(idx_add), _ptr(out_i), _ptr(out_v), _stream()), "mmrec_topk_merge_peers")
+    return out_v, out_i
+
+
+def peer_sum(part_ptrs, n, acc_in=None, acc_out=None, acc_div=1.0, sum_out=None):
+    """K4: `sum_out = sum_r parts[r]` (rank order), `acc_out = (acc_in + sum) / acc_div` -- the user-embedding exchange of
+    the item-sharded propagation as one pass over peer-mapped buffers (`part_ptrs`: raw device addresses, rank order)."""
+    import ctypes
+    lib = _lib.load()
+    arr = (ctypes.c_void_p * len(part_ptrs))(*[int(x) for x in part_ptrs])
+    check(lib.mmrec_peer_sum_f32(int(n), len(part_ptrs), ctypes.cast(arr, ctypes.c_void_p), _ptr(acc_in), _ptr(acc_out), float(acc_div),
+                                 _ptr(sum_out), _stream()), "mmrec_peer_sum_f32")
+    return sum_out, acc_out
 
 
 def bipartite_norm(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, eps: float = 1e-7) -> torch.Tensor:

@@ -95,6 +95,105 @@ def propagate_mean_sharded(a_ui, a_iu, user_emb, item_emb_local, n_layers, spmm=
     return acc_u, acc_i
 
 
+class PeerExchange:
+    """Per-layer partial-sum buffers that every rank has mapped (torch symmetric memory: CUDA IPC over NVLink) plus the
+    device-side barrier between the ranks' streams.  `PeerExchange.create` returns None when this torch build / box cannot
+    provide it -- the caller then keeps the NCCL all-reduce formulation."""
+
+    def __init__(self, hdl, buf, n_users, d, n_layers, rank, world, topk_rows, k):
+        self.hdl, self.buf, self.n, self.rank, self.world = hdl, buf, n_users * d, rank, world
+        self.n_layers, self.k, self.topk_rows = n_layers, k, topk_rows
+        self.parts = [buf[l * self.n:(l + 1) * self.n].view(n_users, d) for l in range(n_layers)]
+        self.ptrs = [[int(p) + l * self.n * 4 for p in hdl.buffer_ptrs] for l in range(n_layers)]
+        # top-k lists of the evaluation, one region per user row: values fp32 [rows, k] then indices int64 [rows, k]
+        # (the buffer is fp32-typed; 8-byte alignment of the index region holds because n_layers * n and rows * k are even)
+        self.val_off = n_layers * self.n
+        self.idx_off = self.val_off + topk_rows * k + ((topk_rows * k) & 1)
+
+    def topk_lists(self, row0, nrows):
+        """(values, indices) views of this rank's list region for user rows [row0, row0 + nrows), and the peers' raw
+        addresses of the same regions (rank order)."""
+        k = self.k
+        v = self.buf[self.val_off + row0 * k: self.val_off + (row0 + nrows) * k].view(nrows, k)
+        i = self.buf[self.idx_off + 2 * row0 * k: self.idx_off + 2 * (row0 + nrows) * k].view(torch.int64).view(nrows, k)
+        vp = [int(p) + 4 * (self.val_off + row0 * k) for p in self.hdl.buffer_ptrs]
+        ip = [int(p) + 4 * (self.idx_off + 2 * row0 * k) for p in self.hdl.buffer_ptrs]
+        return v, i, vp, ip
+
+    @staticmethod
+    def create(n_users, d, n_layers, device, group=None, k=50):
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = group or dist.group.WORLD
+            n = n_users * d
+            words = n_layers * n + n_users * k + ((n_users * k) & 1) + 2 * n_users * k
+            if (n_layers * n) & 1:
+                return None                                          # (index region would lose its 8-byte alignment)
+            buf = symm.empty(words, dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(buf, grp)
+            buf.zero_()
+            px = PeerExchange(hdl, buf, n_users, d, n_layers, dist.get_rank(grp), dist.get_world_size(grp), n_users, k)
+            px.barrier(0)
+            torch.cuda.synchronize(device)
+            return px
+        except Exception:                                            # noqa: BLE001
+            return None
+
+    def barrier(self, channel):
+        self.hdl.barrier(channel=channel)
+
+
+def propagate_mean_sharded_p2p(a_ui, a_iu, user_emb, item_emb_local, n_layers, px: PeerExchange):
+    """`propagate_mean_sharded` with the all-reduce replaced by this library's kernel over peer memory: the user-side
+    SpMM writes its partial into the symmetric buffer, the item-side SpMM runs while the peers finish theirs, one
+    device barrier, then `mmrec_peer_sum_f32` reads all partials over NVLink and applies the layer-mean epilogue.
+    Same sums in the same (rank) order on every rank."""
+    from . import ops
+    U, d = user_emb.shape
+    eu, ei = user_emb, item_emb_local
+    acc_u = user_emb.clone()
+    acc_i = item_emb_local.clone()
+    for l in range(1, n_layers + 1):
+        last = l == n_layers
+        div = float(n_layers + 1) if last else 1.0
+        # the two SpMMs of a layer read only layer l-1: side by side on two streams (fork / join with events, so the pair
+        # is also a valid CUDA-graph capture)
+        main = torch.cuda.current_stream()
+        side = _side_stream(user_emb.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ei_next, acc_i = _cuda_spmm(a_iu, eu, acc_in=acc_i, acc_div=div, want_y=not last)
+        ops.spmm_raw(a_ui, ei, Y=px.parts[l - 1])                    # R_g E_Ig -> peer-visible partial of layer l
+        px.barrier(l - 1)                                            # every rank's partial of layer l is complete
+        eu_next = None if last else torch.empty(U, d, dtype=torch.float32, device=user_emb.device)
+        ops.peer_sum(px.ptrs[l - 1], U * d, acc_in=acc_u, acc_out=acc_u, acc_div=div, sum_out=eu_next)
+        main.wait_stream(side)
+        eu, ei = eu_next, ei_next
+    return acc_u, acc_i
+
+
+_side = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _side:
+        _side[key] = torch.cuda.Stream(device=device)
+    return _side[key]
+
+
+def score_topk_sharded_p2p(shard: ItemShard, user_e, item_e_local, users, lmask, k, px: PeerExchange, row0, channel):
+    """`score_topk_sharded` without a collective: the fused score+top-k kernel writes this rank's (value, local item)
+    lists straight into peer-mapped memory, one device barrier, then every rank merges all ranks' lists in place
+    (`mmrec_topk_merge_peers`, which also relabels local -> global item ids).  `lmask` is the output of `local_mask`."""
+    from . import ops
+    B = users.numel()
+    v, i, vp, ip = px.topk_lists(row0, B)
+    ops.score_topk(user_e, item_e_local, users, lmask, k, out=(v, i))
+    px.barrier(channel)
+    return ops.topk_merge_peers(vp, ip, B, k, user_e.device, idx_mul=shard.world, idx_add=1)
+
+
 def local_mask(shard: ItemShard, mask):
     """The entries of a [2, nnz] (batch row, GLOBAL item) mask that fall on this rank's shard, relabelled to local
     item ids.  Data-dependent size: done once per batch by whoever builds the batches, outside the step."""
@@ -149,11 +248,29 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     state = {}
 
+    px = None if os.environ.get("MMREC_EXCHANGE", "p2p") == "nccl" else PeerExchange.create(U, d, wl.n_layers, dev)
+    have = torch.tensor([1.0 if px is not None else 0.0], device=dev)
+    dist.all_reduce(have, op=dist.ReduceOp.MIN)
+    if have.item() == 0.0:
+        px = None
+    exchange = ("mmrec_peer_sum_f32 / mmrec_topk_merge_peers over symmetric memory (P2P loads), no collective on the data path"
+                if px is not None else "NCCL all-reduce + all-gather")
+
+    def prop(u_in, i_in):
+        if px is not None:
+            return propagate_mean_sharded_p2p(a_ui, a_iu, u_in, i_in, wl.n_layers, px)
+        return propagate_mean_sharded(a_ui, a_iu, u_in, i_in, wl.n_layers)
+
     def sec_a():
-        return propagate_mean_sharded(a_ui, a_iu, ue, ie, wl.n_layers)
+        return prop(ue, ie)
+
+    def score_batch(bi, u_g, i_g, users, lm):
+        if px is not None:
+            return score_topk_sharded_p2p(shard, u_g, i_g, users, lm, TOPK, px, bi * EVAL_BATCH, wl.n_layers + bi % 4)
+        return score_topk_sharded(shard, u_g, i_g, users, lm, TOPK, mask_is_local=True)
 
     def sec_c():
-        return [score_topk_sharded(shard, state["u"], state["i"], users, lm, TOPK, mask_is_local=True) for users, _, lm in batches]
+        return [score_batch(bi, state["u"], state["i"], users, lm) for bi, (users, _, lm) in enumerate(batches)]
 
     # Both sections (kernels of 5-70 us, NCCL collectives included) are captured once into CUDA graphs and replayed,
     # as in the single-GPU arm; if this torch/NCCL build refuses to capture a collective the arm runs them eagerly.
@@ -226,13 +343,12 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             e = [ev() for _ in range(4)]
             e[0].record()
             ue_d, ie_d = ue_h.to(dev, non_blocking=True), ie_h.to(dev, non_blocking=True)
-            u_g, i_g = propagate_mean_sharded(a_ui, a_iu, ue_d, ie_d, wl.n_layers)
+            u_g, i_g = prop(ue_d, ie_d)
             out_u.copy_(u_g, non_blocking=True); out_i.copy_(i_g, non_blocking=True)
             e[1].record()
             e[2].record()
-            for uh, mh, oh in zip(users_h, masks_h, out_idx):
-                _, idx = score_topk_sharded(shard, u_g, i_g, uh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True), TOPK,
-                                            mask_is_local=True)
+            for bi, (uh, mh, oh) in enumerate(zip(users_h, masks_h, out_idx)):
+                _, idx = score_batch(bi, u_g, i_g, uh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True))
                 oh.copy_(idx, non_blocking=True)
             e[3].record()
             torch.cuda.synchronize()
@@ -261,7 +377,7 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
                                    f"{len(wl.tr_u)} train edges, d={d}, {wl.n_layers} UI layers, top-{TOPK} over all users",
                        "l2": "flushed (512 MiB write) before every step",
                        "parallelism": f"item-sharded x{world}: all-reduce of user embeddings per layer, top-k all-gather + merge",
-                       "launch": mode},
+                       "launch": mode, "user_exchange": exchange},
             "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U * I / (msC * 1e-3)},
             "roofline": {"kernel": "spmm_vec_kernel<64> (per rank: 2 per layer)", "bound": "hbm",
                          "achieved": algo_bytes / (msA * 1e-3) / 1e9 / world, "peak": pk["hbm_gbs"], "unit": "GB/s per GPU",

@@ -294,6 +294,10 @@ def test_fused_topk_edge_cases(dev):
         mask = torch.stack([torch.cat(rows), torch.cat(cols)])
         mask = mask[:, torch.randperm(mask.shape[1], generator=g)]                                  # unsorted on purpose
         val, idx = ops.score_topk(ue.to(dev), ie.to(dev), users.to(dev), mask.to(dev), k)
+        # the same mask row-major (what the evaluation loader emits: the one-pass sorted CSR build) gives the same answer
+        srt = mask[:, torch.argsort(mask[0], stable=True)]
+        val_s, idx_s = ops.score_topk(ue.to(dev), ie.to(dev), users.to(dev), srt.to(dev), k)
+        assert torch.equal(idx, idx_s) and torch.equal(val, val_s)
         ref, (rv, ri) = _ref_topk(ue, ie, users, mask, k)
         _check_near_tie(idx, ref, ri, ref[ref > -1e9].abs().max().item())
         hit = torch.zeros(B, I, dtype=torch.bool); hit[mask[0], mask[1]] = True
@@ -379,3 +383,41 @@ def test_full_size_properties_baby(dev):
     ops.set_score_path("auto")
     same = (idx3 == idx).all(dim=1).float().mean().item()
     assert same > 0.99 and (val3 - val).abs().max().item() < 1e-5 * val.abs().max().item() + 1e-9
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_peer_sum_rank_order_and_epilogue(dev, world):
+    """K4 (mmrec_peer_sum_f32) on one device: the partials are ordinary buffers here, the arithmetic is what is under
+    test -- rank-order summation (bit-exact against the same torch loop) and the layer-mean epilogue."""
+    from mmrec_b200 import ops
+    g = torch.Generator(device=dev); g.manual_seed(world)
+    n = 4 * 1237
+    parts = [torch.randn(n, device=dev, generator=g) for _ in range(world)]
+    acc = torch.randn(n, device=dev, generator=g)
+    ref_sum = parts[0].clone()
+    for p in parts[1:]:
+        ref_sum = ref_sum + p
+    for div in (1.0, 4.0):
+        s_out = torch.empty(n, device=dev); a_out = acc.clone()
+        ops.peer_sum([p.data_ptr() for p in parts], n, acc_in=a_out, acc_out=a_out, acc_div=div, sum_out=s_out)
+        assert torch.equal(s_out, ref_sum)
+        ref_acc = (acc + ref_sum) / div if div != 1.0 else acc + ref_sum
+        assert torch.equal(a_out, ref_acc)
+    with pytest.raises(Exception):
+        ops.peer_sum([p.data_ptr() for p in parts], n - 1, sum_out=torch.empty(n, device=dev))
+
+
+@pytest.mark.parametrize("world,B,k", [(2, 300, 50), (3, 17, 20), (8, 64, 50)])
+def test_topk_merge_peers_matches_contiguous_merge(dev, world, B, k):
+    """mmrec_topk_merge_peers (lists by pointer, local -> global relabel inside) == mmrec_topk_merge on the gathered,
+    relabelled lists; ties resolve to the lower global index in both."""
+    from mmrec_b200 import ops
+    g = torch.Generator().manual_seed(world * 1000 + B)
+    vals = torch.sort((torch.randint(0, 40, (world, B, k), generator=g).float() / 8.0), dim=-1, descending=True).values   # many ties
+    idx = torch.stack([torch.stack([torch.randperm(5000, generator=g)[:k] for _ in range(B)]) for _ in range(world)])
+    vd = [vals[p].contiguous().to(dev) for p in range(world)]
+    idd = [idx[p].contiguous().to(dev) for p in range(world)]
+    v1, i1 = ops.topk_merge_peers([t.data_ptr() for t in vd], [t.data_ptr() for t in idd], B, k, dev, idx_mul=world, idx_add=1)
+    glob = torch.stack([idd[p] * world + p for p in range(world)])
+    v2, i2 = ops.topk_merge(torch.stack(vd), glob)
+    assert torch.equal(v1, v2) and torch.equal(i1, i2)

@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r22_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r22_pytest.log; tail -3 gpurun_out/r22_pytest.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_select_kernel -s 2 -c 1 -o gpurun_out/r22_select -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r22_ncu_sel.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r22_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r22_ncu_bench.log 2>&1
+timeout 200 python bench.py --no-cpu-baseline > gpurun_out/r22_bench.log 2>&1; tail -1 gpurun_out/r22_bench.log | cut -c1-300

@@ -1,0 +1,5 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r23_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r23_pytest.log; tail -3 gpurun_out/r23_pytest.log
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r23_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r23_ncu_bench.log 2>&1
+timeout 200 python bench.py --no-cpu-baseline > gpurun_out/r23_bench.log 2>&1; tail -1 gpurun_out/r23_bench.log | cut -c1-300
