@@ -39,7 +39,7 @@ struct FusedParams {
     float* thr;                         // [B][n_splits]
     int32_t* flags;                     // [B] fallback flags
     uint32_t* gthr;                     // [B] highest certified threshold of any split (order-preserving key), zeroed per launch
-    unsigned long long* gbins;          // [B] (lo, width) of the row's histogram window: the first split to seed sets it (0 = unset)
+    unsigned long long* gbins;          // [B] (lo, width) of the row's histogram window and seed threshold, from fz_prep_kernel (0 = degenerate)
     uint32_t* ghist;                    // [B][FZ_NB / 2] candidates counted per bin by ALL splits of the row (two 16-bit counters per word)
 };
 
@@ -165,62 +165,12 @@ __device__ __forceinline__ void fz_epilogue(const FusedParams& p, const FzSmem& 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 
     if (set == 0) {
-        // Seed from the first half tile.  gm[] = maxima of its 16 groups of 8 columns; thr0 = the r-th largest of them,
-        // so about r of the 128 scores pass.  r aims at ~2.5x the share the row finally needs (need / n_items) and is
-        // at least 8 (~6 %): the seed is the one threshold nothing certifies, so it has to be safe -- the row threshold
-        // (max over splits) must still leave k unmasked items above it -- and the certified thresholds take over from
-        // it after a tile or two anyway.
-        mbar_wait(bar + 9 * 8, 0);
-        fence_after_sync();
-        const int n_valid = n_items32 - it0 * TC_N;
-        float gm[16];
-#pragma unroll
-        for (int c = 0; c < FZ_HALF / FZ_CH; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x16(lane_base + c * FZ_CH, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                float m = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float x = (c * FZ_CH + g * 8 + j < n_valid) ? __uint_as_float(v[g * 8 + j]) : -INFINITY;
-                    m = fmaxf(m, x);
-                }
-                gm[c * 2 + g] = m;
-            }
-        }
-        float gmax = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) gmax = fmaxf(gmax, gm[j]);
-        int r = (int)ceilf(2.5f * (float)need * (float)FZ_HALF / (float)p.n_items);
-        r = r < 8 ? 8 : (r > 16 ? 16 : r);
-        float cur = gmax;
-        for (int i = 1; i < r; ++i) {                                // peel off the i-th largest (one instance at a time)
-            float nxt = -INFINITY;
-            bool removed = false;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (!removed && gm[j] == cur) { gm[j] = -INFINITY; removed = true; }
-                nxt = fmaxf(nxt, gm[j]);
-            }
-            cur = nxt;
-        }
-        float width = (gmax - cur) * (1.0f / 16.f), lo = cur, thr = cur;
+        // The row's histogram window (lo, width) and seed threshold were computed by fz_prep_kernel from a fixed sample of
+        // the catalogue (see there): the same for every split of the row, the same in every run.
+        const unsigned long long w = live ? p.gbins[row] : 0ull;
+        float lo = __uint_as_float((uint32_t)(w >> 32)), width = __uint_as_float((uint32_t)w), thr = lo;
         uint32_t bad = 0;
-        if (!(width > 0.f) || !(cur > -INFINITY) || !(gmax < INFINITY)) { bad = 1; width = 1.f; lo = 0.f; thr = INFINITY; }
-        if (!live) thr = INFINITY;                                   // padding rows: nothing passes, nothing is written
-        if (live && !bad) {
-            // One histogram window per ROW: the first split to get here publishes its (lo, width), the others adopt it
-            // (and its seed), so that the candidates of all splits are counted on the same bin edges.
-            const unsigned long long mine = ((unsigned long long)__float_as_uint(lo) << 32) | __float_as_uint(width);
-            const unsigned long long old = atomicCAS(p.gbins + row, 0ull, mine);
-            if (old != 0ull) {
-                lo = __uint_as_float((uint32_t)(old >> 32));
-                width = __uint_as_float((uint32_t)old);
-                thr = lo;
-            }
-        }
+        if (w == 0ull) { bad = live ? 1u : 0u; width = 1.f; lo = 0.f; thr = INFINITY; }   // degenerate sample (or padding row)
         rs[RS_THR * TC_M] = float_key(thr);
         rs[RS_CNT * TC_M] = 0;
         rs[RS_LO * TC_M] = __float_as_uint(lo);
@@ -502,13 +452,127 @@ __global__ void __launch_bounds__(MC_THREADS) mask_csr_small_kernel(int64_t nnz,
     }
 }
 
+// Seed threshold + histogram window of every row of the block, one warp per row: score the row against FZ_SAMPLE items
+// spread evenly over the catalogue (fp32 on CUDA cores: 128 x d FMAs per row), take the maxima of 16 groups of 8, the r-th
+// largest of them is the seed (about r / 128 of the catalogue passes; r aims at 2.5x the share the row needs, at least 8
+// = 6 %), 16 bins from there to the sample maximum and 16 more above.  The seed is the one threshold nothing certifies,
+// so it has to be safe -- the select kernel checks that k unmasked items clear it -- and it has to be the same whatever
+// the timing: it depends on the inputs only.
+constexpr int FZ_SAMPLE_FWD = 128;
+__device__ __forceinline__ void fz_seed_finish(const float (&acc)[4], int lane, int64_t row, int64_t n_items,
+                                               const int32_t* __restrict__ mask_ptr, int k, unsigned long long* __restrict__ gbins) {
+    // 16 groups of 8 sample scores: lanes l and l ^ 16 hold 4 each (items l + 32 e and (l ^ 16) + 32 e)
+    float gm = fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3]));
+    gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
+    float gmax = gm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    int need = k;
+    if (mask_ptr) need += mask_ptr[row + 1] - mask_ptr[row];
+    int r = (int)ceilf(2.5f * (float)need * (float)FZ_SAMPLE_FWD / (float)n_items);
+    r = r < 8 ? 8 : (r > 16 ? 16 : r);
+    // rank of my group's maximum among the 16 (ties broken by group number): the group of rank r - 1 holds the seed
+    int rank = 0;
+    const int grp = lane & 15;
+#pragma unroll
+    for (int g2 = 0; g2 < 16; ++g2) {
+        const float o = __shfl_sync(0xffffffffu, gm, g2);
+        rank += (o > gm) || (o == gm && g2 < grp);
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, rank == r - 1 && lane < 16);
+    const float cur = __shfl_sync(0xffffffffu, gm, who ? __ffs(who) - 1 : 0);
+    if (lane == 0) {
+        const float width = (gmax - cur) * (1.0f / 16.f);
+        unsigned long long w = 0ull;                                 // 0 = degenerate (constant / NaN / inf scores): exact kernel
+        if (who && width > 0.f && cur > -INFINITY && gmax < INFINITY)
+            w = ((unsigned long long)__float_as_uint(cur) << 32) | __float_as_uint(width);
+        gbins[row] = w;
+    }
+}
+
+constexpr int FZ_SAMPLE = 128;
+constexpr int FZ_SEED_ROWS = 32;        // rows per seeding CTA (4 per warp): the sample is staged once per CTA
+constexpr int FZ_SEED_DC = 32;          // embedding columns staged per pass (128 x 33 floats = 16.5 KB of shared memory)
+__device__ __forceinline__ void fz_seed_rows(int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int64_t nb,
+                                             const int64_t* __restrict__ users, const float* __restrict__ Ue, int64_t ldu, int d,
+                                             const int32_t* __restrict__ mask_ptr, int k, unsigned long long* __restrict__ gbins) {
+    __shared__ float tile[FZ_SAMPLE][FZ_SEED_DC + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int RPW = FZ_SEED_ROWS / 8;                            // rows per warp (blockDim = 256)
+    const int64_t row0 = (int64_t)blockIdx.x * FZ_SEED_ROWS + warp * RPW;
+    const bool vec_ok = (ldi & 3) == 0 && (((uintptr_t)Ie) & 15) == 0;
+    float acc[RPW][4];                                               // lane l scores sample items l, l + 32, l + 64, l + 96
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+    // the user rows of this warp, all passes, requested up front (d <= 128: at most 4 passes of 32 columns)
+    float ulv[RPW][4];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int64_t row = row0 + r;
+        const float* u = row < nb ? Ue + (users ? users[row] : row) * ldu : nullptr;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) ulv[r][ps] = (u && ps * FZ_SEED_DC + lane < d) ? __ldg(u + ps * FZ_SEED_DC + lane) : 0.f;
+    }
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+        const int c0 = ps * FZ_SEED_DC;
+        if (c0 >= d) break;                                          // block-uniform
+        __syncthreads();
+        if (vec_ok && c0 + FZ_SEED_DC <= d) {                        // 16-byte loads, all four of a thread in flight
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = (int)threadIdx.x + q * 256, si = idx >> 3, c4 = idx & 7;
+                v[q] = __ldg(reinterpret_cast<const float4*>(Ie + ((int64_t)si * n_items / FZ_SAMPLE) * ldi + c0) + c4);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = (int)threadIdx.x + q * 256, si = idx >> 3, c4 = idx & 7;
+                tile[si][c4 * 4 + 0] = v[q].x; tile[si][c4 * 4 + 1] = v[q].y; tile[si][c4 * 4 + 2] = v[q].z; tile[si][c4 * 4 + 3] = v[q].w;
+            }
+        } else {
+            for (int t = threadIdx.x; t < FZ_SAMPLE * FZ_SEED_DC; t += blockDim.x) {
+                const int si = t / FZ_SEED_DC, c = t % FZ_SEED_DC;   // coalesced along the embedding
+                tile[si][c] = (c0 + c < d) ? __ldg(Ie + ((int64_t)si * n_items / FZ_SAMPLE) * ldi + c0 + c) : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int64_t row = row0 + r;
+            if (row < nb) {                                          // warp-uniform
+                const float ul = ulv[r][ps];                         // FZ_SEED_DC == 32: one column per lane
+#pragma unroll 8
+                for (int c = 0; c < FZ_SEED_DC; ++c) {
+                    const float uc = __shfl_sync(0xffffffffu, ul, c);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[r][e] = fmaf(uc, tile[lane + 32 * e][c], acc[r][e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int64_t row = row0 + r;
+        if (row >= nb) continue;                                     // warp-uniform
+        fz_seed_finish(acc[r], lane, row, n_items, mask_ptr, k, gbins);
+    }
+}
+
 // One launch for everything the scoring kernel needs prepared: item operand (when `n_it` > 0), user operand of this row
 // block, and the zeroing of the per-block scratch words (flags, shared thresholds, slots, slot counter).
 __global__ void fz_prep_kernel(int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int64_t n_it, float* __restrict__ Ihi,
                                float* __restrict__ Ilo, int64_t nb, const int64_t* __restrict__ users, const float* __restrict__ Ue,
                                int64_t ldu, int64_t n_ut, float* __restrict__ Uhi, float* __restrict__ Ulo, int d, int KP,
-                               uint32_t* __restrict__ zero0, int64_t zero0_words, uint32_t* __restrict__ zero1, int64_t zero1_words) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+                               uint32_t* __restrict__ zero0, int64_t zero0_words, uint32_t* __restrict__ zero1, int64_t zero1_words,
+                               const int32_t* __restrict__ mask_ptr, int k, unsigned long long* __restrict__ gbins, int64_t seed_blocks) {
+    if ((int64_t)blockIdx.x < seed_blocks) {                         // warp-uniform role split: the first blocks seed the rows
+        fz_seed_rows(n_items, Ie, ldi, nb, users, Ue, ldu, d, mask_ptr, k, gbins);
+        return;
+    }
+    int64_t t = (blockIdx.x - seed_blocks) * (int64_t)blockDim.x + threadIdx.x;
     const int64_t ti = n_it * TC_N * (KP / 4), tu = n_ut * TC_M * (KP / 4);
     if (t < ti) { pack_split_one<TC_N>(t, n_items, nullptr, Ie, ldi, d, KP, Ihi, Ilo); return; }
     t -= ti;
@@ -1015,9 +1079,9 @@ static inline int fz_kp(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
 
 struct FzPlan {
     int KP, splits, tiles_per_split, cap, cap_rows;
-    int64_t n_ut, n_it, rows_blk;
+    int64_t n_ut, n_it, rows_blk, rows_pad;
     size_t off_uhi, off_ulo, off_ihi, off_ilo, off_cand, off_cnt, off_thr, off_flags, off_mptr, off_mcur, off_mitems, off_cub, off_slot,
-        off_keys,
+        off_keys, off_gbins,
         cub_bytes, total;
 };
 
@@ -1044,7 +1108,9 @@ static FzPlan fz_plan(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz
     P.off_ihi = take((size_t)P.n_it * TC_N * P.KP * 4); P.off_ilo = take((size_t)P.n_it * TC_N * P.KP * 4);
     P.off_cand = take((size_t)P.rows_blk * P.splits * P.cap * 8);
     P.off_cnt = take((size_t)P.rows_blk * P.splits * 4); P.off_thr = take((size_t)P.rows_blk * P.splits * 4);
-    P.off_flags = take((size_t)P.rows_blk * (8 + 8 + 2 * FZ_NB));   // flags | gthr | gbins (u64) | ghist [rows_blk][FZ_NB / 2]
+    P.rows_pad = (P.rows_blk + 3) & ~(int64_t)3;                     // keeps ghist 16-byte aligned behind flags | gthr
+    P.off_flags = take((size_t)(2 * P.rows_pad + (FZ_NB / 2) * P.rows_blk) * 4);   // flags | gthr | ghist [rows_blk][FZ_NB / 2]  (zeroed per block)
+    P.off_gbins = take((size_t)P.rows_blk * 8);                      // (lo, width) per row, written by the prep kernel
     P.off_mptr = take((size_t)(B + 2) * 4);
     P.off_mcur = take((size_t)(B + 2 > 1100 ? B + 2 : 1100) * 4);   // fill cursors, or the per-CTA order flags of the sorted-mask pass
     P.off_mitems = take((size_t)(mask_nnz > 0 ? mask_nnz : 1) * 4);
@@ -1117,11 +1183,13 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         const int64_t n_ut = (nb + TC_M - 1) / TC_M;
         // operands (items: split + re-tiled once, with the first row block) + zeroed scratch words, one launch
         const int64_t n_it_now = r0 == 0 ? P.n_it : 0;
-        const int64_t zero0 = (4 + FZ_NB / 2) * P.rows_blk, zero1 = P.rows_blk + 1;   // flags | gthr | gbins | ghist, slot | counter
+        const int64_t zero0 = 2 * P.rows_pad + (FZ_NB / 2) * P.rows_blk, zero1 = P.rows_blk + 1;   // flags | gthr | ghist, slot | counter
         const int64_t prep_threads = n_it_now * TC_N * (P.KP / 4) + n_ut * TC_M * (P.KP / 4) + zero0 + zero1;
-        fz_prep_kernel<<<(unsigned)((prep_threads + T - 1) / T), T, 0, stream>>>(
+        const int64_t seed_blocks = (nb + FZ_SEED_ROWS - 1) / FZ_SEED_ROWS;          // T = 256 threads: 8 warps x 4 rows
+        fz_prep_kernel<<<(unsigned)(seed_blocks + (prep_threads + T - 1) / T), T, 0, stream>>>(
             n_items, Ie, ldi, n_it_now, Ihi, Ilo, nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_ut, Uhi, Ulo, d, P.KP,
-            (uint32_t*)(base + P.off_flags), zero0, (uint32_t*)slot, zero1);
+            (uint32_t*)(base + P.off_flags), zero0, (uint32_t*)slot, zero1, has_mask ? mptr + r0 : nullptr, k,
+            (unsigned long long*)(base + P.off_gbins), seed_blocks);
         MMREC_LAUNCH_CHECK();
         FusedParams p;
         p.Uhi = Uhi; p.Ulo = Ulo; p.Ihi = Ihi; p.Ilo = Ilo; p.KP = P.KP; p.n_itiles = (int)P.n_it;
@@ -1129,9 +1197,9 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         p.mask_ptr = has_mask ? mptr + r0 : nullptr;
         p.cand = (float2*)(base + P.off_cand); p.cnt = (int32_t*)(base + P.off_cnt); p.thr = (float*)(base + P.off_thr);
         p.flags = (int32_t*)(base + P.off_flags);
-        p.gthr = (uint32_t*)(base + P.off_flags) + P.rows_blk;
-        p.gbins = (unsigned long long*)((uint32_t*)(base + P.off_flags) + 2 * P.rows_blk);
-        p.ghist = (uint32_t*)(base + P.off_flags) + 4 * P.rows_blk;
+        p.gthr = (uint32_t*)(base + P.off_flags) + P.rows_pad;
+        p.gbins = (unsigned long long*)(base + P.off_gbins);
+        p.ghist = (uint32_t*)(base + P.off_flags) + 2 * P.rows_pad;
         score_fused_kernel<<<(unsigned)(n_ut * P.splits), 64 + 128 * L.nsets, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
         fused_select_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, stream>>>(nb, P.splits, P.cap, k, item_offset, p.cand, p.cnt, p.thr, p.mask_ptr,

@@ -1,0 +1,4 @@
+set -x
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests -x -q -m gpu > gpurun_out/r28_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r28_pytest.log; tail -3 gpurun_out/r28_pytest.log
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r28_bench_n2.log 2>&1; echo "rc=$?" >> gpurun_out/r28_bench_n2.log; tail -2 gpurun_out/r28_bench_n2.log | cut -c1-300
