@@ -1,18 +1,20 @@
 // K3 fused: scores on tcgen05 (3xTF32, same pipeline as score_tc.cu) whose epilogue never writes the score matrix.
 //
-// Each epilogue thread owns one user row of the 128 x 256 accumulator tile and streams the items of its CTA's
-// item range through a threshold filter:
-//   * tile 0: thr0 = min over the eight 32-column groups of the group maximum (>= 8 items are above it); it seeds a
-//     32-bin linear histogram [thr0, thr0 + 2 (max0 - thr0)) of the values that pass;
-//   * every value >= thr is appended as a (value, item) pair to the row's candidate list in global memory and
-//     counted in the histogram; after each tile the threshold rises to the highest bin edge that still has
-//     `need` = k + (masked items of the row) candidates above it.  Masked train positives are NOT removed here:
-//     asking for k + m candidates guarantees k unmasked ones survive, so the mask is applied once, on the ~100
-//     finalists, instead of on 7,000 scores;
-//   * select kernel: per row, the finalists (value >= final threshold) of all item splits are gathered, masked
-//     items dropped, and a bitonic sort on (value desc, item asc) emits the top-k -- the contract of topk.cu.
-// Anything the filter cannot certify (candidate overflow, a degenerate histogram, NaNs) raises a per-row flag and
-// the row is recomputed by the exact fp32 kernel at the end of this file; no host round trip.
+//   fz_prep_kernel        one launch: split + re-tile the operands, zero the per-block scratch, and give every row a seed
+//                         threshold + histogram window from a fixed 128-item sample of the catalogue (deterministic);
+//   mask_csr_*_kernel     the batch's (row, item) mask as a CSR over batch rows (one pass when the rows arrive sorted);
+//   score_fused_kernel    each epilogue thread owns one user row of the 128 x 256 accumulator tile (4 sets of 4 warps: a
+//                         column half of one TMEM buffer each) and streams its items through a threshold filter: every
+//                         value >= thr is appended to the row's candidate list and counted in the row's histogram (32
+//                         linear bins in L2, shared by all item splits of the row); after each tile the threshold rises
+//                         to the highest bin edge that still has `need` = k + (masked items of the row) candidates above
+//                         it.  Masked train positives are NOT removed here: asking for k + m candidates guarantees k
+//                         unmasked ones survive, so the mask is applied once, on the ~100 finalists, instead of on 7,000
+//                         scores;
+//   fused_select_kernel   per row (one warp): the finalists (value >= the row's final threshold) of all item splits,
+//                         masked items dropped, top-k on (value desc, item asc) -- the contract of topk.cu.
+// Anything the filter cannot certify (candidate overflow, a degenerate sample, NaNs, fewer than k finalists) raises a
+// per-row flag and the row is recomputed by the exact fp32 kernels at the end of this file; no host round trip.
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -340,7 +342,7 @@ __global__ void mask_fill_kernel(int64_t nnz, const int64_t* __restrict__ rows, 
 }
 
 // Per-batch case (B <= MC_MAX_ROWS rows).  The reference's evaluation loader emits the mask row-major (batch row ascending:
-// src/utils/dataloader.py builds it user by user), so the common case is a sorted row array: mask_csr_sorted_kernel
+// src/utils/dataloader.py:370-391 builds it user by user), so the common case is a sorted row array: mask_csr_sorted_kernel
 // writes the row pointers from the positions where the row changes and checks the order as it goes, one fully parallel
 // pass.  If any CTA saw a descent, mask_csr_small_kernel (one CTA: count in shared memory, scan, fill) redoes the job
 // for arbitrary order; otherwise it exits at once.  No global atomics, no memsets, no library scan.
@@ -459,16 +461,14 @@ __global__ void __launch_bounds__(MC_THREADS) mask_csr_small_kernel(int64_t nnz,
 // so it has to be safe -- the select kernel checks that k unmasked items clear it -- and it has to be the same whatever
 // the timing: it depends on the inputs only.
 constexpr int FZ_SAMPLE_FWD = 128;
-__device__ __forceinline__ void fz_seed_finish(const float (&acc)[4], int lane, int64_t row, int64_t n_items,
-                                               const int32_t* __restrict__ mask_ptr, int k, unsigned long long* __restrict__ gbins) {
+__device__ __forceinline__ void fz_seed_finish(const float (&acc)[4], int lane, int64_t row, int64_t n_items, int need,
+                                               unsigned long long* __restrict__ gbins) {
     // 16 groups of 8 sample scores: lanes l and l ^ 16 hold 4 each (items l + 32 e and (l ^ 16) + 32 e)
     float gm = fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3]));
     gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
     float gmax = gm;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-    int need = k;
-    if (mask_ptr) need += mask_ptr[row + 1] - mask_ptr[row];
     int r = (int)ceilf(2.5f * (float)need * (float)FZ_SAMPLE_FWD / (float)n_items);
     r = r < 8 ? 8 : (r > 16 ? 16 : r);
     // rank of my group's maximum among the 16 (ties broken by group number): the group of rank r - 1 holds the seed
@@ -508,29 +508,40 @@ __device__ __forceinline__ void fz_seed_rows(int64_t n_items, const float* __res
         for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
     // the user rows of this warp, all passes, requested up front (d <= 128: at most 4 passes of 32 columns)
     float ulv[RPW][4];
+    int needv[RPW];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int64_t row = row0 + r;
+        needv[r] = k + ((mask_ptr && row < nb) ? mask_ptr[row + 1] - mask_ptr[row] : 0);
         const float* u = row < nb ? Ue + (users ? users[row] : row) * ldu : nullptr;
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) ulv[r][ps] = (u && ps * FZ_SEED_DC + lane < d) ? __ldg(u + ps * FZ_SEED_DC + lane) : 0.f;
+    }
+    // ... and so is the whole sample (all passes): one memory round trip for the kernel instead of one per pass
+    const bool fast = vec_ok && (d % FZ_SEED_DC) == 0;
+    float4 v[4][4];
+    if (fast) {
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = (int)threadIdx.x + q * 256, si = idx >> 3, c4 = idx & 7;
+                v[ps][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ps * FZ_SEED_DC < d)
+                    v[ps][q] = __ldg(reinterpret_cast<const float4*>(Ie + ((int64_t)si * n_items / FZ_SAMPLE) * ldi + ps * FZ_SEED_DC) + c4);
+            }
     }
 #pragma unroll
     for (int ps = 0; ps < 4; ++ps) {
         const int c0 = ps * FZ_SEED_DC;
         if (c0 >= d) break;                                          // block-uniform
         __syncthreads();
-        if (vec_ok && c0 + FZ_SEED_DC <= d) {                        // 16-byte loads, all four of a thread in flight
-            float4 v[4];
+        if (fast) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int idx = (int)threadIdx.x + q * 256, si = idx >> 3, c4 = idx & 7;
-                v[q] = __ldg(reinterpret_cast<const float4*>(Ie + ((int64_t)si * n_items / FZ_SAMPLE) * ldi + c0) + c4);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int idx = (int)threadIdx.x + q * 256, si = idx >> 3, c4 = idx & 7;
-                tile[si][c4 * 4 + 0] = v[q].x; tile[si][c4 * 4 + 1] = v[q].y; tile[si][c4 * 4 + 2] = v[q].z; tile[si][c4 * 4 + 3] = v[q].w;
+                tile[si][c4 * 4 + 0] = v[ps][q].x; tile[si][c4 * 4 + 1] = v[ps][q].y;
+                tile[si][c4 * 4 + 2] = v[ps][q].z; tile[si][c4 * 4 + 3] = v[ps][q].w;
             }
         } else {
             for (int t = threadIdx.x; t < FZ_SAMPLE * FZ_SEED_DC; t += blockDim.x) {
@@ -557,7 +568,7 @@ __device__ __forceinline__ void fz_seed_rows(int64_t n_items, const float* __res
     for (int r = 0; r < RPW; ++r) {
         const int64_t row = row0 + r;
         if (row >= nb) continue;                                     // warp-uniform
-        fz_seed_finish(acc[r], lane, row, n_items, mask_ptr, k, gbins);
+        fz_seed_finish(acc[r], lane, row, n_items, needv[r], gbins);
     }
 }
 
