@@ -288,27 +288,58 @@ def run_ours(args):
     K = args.steps
     msA, msB, msC = tA / K, tB / K, tC / K
 
-    # ---- e2e: same public API, HOST buffers, copies inside the timed region
+    # ---- e2e: same public API, HOST buffers (pinned), host<->device copies inside the timed region.  The step -- copies
+    # included -- is captured once into a CUDA graph and replayed, as a caller of the API would do for a fixed-shape
+    # step; if the capture of the pinned copies fails on this build the calls run eagerly.
     e2e_A = e2e_C = 0.0
-    h2d = d2h = 0
     out_u = torch.empty(U, d).pin_memory(); out_i = torch.empty(I, d).pin_memory()
     out_idx = [torch.empty(b[0].numel(), TOPK, dtype=torch.int64).pin_memory() for b in batches]
     users_h = [b[0].pin_memory() for b in batches]
+
+    def e2e_a():
+        ego_d = ego_h.to(dev, non_blocking=True)
+        all_emb = ops.propagate_mean(adj, ego_d, wl.n_layers)
+        i_out = ops.spmm(mm, ego_d[U:], base=all_emb[U:])
+        out_u.copy_(all_emb[:U], non_blocking=True); out_i.copy_(i_out, non_blocking=True)
+        return all_emb, i_out
+
+    def e2e_c():
+        for (u, m, mp), uh, oh in zip(batches, users_h, out_idx):
+            ud, md = uh.to(dev, non_blocking=True), mp.to(dev, non_blocking=True)
+            _, idx = ops.score_topk(state["ea"][:U], state["ei"], ud, md, TOPK)
+            oh.copy_(idx, non_blocking=True)
+
+    e2e_graphs, e2e_mode = {}, "cuda graph replay (pinned H2D/D2H copies inside the graph)"
+    with torch.cuda.stream(side), torch.no_grad():
+        state["ea"], state["ei"] = e2e_a(); e2e_c()
+        torch.cuda.synchronize()
+        try:
+            for name, fn in (("a", e2e_a), ("c", e2e_c)):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    out = fn()
+                e2e_graphs[name] = gph
+                if name == "a":
+                    state["ea"], state["ei"] = out
+            torch.cuda.synchronize()
+        except Exception as exc:                                     # noqa: BLE001
+            e2e_graphs, e2e_mode = {}, f"eager ({type(exc).__name__} during graph capture)"
+            torch.cuda.synchronize()
     with torch.no_grad():
         for step in range(args.warmup + args.steps):
             flush.zero_()
             e = [ev() for _ in range(4)]
             e[0].record()
-            ego_d = ego_h.to(dev, non_blocking=True)
-            all_emb = ops.propagate_mean(adj, ego_d, wl.n_layers)
-            i_out = ops.spmm(mm, ego_d[U:], base=all_emb[U:])
-            out_u.copy_(all_emb[:U], non_blocking=True); out_i.copy_(i_out, non_blocking=True)
+            if e2e_graphs:
+                e2e_graphs["a"].replay()
+            else:
+                state["ea"], state["ei"] = e2e_a()
             e[1].record()
             e[2].record()
-            for (u, m, mp), uh, oh in zip(batches, users_h, out_idx):
-                ud, md = uh.to(dev, non_blocking=True), mp.to(dev, non_blocking=True)
-                _, idx = ops.score_topk(all_emb[:U], i_out, ud, md, TOPK)
-                oh.copy_(idx, non_blocking=True)
+            if e2e_graphs:
+                e2e_graphs["c"].replay()
+            else:
+                e2e_c()
             e[3].record()
             torch.cuda.synchronize()
             if step >= args.warmup:
@@ -346,7 +377,7 @@ def run_ours(args):
                              "frac": score_flops / (msC * 1e-3) / 1e12 / (pk["bf16_tflops"] / 2),
                              "note": "peak = measured bf16 dense / 2 (TF32 rate); useful flops 2*B*I*d"},
         "e2e": {"value": edges / (e2e_msA * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "prop_ms": e2e_msA, "score_topk_ms": e2e_msC, "scored_items_per_sec": score_items / (e2e_msC * 1e-3)},
+                "prop_ms": e2e_msA, "score_topk_ms": e2e_msC, "scored_items_per_sec": score_items / (e2e_msC * 1e-3), "launch": e2e_mode},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if not args.no_cpu_baseline:

@@ -491,7 +491,7 @@ __device__ __forceinline__ void fz_seed_finish(const float (&acc)[4], int lane, 
 }
 
 constexpr int FZ_SAMPLE = 128;
-constexpr int FZ_SEED_ROWS = 32;        // rows per seeding CTA (4 per warp): the sample is staged once per CTA
+constexpr int FZ_SEED_ROWS = 16;        // rows per seeding CTA (2 per warp): the sample is staged once per CTA
 constexpr int FZ_SEED_DC = 32;          // embedding columns staged per pass (128 x 33 floats = 16.5 KB of shared memory)
 __device__ __forceinline__ void fz_seed_rows(int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int64_t nb,
                                              const int64_t* __restrict__ users, const float* __restrict__ Ue, int64_t ldu, int d,
@@ -550,17 +550,16 @@ __device__ __forceinline__ void fz_seed_rows(int64_t n_items, const float* __res
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-            const int64_t row = row0 + r;
-            if (row < nb) {                                          // warp-uniform
-                const float ul = ulv[r][ps];                         // FZ_SEED_DC == 32: one column per lane
 #pragma unroll 8
-                for (int c = 0; c < FZ_SEED_DC; ++c) {
-                    const float uc = __shfl_sync(0xffffffffu, ul, c);
+        for (int c = 0; c < FZ_SEED_DC; ++c) {                       // FZ_SEED_DC == 32: lane c holds column c0 + c of each row
+            float tv[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[r][e] = fmaf(uc, tile[lane + 32 * e][c], acc[r][e]);
-                }
+            for (int e = 0; e < 4; ++e) tv[e] = tile[lane + 32 * e][c];
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {                          // (rows beyond the block: zeros, nothing is written for them)
+                const float uc = __shfl_sync(0xffffffffu, ulv[r][ps], c);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[r][e] = fmaf(uc, tv[e], acc[r][e]);
             }
         }
     }
@@ -1196,7 +1195,7 @@ int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, i
         const int64_t n_it_now = r0 == 0 ? P.n_it : 0;
         const int64_t zero0 = 2 * P.rows_pad + (FZ_NB / 2) * P.rows_blk, zero1 = P.rows_blk + 1;   // flags | gthr | ghist, slot | counter
         const int64_t prep_threads = n_it_now * TC_N * (P.KP / 4) + n_ut * TC_M * (P.KP / 4) + zero0 + zero1;
-        const int64_t seed_blocks = (nb + FZ_SEED_ROWS - 1) / FZ_SEED_ROWS;          // T = 256 threads: 8 warps x 4 rows
+        const int64_t seed_blocks = (nb + FZ_SEED_ROWS - 1) / FZ_SEED_ROWS;          // T = 256 threads: 8 warps x 2 rows
         fz_prep_kernel<<<(unsigned)(seed_blocks + (prep_threads + T - 1) / T), T, 0, stream>>>(
             n_items, Ie, ldi, n_it_now, Ihi, Ilo, nb, users ? users + r0 : nullptr, users ? Ue : Ue + r0 * ldu, ldu, n_ut, Uhi, Ulo, d, P.KP,
             (uint32_t*)(base + P.off_flags), zero0, (uint32_t*)slot, zero1, has_mask ? mptr + r0 : nullptr, k,
