@@ -1,16 +1,18 @@
 // K1: CSR SpMM  y = A X  with the layer-combination epilogue fused (running sum / mean, "+h", LayerGCN's
-// cosine gate).  HBM/L2-bound gather kernel: no tensor cores (0.25-0.5 flop/byte).
+// cosine gate).  L2/HBM-bound gather kernel: no tensor cores (0.25-0.5 flop/byte).
 //
 // Mapping (D = embedding width, a multiple of 32 floats):
 //   * a task is a whole row or, for rows longer than the plan's segment length, one segment of it
 //     (mmrec_spmm_plan; tasks arrive sorted longest-first) -- the power-law item rows would otherwise
 //     serialise on one warp;
-//   * T lanes (default D/8) own one task, a warp runs 32/T tasks side by side; each lane holds V = D/(4T)
-//     float4 of the row, so one row of X is V coalesced T*16-byte requests; UNR rows of X are in flight per
-//     lane group before the first FMA;
-//   * column indices / values are fetched T at a time with one coalesced load per group and handed round
-//     with width-T shuffles; the next task's descriptor and the running-sum row of the epilogue are
-//     prefetched while the gather is in flight;
+//   * T lanes (default D/4: one float4 per lane) own one task, a warp runs 32/T tasks side by side; each lane
+//     holds V = D/(4T) float4 of the row, so one row of X is V coalesced T*16-byte requests; UNR rows of X are
+//     in flight per lane group before the first FMA;
+//   * every lane loads the (column, value) pairs it needs itself -- the T lanes of a group read the same
+//     address, one broadcast transaction, no shuffles in the gather loop; the next batch's indices, the next
+//     task's descriptor and the running-sum row of the epilogue are requested while the gather is in flight;
+//   * the longest tasks (plan: n_cta_tasks) are run by a whole CTA each, reduced through shared memory in
+//     lane-group order; the rest one lane group each, warps walking the sorted list boustrophedon;
 //   * split rows: each segment writes its partial sum to scratch, the LAST segment to arrive (per-row
 //     counter) adds the partials in segment order -> the summation order never depends on scheduling, so
 //     results are bit-reproducible.

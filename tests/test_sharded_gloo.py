@@ -79,6 +79,13 @@ def worker(rank, world, port, tmp):
             full_i[r::world] = parts[r]
         rv, ri = cpu_score_topk(u_g, full_i, users, mask, 20)
         assert torch.equal(idx, ri) and torch.allclose(v, rv, rtol=0, atol=0)
+        # the mask pre-filtered to the shard (what the bench / a per-rank loader passes) gives the same lists
+        lm = sharded.local_mask(sh, mask)
+        assert lm.shape[1] == int(((mask[1] % world) == rank).sum()) and torch.all(lm[1] < sh.n_local)
+        v2, idx2 = sharded.score_topk_sharded(sh, u_g, i_loc, users, lm, 20, score_topk=cpu_score_topk, merge=cpu_merge,
+                                              mask_is_local=True)
+        assert torch.equal(idx2, idx) and torch.equal(v2, v)
+        assert sharded.local_mask(sh, None) is None
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
