@@ -177,6 +177,50 @@ class Workload:
         return np.stack([self.tr_u[m][order] - lo, self.tr_i[m][order]])
 
 
+def torch_gpu_comparator(wl, kr, kc, kv, ego, batches_dev, flush, reps=5):
+    """The reference's own formulation on the same GPU with stock PyTorch kernels -- un-coalesced COO adjacency through
+    `torch.sparse.mm` per layer + `stack().mean()` (`src/models/freedom.py:164-178`), `matmul` + in-place mask +
+    `torch.topk` (`freedom.py:216-220`, `src/common/trainer.py:304-309`) -- timed with CUDA events.  This is the
+    "vs torch.sparse.mm" comparator BASELINE.json's config 2 names; it is context for the speed-up, not the product."""
+    from mmrec_b200 import graph
+    dev = ego.device
+    U, I = wl.U, wl.I
+    r, c, v = graph.norm_adj_entries(wl.tr_u, wl.tr_i, U, I)
+    adj = torch.sparse_coo_tensor(torch.from_numpy(np.stack([r, c])).to(dev), torch.from_numpy(v).to(dev), (U + I, U + I))
+    mm = torch.sparse_coo_tensor(torch.from_numpy(np.stack([kr, kc])).to(dev), torch.from_numpy(kv).to(dev), (I, I))
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def prop():
+        h = torch.sparse.mm(mm, ego[U:])
+        e, outs = ego, [ego]
+        for _ in range(wl.n_layers):
+            e = torch.sparse.mm(adj, e)
+            outs.append(e)
+        a = torch.stack(outs, dim=1).mean(dim=1)
+        return a[:U], a[U:] + h
+
+    def score(u_g, i_g):
+        for users, mask in batches_dev:
+            s = torch.matmul(u_g[users], i_g.t())
+            s[mask[0], mask[1]] = -1e10
+            torch.topk(s, TOPK, dim=-1)
+
+    tA = tC = 0.0
+    with torch.no_grad():
+        for it in range(reps + 2):
+            flush.zero_()
+            e = [ev() for _ in range(4)]
+            e[0].record(); u_g, i_g = prop(); e[1].record()
+            e[2].record(); score(u_g, i_g); e[3].record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tA += e[0].elapsed_time(e[1]); tC += e[2].elapsed_time(e[3])
+    edges = wl.n_layers * adj._nnz() + mm._nnz()
+    return {"what": "reference formulation with stock torch CUDA ops on this GPU (torch.sparse.mm on the un-coalesced COO, matmul + mask + "
+                    "torch.topk), eager", "edges_per_sec": edges / (tA / reps * 1e-3), "prop_ms": tA / reps,
+            "scored_items_per_sec": U * I / (tC / reps * 1e-3), "score_topk_ms": tC / reps}
+
+
 # ------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------
@@ -380,6 +424,10 @@ def run_ours(args):
                 "prop_ms": e2e_msA, "score_topk_ms": e2e_msC, "scored_items_per_sec": score_items / (e2e_msC * 1e-3), "launch": e2e_mode},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    try:
+        res["extra"]["torch_gpu_comparator"] = torch_gpu_comparator(wl, kr, kc, kv, ego, batches_dev, flush)
+    except Exception as exc:                                         # noqa: BLE001  (context only: never fail the bench line over it)
+        res["extra"]["torch_gpu_comparator"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     if not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(wl, kr, kc, kv, steps=3)
     print(json.dumps(res))
