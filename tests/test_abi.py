@@ -42,6 +42,16 @@ def test_argument_errors_without_a_gpu():
     assert lib.mmrec_topk_rows_f32(4, 10, None, 10, 11, 0, None, None, None) == -1     # k > n_items
     assert lib.mmrec_project_f32(-5, None, None, 0, 0, None, None, 0, 0, None, 0, None, 0, None) == -1
     assert lib.mmrec_topk_merge(100, 4, 50, None, None, None, None, None) == -1        # parts * k > 4096
+    # K4, peer-memory exchange: world out of range, n not a multiple of 4 floats, null list pointers
+    two = (ctypes.c_void_p * 2)(16, 32)
+    assert lib.mmrec_peer_sum_f32(8, 0, ctypes.cast(two, ctypes.c_void_p), None, None, 1.0, None, None) == -1
+    assert lib.mmrec_peer_sum_f32(6, 2, ctypes.cast(two, ctypes.c_void_p), None, None, 1.0, None, None) == -1
+    assert b"peer_sum" in lib.mmrec_last_error()
+    assert lib.mmrec_topk_merge_peers(17, 4, 10, ctypes.cast(two, ctypes.c_void_p), ctypes.cast(two, ctypes.c_void_p), 1, 0,
+                                      None, None, None) == -1                          # more than 16 lists
+    assert lib.mmrec_topk_merge_peers(2, 0, 10, ctypes.cast(two, ctypes.c_void_p), ctypes.cast(two, ctypes.c_void_p), 2, 1,
+                                      None, None, None) == 0                           # B == 0: nothing to do
+    assert lib.mmrec_launch_count() >= 0
 
 
 def test_product_path_refuses_cpu_tensors():
@@ -61,6 +71,7 @@ def test_product_never_imports_the_oracle():
     out = subprocess.run([sys.executable, "-c",
                           "import sys; sys.path.insert(0, %r); import mmrec_b200.ops, mmrec_b200.graph, "
                           "mmrec_b200.models.freedom, mmrec_b200.models.bm3, mmrec_b200.models.mgcn, "
+                          "mmrec_b200.models.lightgcn, mmrec_b200.models.layergcn, mmrec_b200.models.mmgcn, mmrec_b200.sharded, "
                           "mmrec_b200.common.trainer, mmrec_b200.utils.quick_start; "
                           "print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))" % ROOT],
                          capture_output=True, text=True, check=True)
