@@ -157,3 +157,13 @@ def test_models_fail_loudly_without_cuda(tiny_run):
             cfg[k] = cfg[k][0]
     with pytest.raises(MMRecError):
         get_model("FREEDOM")(cfg, dl)
+
+
+def test_reference_arm_runs_on_rank_zero_only():
+    """`bench.py --impl reference` under torchrun: every rank but 0 exits 0 without work and without output."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
