@@ -49,39 +49,45 @@ class BM3(GeneralRecommender):
         return u_g, i_g + h
 
     def calculate_loss(self, interactions):
-        u_online_ori, i_online_ori = self.forward()
-        t_feat_online, v_feat_online = None, None
+        """`bm3.py:97-147`.  The graph encoder and the two projections run on the hot-path kernels; what follows them
+        (`_objective`) is row-wise torch arithmetic on [N, d] tensors, kept op for op in the reference's order because
+        the dropout targets consume the RNG stream and the loss is compared bit for bit."""
+        u_all, i_all = self.forward()
+        t_proj = v_proj = None
         if self.t_feat is not None:
-            t_feat_online = ops.project(self.text_embedding.weight, self.text_trs.weight, self.text_trs.bias)
+            t_proj = ops.project(self.text_embedding.weight, self.text_trs.weight, self.text_trs.bias)
         if self.v_feat is not None:
-            v_feat_online = ops.project(self.image_embedding.weight, self.image_trs.weight, self.image_trs.bias)
+            v_proj = ops.project(self.image_embedding.weight, self.image_trs.weight, self.image_trs.bias)
+        return self._objective(u_all, i_all, t_proj, v_proj, interactions[0], interactions[1])
+
+    @staticmethod
+    def _apart(online, target):
+        """1 - mean cosine similarity of the online view to a stop-gradient target (`bm3.py:134-146`)."""
+        return 1 - cosine_similarity(online, target.detach(), dim=-1).mean()
+
+    def _objective(self, u_all, i_all, t_proj, v_proj, users, items):
+        # targets: dropout views of the online embeddings, drawn in the reference's order (users, items, text, image)
         with torch.no_grad():
-            u_target, i_target = u_online_ori.clone(), i_online_ori.clone()
+            u_target, i_target = u_all.clone(), i_all.clone()
             u_target = F.dropout(u_target, self.dropout)
             i_target = F.dropout(i_target, self.dropout)
-            if self.t_feat is not None:
-                t_feat_target = F.dropout(t_feat_online.clone(), self.dropout)
-            if self.v_feat is not None:
-                v_feat_target = F.dropout(v_feat_online.clone(), self.dropout)
-        u_online, i_online = self.predictor(u_online_ori), self.predictor(i_online_ori)
-        users, items = interactions[0], interactions[1]
+            t_target = None if t_proj is None else F.dropout(t_proj.clone(), self.dropout)
+            v_target = None if v_proj is None else F.dropout(v_proj.clone(), self.dropout)
+        u_online, i_online = self.predictor(u_all), self.predictor(i_all)
         u_online, i_online = u_online[users, :], i_online[items, :]
         u_target, i_target = u_target[users, :], i_target[items, :]
-        loss_t, loss_v, loss_tv, loss_vt = 0.0, 0.0, 0.0, 0.0
-        if self.t_feat is not None:
-            t_feat_online = self.predictor(t_feat_online)[items, :]
-            t_feat_target = t_feat_target[items, :]
-            loss_t = 1 - cosine_similarity(t_feat_online, i_target.detach(), dim=-1).mean()
-            loss_tv = 1 - cosine_similarity(t_feat_online, t_feat_target.detach(), dim=-1).mean()
-        if self.v_feat is not None:
-            v_feat_online = self.predictor(v_feat_online)[items, :]
-            v_feat_target = v_feat_target[items, :]
-            loss_v = 1 - cosine_similarity(v_feat_online, i_target.detach(), dim=-1).mean()
-            loss_vt = 1 - cosine_similarity(v_feat_online, v_feat_target.detach(), dim=-1).mean()
-        loss_ui = 1 - cosine_similarity(u_online, i_target.detach(), dim=-1).mean()
-        loss_iu = 1 - cosine_similarity(i_online, u_target.detach(), dim=-1).mean()
-        return (loss_ui + loss_iu).mean() + self.reg_weight * self.reg_loss(u_online_ori, i_online_ori) + \
-            self.cl_weight * (loss_t + loss_v + loss_tv + loss_vt).mean()
+        # per modality: (feature view vs. id target, feature view vs. its own dropout target)
+        loss_t = loss_tv = loss_v = loss_vt = 0.0
+        if t_proj is not None:
+            t_online = self.predictor(t_proj)[items, :]
+            loss_t, loss_tv = self._apart(t_online, i_target), self._apart(t_online, t_target[items, :])
+        if v_proj is not None:
+            v_online = self.predictor(v_proj)[items, :]
+            loss_v, loss_vt = self._apart(v_online, i_target), self._apart(v_online, v_target[items, :])
+        align = (self._apart(u_online, i_target) + self._apart(i_online, u_target)).mean()
+        reg = self.reg_weight * self.reg_loss(u_all, i_all)
+        modal = self.cl_weight * (loss_t + loss_v + loss_tv + loss_vt).mean()
+        return align + reg + modal
 
     def _score_embeddings(self):
         def run():

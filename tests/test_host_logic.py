@@ -167,3 +167,43 @@ def test_reference_arm_runs_on_rank_zero_only():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "3"],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bm3_objective_is_the_references_op_sequence():
+    """BM3's loss arithmetic after the hot-path kernels (`BM3._objective`) against the golden-pinned oracle `bm3_loss`
+    on CPU tensors: same RNG draws, bit-identical loss and parameter gradients.  (n_layers = 0 makes the oracle's
+    graph encoder the identity, so both sides see the same encoder outputs without a GPU.)"""
+    import types
+    import torch.nn.functional as F
+    from oracle import mmrec_oracle as O
+    from mmrec_b200.models.bm3 import BM3
+    from mmrec_b200.common.loss import EmbLoss
+    g = torch.Generator().manual_seed(5)
+    U, I, d, Fv, Ft, B = 30, 25, 16, 40, 24, 64
+    names = {"user_embedding.weight": (U, d), "item_id_embedding.weight": (I, d), "image_embedding.weight": (I, Fv),
+             "text_embedding.weight": (I, Ft), "image_trs.weight": (d, Fv), "image_trs.bias": (d,), "text_trs.weight": (d, Ft),
+             "text_trs.bias": (d,), "predictor.weight": (d, d), "predictor.bias": (d,)}
+    base = {k: torch.randn(*shape, generator=g) * 0.3 for k, shape in names.items()}
+    batch = torch.stack([torch.randint(0, U, (B,), generator=g), torch.randint(0, I, (B,), generator=g)])
+    adj = torch.sparse_coo_tensor(torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0), (U + I, U + I))
+    results = []
+    for side in ("oracle", "product"):
+        p = {k: v.clone().requires_grad_(True) for k, v in base.items()}
+        torch.manual_seed(123)
+        if side == "oracle":
+            loss = O.bm3_loss(p, adj, batch, 0, 0.1, 2.0, 0.3)
+        else:
+            pred = types.SimpleNamespace(weight=p["predictor.weight"], bias=p["predictor.bias"])
+            ns = types.SimpleNamespace(dropout=0.3, reg_weight=0.1, cl_weight=2.0, reg_loss=EmbLoss(), _apart=BM3._apart,
+                                       predictor=lambda x: F.linear(x, pred.weight, pred.bias))
+            u_all = p["user_embedding.weight"]
+            i_all = p["item_id_embedding.weight"] + p["item_id_embedding.weight"]
+            t_proj = F.linear(p["text_embedding.weight"], p["text_trs.weight"], p["text_trs.bias"])
+            v_proj = F.linear(p["image_embedding.weight"], p["image_trs.weight"], p["image_trs.bias"])
+            loss = BM3._objective(ns, u_all, i_all, t_proj, v_proj, batch[0], batch[1])
+        loss.backward()
+        results.append((loss.detach(), {k: v.grad for k, v in p.items()}))
+    (l0, g0), (l1, g1) = results
+    assert torch.equal(l0, l1)
+    for k in names:
+        assert torch.allclose(g0[k], g1[k], rtol=1e-6, atol=1e-9), k
