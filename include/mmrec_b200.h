@@ -33,7 +33,7 @@ extern "C" {
 #define MMREC_ECUDA (-3)       /* a CUDA runtime call failed; see mmrec_last_error() */
 #define MMREC_EUNSUPPORTED (-4)/* device is not sm_100 (the library carries sm_100a code only) */
 
-#define MMREC_ABI_VERSION 1
+#define MMREC_ABI_VERSION 2
 
 int mmrec_abi_version(void);
 const char* mmrec_last_error(void);
@@ -141,16 +141,25 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
  *                     [item_offset, item_offset + n_items)
  * mmrec_topk_rows_f32: out_idx/out_val [B, k], descending value, ties -> lower index, index
  *                     reported as column + item_offset.  1 <= k <= 1024, k <= n_items.
- * mmrec_score_topk_f32: all three fused, scores never materialised in HBM.
- *                     ws from mmrec_score_topk_workspace_bytes.
+ * mmrec_score_topk_f32: all three fused, scores never materialised in HBM (score_cf.cu): the tensor cores compute
+ *                     tf32 scores with a proven error bound and only FILTER (per-row certified threshold = the
+ *                     (k + masked)-th largest group maximum minus the bound); every candidate that survives is scored
+ *                     again in fp32 (fmaf) from the original tables and ranked on that value, ties -> lower index.
+ *                     Nothing depends on timing.  ws from mmrec_score_topk_workspace_bytes.
+ * mmrec_catalog_pack_f32 / mmrec_score_topk_cat_f32: the same with the item operand prepared once per embedding
+ *                     table instead of once per batch (the reference calls full_sort_predict per eval batch of 4096
+ *                     users against the same item table, src/common/trainer.py:302-310).  `cat`: 1024-byte aligned
+ *                     buffer of mmrec_catalog_bytes(n_items, d) bytes; it must be re-packed whenever Ie changes and
+ *                     passed together with the same (n_items, Ie, ldi, d).  cat == NULL packs into ws.
  * mmrec_topk_merge:   merge `parts` sorted lists per user ([parts, B, k] values + indices) into
  *                     one (the per-user top-k reduction across item shards).
  * ------------------------------------------------------------------------------------------- */
 /* path of mmrec_score_f32 / mmrec_score_topk_f32 (env MMREC_SCORE_PATH = simt | tc | auto | fused sets the start value):
  *   0 simt   exact fp32 on CUDA cores
  *   1 tc     tcgen05 3xTF32 GEMM into an L2-resident score block, then mask + radix-select top-k kernels
- *   2 auto   (default) fused wherever its shape rules allow (n_items >= 8k + 512, k <= 256, d <= 128), else tc
- *   3 fused  tcgen05 3xTF32 GEMM with the threshold-filter top-k fused into its epilogue, no score matrix */
+ *   2 auto   (default) fused wherever its shape rules allow (k <= 256, d <= 128, at least 2k item groups of 16..128
+ *            items), else tc
+ *   3 fused  certified-filter path, no score matrix */
 int mmrec_score_set_path(int path);
 size_t mmrec_score_workspace_bytes(int64_t B, int64_t n_items, int d);
 int mmrec_score_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu,
@@ -166,8 +175,17 @@ int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64
                          int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols,
                          int k, int64_t item_offset, int64_t* out_idx, float* out_val,
                          void* ws, size_t ws_bytes, void* stream);
-/* diagnostic, synchronising: rows of the last row block of the last fused call on `ws` that needed the exact kernel */
-int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz);
+size_t mmrec_catalog_bytes(int64_t n_items, int d);
+int mmrec_catalog_pack_f32(int64_t n_items, const float* Ie, int64_t ldi, int d,
+                           void* cat, size_t cat_bytes, void* stream);
+int mmrec_score_topk_cat_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu,
+                             int64_t n_items, const float* Ie, int64_t ldi, int d, const void* cat,
+                             int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols,
+                             int k, int64_t item_offset, int64_t* out_idx, float* out_val,
+                             void* ws, size_t ws_bytes, void* stream);
+/* diagnostic, synchronising: rows of the last row block of the last fused call on `ws` that needed the exact kernel
+ * (with_cat: the call packed its catalogue into ws, i.e. cat was NULL) */
+int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, int with_cat);
 int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, const int64_t* idx,
                      int64_t* out_idx, float* out_val, void* stream);
 /* the same merge over lists left where each rank wrote them (peer-mapped memory): vals[p] / idx[p] are host

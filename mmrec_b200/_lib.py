@@ -39,13 +39,18 @@ PROTOTYPES = {
     "mmrec_score_topk_workspace_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "mmrec_score_topk_f32": (_i32, [_i64, _p, _p, _i64, _i64, _p, _i64, _i32, _i64, _p, _p, _i32, _i64, _p, _p, _p,
                                     _sz, _p]),
-    "mmrec_debug_fused_fallback_rows": (_i64, [_p, _i64, _i64, _i32, _i32, _i64]),
+    "mmrec_catalog_bytes": (_sz, [_i64, _i32]),
+    "mmrec_catalog_pack_f32": (_i32, [_i64, _p, _i64, _i32, _p, _sz, _p]),
+    "mmrec_score_topk_cat_f32": (_i32, [_i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p, _i64, _p, _p, _i32, _i64, _p, _p, _p,
+                                        _sz, _p]),
+    "mmrec_debug_fused_fallback_rows": (_i64, [_p, _i64, _i64, _i32, _i32, _i64, _i32]),
     "mmrec_topk_merge": (_i32, [_i32, _i64, _i32, _p, _p, _p, _p, _p]),
     "mmrec_topk_merge_peers": (_i32, [_i32, _i64, _i32, _p, _p, _i64, _i64, _p, _p, _p]),
     "mmrec_peer_sum_f32": (_i32, [_i64, _i32, _p, _p, _p, _f32, _p, _p]),
 }
 
 _lib = None
+ABI_VERSION = 2
 
 
 class MMRecError(RuntimeError):
@@ -64,7 +69,7 @@ def load():
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.mmrec_abi_version() != 1:
+    if lib.mmrec_abi_version() != ABI_VERSION:
         raise MMRecError("libmmrec_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -18,18 +18,21 @@ namespace mmrec {
 int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie,
              int64_t ldi, int d, float* S, int64_t ldS, void* ws, size_t ws_bytes, cudaStream_t stream);
 size_t score_tc_workspace_bytes(int64_t B, int64_t n_items, int d);
-// score_fused.cu: 1 handled, 0 unsupported
-int score_fused(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie, int64_t ldi,
-                int d, int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int k, int64_t item_offset,
-                int64_t* out_idx, float* out_val, void* ws, size_t ws_bytes, cudaStream_t stream);
-size_t score_fused_workspace_bytes(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz);
+// score_cf.cu (certified-filter fused path): 1 handled, 0 unsupported shape / workspace
+int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie, int64_t ldi,
+             int d, const void* cat, int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int k, int64_t item_offset,
+             int64_t* out_idx, float* out_val, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t score_cf_workspace_bytes(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, bool with_cat);
+size_t cf_catalog_bytes(int64_t n_items, int d);
+int cf_catalog_pack(int64_t n_items, const float* Ie, int64_t ldi, int d, void* cat, size_t cat_bytes, cudaStream_t stream);
+int64_t score_cf_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, bool with_cat);
 
 int mask_apply(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int64_t row0, int64_t B,
                int64_t n_items, int64_t item_offset, float* S, int64_t ldS, cudaStream_t stream);
 
 // -1 unset | 0 simt: exact fp32 CUDA cores | 1 tc: tcgen05 GEMM -> L2-resident score block -> mask -> streaming top-k
-//  2 auto (default): fused wherever its shape rules allow (measured faster than tc from 7k items up), else tc
-//  3 fused: tcgen05 GEMM with the threshold-filter top-k in its epilogue (no score matrix at all)
+//  2 auto (default): fused wherever its shape rules allow (enough item groups for the certified threshold), else tc
+//  3 fused: the certified-filter path of score_cf.cu (tcgen05 tf32 filter + exact fp32 finalists, no score matrix at all)
 static int g_score_path = -1;
 static int score_path() {
     if (g_score_path < 0) {
@@ -41,7 +44,7 @@ static int score_path() {
     }
     return g_score_path;
 }
-static bool want_fused(int64_t n_items) { (void)n_items; return score_path() >= 2; }   // measured: fused wins from 7k items up
+static bool want_fused(int64_t n_items) { (void)n_items; return score_path() >= 2; }
 }  // namespace mmrec
 
 using namespace mmrec;
@@ -83,24 +86,46 @@ extern "C" size_t mmrec_score_topk_workspace_bytes(int64_t B, int64_t n_items, i
     const int64_t rows = score_block_rows(B, n_items);
     const size_t unfused = align_up((size_t)rows * (size_t)((n_items + 3) / 4 * 4) * sizeof(float) + 256, 1024) +
                            mmrec_score_workspace_bytes(rows, n_items, d);
-    const size_t fused = score_fused_workspace_bytes(B, n_items, d, k, B * 64 + 4096);   // mask_nnz is not known here
+    const size_t fused = score_cf_workspace_bytes(B, n_items, d, k, B * 64 + 4096, true);   // mask_nnz is not known here
     return unfused > fused ? unfused : fused;
+}
+
+extern "C" size_t mmrec_catalog_bytes(int64_t n_items, int d) { return cf_catalog_bytes(n_items, d); }
+
+extern "C" int mmrec_catalog_pack_f32(int64_t n_items, const float* Ie, int64_t ldi, int d, void* cat, size_t cat_bytes, void* stream_) {
+    MMREC_CHECK_ARG(n_items >= 1 && d >= 1 && Ie && ldi >= d, "catalog_pack: bad sizes / null pointer");
+    MMREC_CHECK_ARG(cf_catalog_bytes(n_items, d) > 0, "catalog_pack: d > 128 has no tensor-core path");
+    return cf_catalog_pack(n_items, Ie, ldi, d, cat, cat_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, int with_cat) {
+    return score_cf_fallback_rows(ws, B, n_items, d, k, mask_nnz, with_cat != 0);
 }
 
 extern "C" int mmrec_score_topk_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items,
                                     const float* Ie, int64_t ldi, int d, int64_t mask_nnz, const int64_t* mask_rows,
                                     const int64_t* mask_cols, int k, int64_t item_offset, int64_t* out_idx,
                                     float* out_val, void* ws, size_t ws_bytes, void* stream_) {
+    return mmrec_score_topk_cat_f32(B, users, Ue, ldu, n_items, Ie, ldi, d, nullptr, mask_nnz, mask_rows, mask_cols, k, item_offset, out_idx,
+                                    out_val, ws, ws_bytes, stream_);
+}
+
+extern "C" int mmrec_score_topk_cat_f32(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items,
+                                        const float* Ie, int64_t ldi, int d, const void* cat, int64_t mask_nnz,
+                                        const int64_t* mask_rows, const int64_t* mask_cols, int k, int64_t item_offset,
+                                        int64_t* out_idx, float* out_val, void* ws, size_t ws_bytes, void* stream_) {
     MMREC_CHECK_ARG(B >= 0 && n_items >= 1 && d >= 1 && k >= 1, "score_topk: bad sizes");
     if (B == 0) return MMREC_OK;
+    MMREC_CHECK_ARG(Ue && Ie && out_idx && out_val && ldu >= d && ldi >= d, "score_topk: null pointer or bad leading dimension");
+    MMREC_CHECK_ARG(mask_nnz == 0 || (mask_rows && mask_cols), "score_topk: mask pointers missing");
     const size_t need = mmrec_score_topk_workspace_bytes(B, n_items, d, k);
     if (!ws || ws_bytes < need) {
         set_error("score_topk: workspace %zu < %zu", ws_bytes, need);
         return MMREC_EWORKSPACE;
     }
-    if (want_fused(n_items) && score_fused_workspace_bytes(B, n_items, d, k, mask_nnz) <= ws_bytes) {
-        int r = score_fused(B, users, Ue, ldu, n_items, Ie, ldi, d, mask_nnz, mask_rows, mask_cols, k, item_offset, out_idx,
-                            out_val, ws, ws_bytes, (cudaStream_t)stream_);
+    if (want_fused(n_items)) {
+        int r = score_cf(B, users, Ue, ldu, n_items, Ie, ldi, d, cat, mask_nnz, mask_rows, mask_cols, k, item_offset, out_idx,
+                         out_val, ws, ws_bytes, (cudaStream_t)stream_);
         if (r != 0) return r < 0 ? r : MMREC_OK;
     }
     float* S = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);

@@ -1,0 +1,1055 @@
+// K3: full-catalog scoring fused with mask + top-k as a CERTIFIED FILTER on the tensor cores.
+//
+// The score matrix (115 MB per 4096 users at 7k items, 16 GB at 1M) is never written and no threshold depends on
+// timing.  The tensor cores (tcgen05, kind::tf32, ONE pass over operands rounded to tf32) compute APPROXIMATE scores
+// s~ with a proven bound |s~ - s| <= eps * |u| * max|i|; they are only used to decide which (user, item) pairs can
+// be in the top-k.  Every pair that can is then scored again in full fp32 (fmaf chain, the arithmetic of the exact
+// kernel below), and the final order is taken on those fp32 values -- so the result is the fp32 top-k, tie -> lower
+// item index, exactly the contract of topk.cu.
+//
+//   cf_pack_kernel      operands -> tf32 (round to nearest) in the UMMA canonical K-major no-swizzle layout, tiles of
+//                       128 rows; row norms (users) / maximum row norm (catalogue).  The catalogue side is packed once
+//                       per embedding table (mmrec_catalog_pack_f32), not once per batch.
+//   cf_pass_kernel<1>   s~ for every (user, item); epilogue = maximum of every group of w = 16 gw consecutive items
+//                       (tcgen05.ld -> FMNMX3 tree), written as gmax[row][group].  No branches, no atomics.
+//   cf_thr_kernel       per row: t = the need-th largest group maximum, need = k + (masked items of the row).  At
+//                       least `need` distinct items have s~ >= t, so >= k unmasked ones have s >= t - eps'; hence every
+//                       member of the true top-k has s~ >= thr = t - 2 eps'.
+//   cf_pass_kernel<2>   s~ again (same instructions, same bits); epilogue = one bit per score, s~ >= thr, 128 bits per
+//                       (row, item tile) written as one 16-byte store.  ~ (need + a few) bits per row are set.
+//   cf_final_kernel     per row (one warp): the set bits -> drop masked items -> exact fp32 score from the ORIGINAL
+//                       tables -> rank on (value desc, item asc) -> top-k.
+//   cf_exact_kernel     rows the filter cannot serve (need > number of groups, > CF_CAP candidates, non-finite scores):
+//                       all items in fp32 on CUDA cores + radix select; exits at once when no row is flagged.
+// Work distribution of the passes: a unit = (pair of 128-user tiles, 128-item tile); the units are dealt to the CTAs
+// (one per SM) in contiguous runs, so every SM gets the same number of units whatever the batch size (no wave
+// quantisation), a 256-user operand stays resident while its run of item tiles streams through a bulk-copy ring, and
+// every item slab read from L2 feeds two MMAs (32 B/cycle/SM at full tensor rate; one 128-user tile per CTA would
+// need 64, more than L2 delivers to 148 SMs).
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cub/device/device_scan.cuh>
+
+#include "tc_common.cuh"
+
+namespace mmrec {
+
+using namespace tc;
+
+constexpr int CF_TILE = 128;                    // rows of one MMA operand tile (users: TMEM lanes; items: TMEM columns)
+constexpr int CF_KC = 32;                       // k per item slab
+constexpr int CF_SLAB = CF_TILE * CF_KC * 4;    // 16 KB
+constexpr int CF_EPI_WARPS = 16;                // (buffer parity, user half, TMEM lane quarter)
+constexpr int CF_THREADS = 64 + 32 * CF_EPI_WARPS;
+constexpr int CF_MAX_STAGES = 8;
+constexpr int CF_CAP = 512;                     // candidates one warp ranks per row
+constexpr int CF_EX_SLOTS = 128;                // CTAs (and key buffers) of the exact kernel
+constexpr float CF_EPS = 1.125f / 1024.f;       // |s~ - s| <= CF_EPS |u| |i|: two RN roundings to tf32 (2^-11 each) + accumulation slack
+
+struct CfSmem {
+    uint32_t a, slab0, bars, tmem_ptr, total;
+    int stages;
+};
+__host__ __device__ inline CfSmem cf_smem(int KP) {
+    CfSmem L;
+    L.a = 0;
+    L.slab0 = 2 * CF_TILE * KP * 4;             // the 256-user operand: two tiles of 128
+    L.stages = KP >= 128 ? 5 : CF_MAX_STAGES;
+    L.bars = L.slab0 + L.stages * CF_SLAB;
+    L.tmem_ptr = L.bars + 32 * 8;
+    L.total = L.tmem_ptr + 16;
+    return L;
+}
+// barrier slots
+enum { CB_AFULL = 0, CB_AFREE = 1, CB_FULL = 2, CB_EMPTY = 2 + CF_MAX_STAGES, CB_TFULL = 2 + 2 * CF_MAX_STAGES, CB_TEMPTY = 4 + 2 * CF_MAX_STAGES };
+
+struct CfParams {
+    const float* Upk;                           // [pairs][2][KP/4][16][8][4]
+    const float* Ipk;                           // [item tiles][KP/4][16][8][4]
+    int KP, n_it;
+    int64_t B, n_items, n_units;
+    float* gmax; int G, gw;                     // pass 1: [B][G], G = n_it * (8 / gw)
+    const float* thr; uint4* bitmap;            // pass 2: [B], [B][n_it]
+};
+
+__device__ __forceinline__ void cf_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+// wait for the outstanding tcgen05.ld of this thread; the registers are operands so that no use of them can be
+// scheduled above the wait
+__device__ __forceinline__ void cf_tmem_wait16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
+__device__ __forceinline__ float cf_max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float cf_max16(const uint32_t (&v)[16]) {
+#define CF_F(i) __uint_as_float(v[i])
+    const float a = cf_max3(CF_F(0), CF_F(1), CF_F(2)), b = cf_max3(CF_F(3), CF_F(4), CF_F(5)), c = cf_max3(CF_F(6), CF_F(7), CF_F(8));
+    const float d = cf_max3(CF_F(9), CF_F(10), CF_F(11)), e = cf_max3(CF_F(12), CF_F(13), CF_F(14));
+    return fmaxf(cf_max3(a, b, c), cf_max3(d, e, CF_F(15)));
+#undef CF_F
+}
+// 16 scores -> 16 bits, bit (15 - j) = (v[j] < thr): sign of the (exact, Sterbenz) difference, shifted in by a funnel
+// shift -- FADD on the fma pipe, SHF on the alu pipe, two chains for ILP
+__device__ __forceinline__ uint32_t cf_lt16(const uint32_t (&v)[16], float thr) {
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a = __funnelshift_l(__float_as_uint(__uint_as_float(v[j]) - thr), a, 1);
+        b = __funnelshift_l(__float_as_uint(__uint_as_float(v[8 + j]) - thr), b, 1);
+    }
+    return ((a & 0xffu) << 8) | (b & 0xffu);
+}
+
+// ---- producer: the 256-user operand of the current pair, then its run of item slabs ----------------------------
+__device__ __forceinline__ void cf_producer(const CfParams& p, const CfSmem& L, uint32_t sbase, int64_t u0, int64_t u1) {
+    const uint32_t bar = sbase + L.bars;
+    const uint32_t a_bytes = 2 * CF_TILE * p.KP * 4;
+    const int kchunks = p.KP / CF_KC;
+    int64_t cur_pair = -1;
+    uint32_t a_cnt = 0, s = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+        const int64_t pair = u / p.n_it;
+        const int it = (int)(u % p.n_it);
+        if (pair != cur_pair) {
+            if (a_cnt > 0) mbar_wait(bar + CB_AFREE * 8, (a_cnt - 1) & 1);   // every MMA that reads the old operand is done
+            mbar_expect_tx(bar + CB_AFULL * 8, a_bytes);
+            const char* src = (const char*)(p.Upk + pair * (int64_t)(2 * CF_TILE) * p.KP);
+            for (uint32_t o = 0; o < a_bytes; o += 16384) bulk_g2s(sbase + L.a + o, src + o, 16384, bar + CB_AFULL * 8);
+            ++a_cnt;
+            cur_pair = pair;
+        }
+        for (int kc = 0; kc < kchunks; ++kc, ++s) {
+            const uint32_t slot = s % L.stages, use = s / L.stages;
+            mbar_wait(bar + (CB_EMPTY + slot) * 8, (use & 1) ^ 1);
+            mbar_expect_tx(bar + (CB_FULL + slot) * 8, CF_SLAB);
+            const float* src = p.Ipk + ((int64_t)it * (p.KP / 4) + kc * (CF_KC / 4)) * (CF_TILE / 8) * 32;
+            bulk_g2s(sbase + L.slab0 + slot * CF_SLAB, src, CF_SLAB, bar + (CB_FULL + slot) * 8);
+        }
+    }
+}
+
+// ---- MMA issuer: one thread, M128 N128 K8, two user halves per item slab ------------------------------------------
+__device__ __forceinline__ void cf_mma(const CfParams& p, const CfSmem& L, uint32_t sbase, uint32_t tmem_base, int64_t u0, int64_t u1) {
+    const uint32_t bar = sbase + L.bars;
+    constexpr uint32_t LBO = (CF_TILE / 8) * 128, SBO = 128;         // both operands: tiles of 128 rows
+    const uint32_t idesc = idesc_tf32(CF_TILE, CF_TILE);
+    const int kchunks = p.KP / CF_KC;
+    const uint32_t half_bytes = CF_TILE * p.KP * 4;
+    int64_t cur_pair = -1;
+    uint32_t a_cnt = 0, s = 0;
+    int halves = 2;
+    for (int64_t u = u0, t = 0; u < u1; ++u, ++t) {
+        const int64_t pair = u / p.n_it;
+        const uint32_t buf = (uint32_t)t & 1;
+        mbar_wait(bar + (CB_TEMPTY + buf) * 8, (((uint32_t)t >> 1) & 1) ^ 1);     // accumulators drained by the epilogue
+        if (pair != cur_pair) {
+            mbar_wait(bar + CB_AFULL * 8, a_cnt & 1);
+            ++a_cnt;
+            cur_pair = pair;
+            halves = (pair * 2 * CF_TILE + CF_TILE < p.B) ? 2 : 1;
+        }
+        fence_after_sync();
+        for (int kc = 0; kc < kchunks; ++kc, ++s) {
+            const uint32_t slot = s % L.stages, use = s / L.stages;
+            mbar_wait(bar + (CB_FULL + slot) * 8, use & 1);
+            fence_after_sync();
+            const uint32_t b_base = sbase + L.slab0 + slot * CF_SLAB;
+#pragma unroll
+            for (int j = 0; j < CF_KC / 8; ++j) {
+                const uint64_t bd = smem_desc(b_base + j * 2 * LBO, LBO, SBO);
+                const uint32_t a_off = (kc * (CF_KC / 4) + 2 * j) * LBO;
+                const uint32_t acc = (kc | j) ? 1u : 0u;
+                mma_tf32(tmem_base + (buf * 2 + 0) * CF_TILE, smem_desc(sbase + L.a + a_off, LBO, SBO), bd, idesc, acc);
+                if (halves == 2)
+                    mma_tf32(tmem_base + (buf * 2 + 1) * CF_TILE, smem_desc(sbase + L.a + half_bytes + a_off, LBO, SBO), bd, idesc, acc);
+            }
+            mma_commit(bar + (CB_EMPTY + slot) * 8);                  // slab consumed -> slot back to the producer
+        }
+        mma_commit(bar + (CB_TFULL + buf) * 8);                       // accumulators complete -> epilogue
+        if (u + 1 == u1 || (u + 1) / p.n_it != pair) mma_commit(bar + CB_AFREE * 8);
+    }
+}
+
+// ---- epilogue: thread = one user row, 128 accumulator columns per unit in 8 chunks of 16, loads one chunk ahead --------
+template <int PASS, int GPT>
+__device__ __forceinline__ void cf_epilogue(const CfParams& p, const CfSmem& L, uint32_t sbase, uint32_t tmem_base, int u0, int u1,
+                                            int e, int lane) {
+    const uint32_t bar = sbase + L.bars;
+    const int q = e & 3, h = (e >> 2) & 1, par = e >> 3;
+    constexpr int gpt = GPT;                                          // groups per item tile (pass 1): 8 / gw
+    int cur_pair = -1;
+    int64_t row = 0;
+    bool live = false;
+    float thr = INFINITY;
+    for (int u = u0 + par, t = par; u < u1; u += 2, t += 2) {
+        const int pair = u / p.n_it;
+        const int it = u - pair * p.n_it;
+        if (pair != cur_pair) {
+            cur_pair = pair;
+            row = (int64_t)pair * (2 * CF_TILE) + h * CF_TILE + q * 32 + lane;
+            live = row < p.B;
+            if (PASS == 2) thr = live ? __ldg(p.thr + row) : INFINITY;
+        }
+        mbar_wait(bar + (CB_TFULL + par) * 8, ((uint32_t)t >> 1) & 1);
+        fence_after_sync();
+        // (a whole half beyond the batch: nothing to read, but the buffer still has to be released)
+        if ((int64_t)pair * (2 * CF_TILE) + h * CF_TILE < p.B) {
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (par * 2 + h) * CF_TILE;
+            const int n_valid = (int)(p.n_items - (int64_t)it * CF_TILE);      // < 128 on the last tile only
+            uint32_t va[16], vb[16];
+            float gm[8];
+            uint32_t w[4];
+            cf_tmem_ld16(t0, va);
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                cf_tmem_wait16(va);
+                cf_tmem_ld16(t0 + (c + 1) * 16, vb);
+                if (n_valid < CF_TILE) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c * 16 + j >= n_valid) va[j] = 0xff800000u;          // -inf: never a maximum, never a hit
+                }
+                if (PASS == 1) gm[c] = cf_max16(va);
+                const uint32_t lt0 = PASS == 2 ? cf_lt16(va, thr) : 0u;
+                cf_tmem_wait16(vb);
+                if (c + 2 < 8) cf_tmem_ld16(t0 + (c + 2) * 16, va);
+                if (n_valid < CF_TILE) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if ((c + 1) * 16 + j >= n_valid) vb[j] = 0xff800000u;
+                }
+                if (PASS == 1) {
+                    gm[c + 1] = cf_max16(vb);
+                    if (gpt <= 4) gm[c] = fmaxf(gm[c], gm[c + 1]);    // groups of 32 items and wider: fold as we go
+                    if (gpt == 8 && (c & 2) && live)                  // groups of 16: four maxima are a 16-byte store
+                        reinterpret_cast<float4*>(p.gmax + row * p.G + (int64_t)it * 8)[c >> 2] = make_float4(gm[c - 2], gm[c - 1], gm[c], gm[c + 1]);
+                }
+                if (PASS == 2) w[c >> 1] = ~((lt0 << 16) | cf_lt16(vb, thr));   // bit (31 - j) of word (c / 2): column 32 (c / 2) + j passes
+            }
+            if (live) {
+                if (PASS == 1) {
+                    float* dst = p.gmax + row * p.G + (int64_t)it * gpt;
+                    if (gpt == 8) {
+                        // (stored inside the loop)
+                    } else if (gpt == 4) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(gm[0], gm[2], gm[4], gm[6]);
+                    } else if (gpt == 2) {
+                        *reinterpret_cast<float2*>(dst) = make_float2(fmaxf(gm[0], gm[2]), fmaxf(gm[4], gm[6]));
+                    } else {
+                        *dst = fmaxf(fmaxf(gm[0], gm[2]), fmaxf(gm[4], gm[6]));
+                    }
+                } else {
+                    p.bitmap[row * p.n_it + it] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar + (CB_TEMPTY + par) * 8);
+    }
+}
+
+template <int PASS, int GPT>
+__global__ void __launch_bounds__(CF_THREADS, 1) cf_pass_kernel(const CfParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const CfSmem L = cf_smem(p.KP);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar = sbase + L.bars;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CB_TEMPTY; ++i) mbar_init(bar + i * 8, 1);
+        mbar_init(bar + CB_TEMPTY * 8, 8); mbar_init(bar + (CB_TEMPTY + 1) * 8, 8);   // 2 halves x 4 lane quarters release a buffer pair
+        mbar_fence_init();
+    }
+    if (warp == 1) { tmem_alloc(sbase + L.tmem_ptr, 512); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.tmem_ptr);
+    // contiguous run of units for this CTA
+    const int64_t u0 = (int64_t)blockIdx.x * p.n_units / gridDim.x;
+    const int64_t u1 = (int64_t)(blockIdx.x + 1) * p.n_units / gridDim.x;
+    if (warp == 0) {
+        if (lane == 0) cf_producer(p, L, sbase, u0, u1);
+    } else if (warp == 1) {
+        if (lane == 0) cf_mma(p, L, sbase, tmem_base, u0, u1);
+    } else {
+        cf_epilogue<PASS, GPT>(p, L, sbase, tmem_base, (int)u0, (int)u1, warp - 2, lane);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// operand packing
+// ------------------------------------------------------------------------------------------------------------------
+// One thread per (padded row, k block of 4): round to tf32, store into the tile layout; the KP/4 threads of a row are
+// consecutive lanes and reduce the row's squared norm with shuffles.
+__device__ __forceinline__ void cf_pack_one(int64_t t, int64_t n_rows, const int64_t* __restrict__ idx, const float* __restrict__ E, int64_t ld,
+                                            int d, int KP, float* __restrict__ out, float* __restrict__ row_norm, uint32_t* __restrict__ max_norm) {
+    const int kblks = KP / 4;
+    const int64_t row = t / kblks;
+    const int kb = (int)(t % kblks);
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < n_rows) {
+        const float* src = E + (idx ? idx[row] : row) * ld;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (kb * 4 + e < d) x[e] = __ldg(src + kb * 4 + e);
+    }
+    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+    for (int o = kblks / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    uint32_t r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[e]) : "f"(x[e]));
+    const int64_t tile = row / CF_TILE;
+    const int rr = (int)(row % CF_TILE);
+    const int64_t off = ((tile * kblks + kb) * (CF_TILE / 8) + rr / 8) * 32 + (rr % 8) * 4;
+    *reinterpret_cast<uint4*>(out + off) = make_uint4(r[0], r[1], r[2], r[3]);
+    if (kb == 0 && row < n_rows) {
+        const float nrm = sqrtf(ss) * (1.0f + 1e-6f);                 // (rounded up: the bound must hold)
+        if (row_norm) row_norm[row] = nrm;
+        if (max_norm) atomicMax(max_norm, __float_as_uint(nrm));      // non-negative floats order like their bit patterns
+    }
+}
+
+// header word 0 (the running maximum norm) is zeroed by a memset node before the launch; thread 0 fills in the rest
+__global__ void __launch_bounds__(256) cf_pack_items_kernel(int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int d, int KP,
+                                                            float* __restrict__ Ipk, uint32_t* __restrict__ header, int64_t n_threads) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;                                       // (n_threads is a multiple of 32: whole warps leave together)
+    if (t == 0) { header[1] = (uint32_t)n_items; header[2] = (uint32_t)d; header[3] = (uint32_t)KP; }
+    cf_pack_one(t, n_items, nullptr, Ie, ldi, d, KP, Ipk, nullptr, header);
+}
+
+// ---- mask CSR over batch rows -------------------------------------------------------------------------------------
+// The reference's evaluation loader emits the mask row-major (batch row ascending: src/utils/dataloader.py:370-391 builds
+// it user by user), so the common case is a sorted row array: the row pointers are the positions where the row
+// changes, checked as we go, one fully parallel pass.  If any block saw a descent, mask_csr_small_kernel (one CTA:
+// count in shared memory, scan, fill) redoes the job for arbitrary order; otherwise it exits at once.
+__device__ __forceinline__ void cf_mask_sorted_block(int64_t blk, int64_t nnz, const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
+                                                     int B, int64_t item_offset, int32_t* __restrict__ ptr, int32_t* __restrict__ items,
+                                                     int32_t* __restrict__ unsorted) {
+    const int64_t j = blk * (int64_t)blockDim.x + threadIdx.x;        // entry j, plus one sentinel thread j == nnz
+    int bad = 0;
+    if (j <= nnz) {
+        const int64_t rj = j < nnz ? rows[j] : (int64_t)B;
+        const int64_t rp = j > 0 ? rows[j - 1] : -1;
+        bad = j < nnz && rp > rj;
+        if (j < nnz) items[j] = (int32_t)(cols[j] - item_offset);
+        // rows (rp, rj] start at entry j (rows outside [0, B) own no pointer; clamped so that they delimit correctly)
+        const int64_t lo = rp < -1 ? -1 : (rp > B ? B : rp), hi = rj < -1 ? -1 : (rj > B ? B : rj);
+        for (int64_t r = lo + 1; r <= hi; ++r) ptr[r] = (int32_t)j;
+    }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0) unsorted[blk] = bad;
+}
+
+constexpr int MC_MAX_ROWS = 8192;
+constexpr int MC_THREADS = 1024;
+__global__ void __launch_bounds__(MC_THREADS) mask_csr_small_kernel(int64_t nnz, const int64_t* __restrict__ rows,
+                                                                    const int64_t* __restrict__ cols, int B, int64_t item_offset,
+                                                                    int32_t* __restrict__ ptr, int32_t* __restrict__ items,
+                                                                    const int32_t* __restrict__ unsorted, int n_unsorted) {
+    extern __shared__ int32_t mc_sm[];                               // count / cursor [B + 1] | warp totals [32]
+    {   // runs only when the sorted pass found the rows out of order (it then left garbage behind)
+        int any = 0;
+        for (int i = threadIdx.x; i < n_unsorted; i += MC_THREADS) any |= unsorted[i];
+        if (!__syncthreads_or(any)) return;
+    }
+    int32_t* cnt = mc_sm;
+    int32_t* wtot = mc_sm + B + 1;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int r = tid; r <= B; r += MC_THREADS) cnt[r] = 0;
+    __syncthreads();
+    constexpr int MC_U = 8;                                          // loads in flight per thread (the loop is latency-bound)
+    for (int64_t jb = 0; jb < nnz; jb += (int64_t)MC_U * MC_THREADS) {        // warp-uniform trip count (match / shfl below)
+        const int64_t j0 = jb + tid;
+        int64_t r[MC_U];
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            const int64_t j = j0 + (int64_t)u * MC_THREADS;
+            r[u] = j < nnz ? __ldg(rows + j) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            // one atomic per distinct row of the warp (same-address shared atomics serialise a full round trip each)
+            const int rr = (r[u] >= 0 && r[u] < B) ? (int)r[u] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, rr);
+            if (rr >= 0 && lane == __ffs(peers) - 1) atomicAdd(cnt + rr, __popc(peers));
+        }
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..B]: each thread owns a contiguous run of rows
+    const int per = (B + 1 + MC_THREADS - 1) / MC_THREADS;
+    const int r0 = tid * per, r1 = min(B + 1, r0 + per);
+    int local = 0;
+    for (int r = r0; r < r1; ++r) local += cnt[r];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int v = wtot[lane], sc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, sc, o);
+            if (lane >= o) sc += u;
+        }
+        wtot[lane] = sc - v;                                         // exclusive warp offsets
+    }
+    __syncthreads();
+    int run = wtot[wid] + incl - local;
+    for (int r = r0; r < r1; ++r) {
+        const int c = cnt[r];
+        ptr[r] = run;
+        cnt[r] = run;                                                // becomes the fill cursor
+        run += c;
+    }
+    __syncthreads();
+    for (int64_t jb = 0; jb < nnz; jb += (int64_t)MC_U * MC_THREADS) {
+        const int64_t j0 = jb + tid;
+        int64_t r[MC_U], c[MC_U];
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            const int64_t j = j0 + (int64_t)u * MC_THREADS;
+            r[u] = j < nnz ? __ldg(rows + j) : -1;
+            c[u] = j < nnz ? __ldg(cols + j) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < MC_U; ++u) {
+            const int rr = (r[u] >= 0 && r[u] < B) ? (int)r[u] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, rr);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (rr >= 0 && lane == leader) base = atomicAdd(cnt + rr, __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (rr >= 0) items[base + __popc(peers & ((1u << lane) - 1u))] = (int32_t)(c[u] - item_offset);   // order inside a row is free
+        }
+    }
+}
+// large batches / masks: global count, library scan, fill
+__global__ void mask_count_kernel(int64_t nnz, const int64_t* __restrict__ rows, int64_t B, int32_t* __restrict__ counts) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < nnz && rows[j] >= 0 && rows[j] < B) atomicAdd(counts + rows[j], 1);
+}
+__global__ void mask_fill_kernel(int64_t nnz, const int64_t* __restrict__ rows, const int64_t* __restrict__ cols, int64_t B,
+                                 int64_t item_offset, const int32_t* __restrict__ ptr, int32_t* __restrict__ cursor,
+                                 int32_t* __restrict__ items) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= nnz || rows[j] < 0 || rows[j] >= B) return;
+    const int pos = ptr[rows[j]] + atomicAdd(cursor + rows[j], 1);
+    items[pos] = (int32_t)(cols[j] - item_offset);     // may fall outside [0, n_items): then it never matches
+}
+
+// One launch per row block for everything the passes need prepared: the sorted-mask CSR (first call only), the user
+// operand + row norms, and the zeroing of the flags / slot counter.
+__global__ void __launch_bounds__(256) cf_prep_kernel(int64_t mask_blocks, int64_t mask_nnz, const int64_t* __restrict__ mask_rows,
+                                                      const int64_t* __restrict__ mask_cols, int B_all, int64_t item_offset,
+                                                      int32_t* __restrict__ mptr, int32_t* __restrict__ mitems, int32_t* __restrict__ unsorted,
+                                                      int64_t nb, const int64_t* __restrict__ users, const float* __restrict__ Ue, int64_t ldu,
+                                                      int d, int KP, float* __restrict__ Upk, float* __restrict__ unorm, int64_t pack_threads,
+                                                      uint32_t* __restrict__ zero, int64_t zero_words) {
+    if ((int64_t)blockIdx.x < mask_blocks) {
+        cf_mask_sorted_block(blockIdx.x, mask_nnz, mask_rows, mask_cols, B_all, item_offset, mptr, mitems, unsorted);
+        return;
+    }
+    int64_t t = (blockIdx.x - mask_blocks) * (int64_t)blockDim.x + threadIdx.x;
+    if (t < pack_threads) { cf_pack_one(t, nb, users, Ue, ldu, d, KP, Upk, unorm, nullptr); return; }   // (multiple of 256: whole blocks)
+    t -= pack_threads;
+    if (t < zero_words) zero[t] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// threshold: the need-th largest group maximum of the row, minus the certified margin.  One warp per row.
+// ------------------------------------------------------------------------------------------------------------------
+// Warp radix select over 32-bit keys read through `key_at(t)`, t < n: returns the key of the `need`-th largest.
+template <typename F>
+__device__ __forceinline__ uint32_t cf_warp_kth(F key_at, int n, int need, uint32_t* hist, int lane) {
+    uint32_t prefix = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int b = lane; b < 256; b += 32) hist[b] = 0;
+        __syncwarp();
+        for (int t = lane; t < n; t += 32) {
+            const uint32_t key = key_at(t);
+            if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        // lane l owns bins [8l, 8l+8); `cum` = keys in the bins above (exclusive suffix sum)
+        uint32_t mine[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { mine[j] = hist[lane * 8 + j]; tot += mine[j]; }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += v;
+        }
+        uint32_t cum = incl - tot;
+        int dgt = -1;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            if (dgt < 0) {
+                if (cum + mine[j] >= (uint32_t)need) dgt = lane * 8 + j;
+                else cum += mine[j];
+            }
+        }
+        const unsigned found = __ballot_sync(0xffffffffu, dgt >= 0);   // (never empty: need <= n)
+        const int win = found ? 31 - __clz(found) : 0;
+        dgt = __shfl_sync(0xffffffffu, dgt, win);
+        cum = __shfl_sync(0xffffffffu, cum, win);
+        if (dgt < 0) dgt = 0;
+        prefix |= (uint32_t)dgt << shift;
+        need -= (int)cum;
+        __syncwarp();
+    }
+    return prefix;
+}
+
+__global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int k, const float* __restrict__ gmax, const float* __restrict__ unorm,
+                                                     const uint32_t* __restrict__ max_norm, const int32_t* __restrict__ mask_ptr,
+                                                     float* __restrict__ thr, int32_t* __restrict__ flags) {
+    __shared__ uint32_t hist_all[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+    if (row >= nb) return;
+    const int need = k + (mask_ptr ? mask_ptr[row + 1] - mask_ptr[row] : 0);
+    if (need > G) {                                                  // more finalists wanted than there are groups: exact kernel
+        if (lane == 0) { thr[row] = INFINITY; flags[row] = 1; }
+        return;
+    }
+    const float* g = gmax + row * G;
+    const uint32_t kth = cf_warp_kth([&](int t) { return float_key(__ldg(g + t)); }, G, need, hist_all[warp], lane);
+    if (lane == 0) {
+        const float t = key_float(kth);
+        const float margin = 2.0f * CF_EPS * unorm[row] * __uint_as_float(*max_norm);
+        const float out = t - margin;
+        if (!(fabsf(t) < INFINITY) || !(margin < INFINITY)) { thr[row] = INFINITY; flags[row] = 2; }   // NaN / inf scores
+        else thr[row] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exact fp32 score of one (user, item) pair.  THE arithmetic of this file's results: 32 partial sums (element c goes to
+// partial c % 32, fmaf in ascending c), then the pairwise tree 16, 8, 4, 2, 1 -- what a warp computes with one lane
+// per partial and an xor butterfly (cf_exact_kernel), here by one thread.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, const float* __restrict__ v, int d, bool vec_ok) {
+    float part[32];
+#pragma unroll
+    for (int L = 0; L < 32; ++L) part[L] = 0.f;
+    if (vec_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                // d <= 128
+            if (q * 32 < d) {
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const int c = q * 32 + i4 * 4;
+                    if (c < d) {                                     // d % 4 == 0 on this path
+                        const float4 x = ldg4(v + c);
+                        const float4 uu = *reinterpret_cast<const float4*>(u_sm + c);
+                        part[i4 * 4 + 0] = fmaf(uu.x, x.x, part[i4 * 4 + 0]);
+                        part[i4 * 4 + 1] = fmaf(uu.y, x.y, part[i4 * 4 + 1]);
+                        part[i4 * 4 + 2] = fmaf(uu.z, x.z, part[i4 * 4 + 2]);
+                        part[i4 * 4 + 3] = fmaf(uu.w, x.w, part[i4 * 4 + 3]);
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int L = 0; L < 32; ++L) {
+                const int c = q * 32 + L;
+                if (c < d) part[L] = fmaf(u_sm[c], __ldg(v + c), part[L]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int L = 0; L < 32; ++L)
+            if (L < o) part[L] = part[L] + part[L + o];
+    }
+    return part[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// finalists: set bits of the row's bitmap -> unmasked -> exact fp32 -> top-k in contract order.  One warp per row.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
+                                                       const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
+                                                       const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
+                                                       const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
+                                                       int32_t* __restrict__ flags, int32_t* __restrict__ counter, int32_t* __restrict__ row_of_slot,
+                                                       int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    __shared__ uint64_t fin_all[4][CF_CAP];
+    __shared__ __align__(16) float u_all[4][128];
+    __shared__ uint32_t hist_all[4][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 4 + warp;
+    if (row >= nb) return;
+    auto condemn = [&](int why) {                                    // the exact kernel takes the row
+        if (lane == 0) {
+            if (why) flags[row] = why;
+            row_of_slot[atomicAdd(counter, 1)] = (int32_t)row;
+        }
+    };
+    if (flags[row]) { condemn(0); return; }
+    uint64_t* fin = fin_all[warp];
+    float* u_sm = u_all[warp];
+    const float* u = Ue + (users ? users[row] : row) * ldu;
+    for (int c = lane; c < 128; c += 32) u_sm[c] = c < d ? __ldg(u + c) : 0.f;
+    const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
+    // 1. the set bits, in ascending item order per lane; positions from a running warp prefix
+    const uint4* bm = bitmap + row * n_it;
+    int n = 0;
+    bool over = false;
+    for (int w0 = 0; w0 < n_it; w0 += 32) {
+        const int wi = w0 + lane;
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        if (wi < n_it) b = __ldg(bm + wi);
+        const int mine = __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int pos = n + incl - mine;
+        n += __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t ws[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t x = ws[q];
+            while (x) {
+                const int j = __clz(x);                              // bit (31 - j) <-> column 32 q + j of the tile
+                x &= ~(0x80000000u >> j);
+                if (pos < CF_CAP) fin[pos] = (uint32_t)(wi * CF_TILE + q * 32 + j);
+                else over = true;
+                ++pos;
+            }
+        }
+    }
+    over = __any_sync(0xffffffffu, over);
+    if (over) { condemn(4); return; }
+    __syncwarp();
+    // 2. masked train positives out, exact fp32 score in
+    const bool vec_ok = (ldi & 3) == 0 && (d & 3) == 0 && ((((uintptr_t)Ie) & 15) == 0);
+    int kept = 0;
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        uint64_t comp = 0;                                           // 0 sorts last: a dropped candidate
+        if (t < n) {
+            const int item = (int)(uint32_t)fin[t];
+            bool keep = item < n_items;
+            for (int qd = m0; qd < m1; ++qd) keep &= (__ldg(mask_items + qd) != item);
+            if (keep) {
+                const float s = cf_dot_thread(u_sm, Ie + (int64_t)item * ldi, d, vec_ok);
+                comp = ((uint64_t)float_key(s) << 32) | (uint32_t)(~(uint32_t)item);
+            }
+        }
+        kept += __popc(__ballot_sync(0xffffffffu, comp != 0));
+        __syncwarp();
+        if (t < n) fin[t] = comp;
+    }
+    __syncwarp();
+    if (kept < k) { condemn(8); return; }                            // (cannot happen for finite scores: the threshold is certified)
+    // 3. rank.  Few finalists (the usual case): all against all.  Many: first the k-th largest value key by a warp radix
+    //    select, then only the composites at or above it (k plus ties on the value).
+    int m = n;
+    if (n > 96) {
+        const uint32_t kth = cf_warp_kth([&](int t) { return (uint32_t)(fin[t] >> 32); }, n, k, hist_all[warp], lane);
+        m = 0;
+        for (int t0 = 0; t0 < n; t0 += 32) {
+            const int t = t0 + lane;
+            const uint64_t c = t < n ? fin[t] : 0;
+            const bool keep = t < n && c != 0 && (uint32_t)(c >> 32) >= kth;
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) fin[m + __popc(bal & ((1u << lane) - 1u))] = c;     // in place: writes never pass the reads
+            m += __popc(bal);
+            __syncwarp();
+        }
+    }
+    // composites are unique (item index in the low word): rank = number of larger composites = output position
+    for (int t = lane; t < m; t += 32) {
+        const uint64_t me = fin[t];
+        if (me == 0) continue;
+        int rank = 0;
+        for (int u2 = 0; u2 < m; ++u2) rank += fin[u2] > me;
+        if (rank < k) {
+            out_idx[row * k + rank] = (int64_t)(uint32_t)(~(uint32_t)me) + item_offset;
+            out_val[row * k + rank] = key_float((uint32_t)(me >> 32));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// exact fp32 rows (flagged only): all items on CUDA cores, mask, radix select, ordered ties, sort -- the contract of
+// mmrec_topk_rows_f32.  CTA `sl` serves the flagged rows sl, sl + CF_EX_SLOTS, ... with its own key buffer; all CTAs
+// exit at once when nothing was flagged.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ void cf_bitonic_desc(uint64_t* a, int n) {
+    for (int size = 2; size <= n; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+                int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t x = a[lo], y = a[hi];
+                if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+            }
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) cf_exact_kernel(const int64_t* __restrict__ users, const float* __restrict__ Ue, int64_t ldu,
+                                                       int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int d, int k,
+                                                       int64_t item_offset, const int32_t* __restrict__ mask_ptr,
+                                                       const int32_t* __restrict__ mask_items, const int32_t* __restrict__ counter,
+                                                       const int32_t* __restrict__ row_of_slot, unsigned* __restrict__ keys_all,
+                                                       int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    __shared__ unsigned hist[256];
+    __shared__ uint64_t sel[1024];
+    __shared__ unsigned tie_idx[1024];
+    __shared__ unsigned s_prefix, s_need, s_count, s_base, n_ties;
+    __shared__ unsigned warp_tot[8];
+    const int n_flagged = *counter;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned* keys = keys_all + (int64_t)blockIdx.x * n_items;
+    for (int fr = blockIdx.x; fr < n_flagged; fr += gridDim.x) {
+        const int64_t row = row_of_slot[fr];
+        __syncthreads();
+        // ---- keys: one warp per item, lane L sums the elements L, L + 32, ... (fmaf), xor butterfly: cf_dot_thread's bits
+        const float* u = Ue + (users ? users[row] : row) * ldu;
+        float ur[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ur[i] = (lane + 32 * i < d) ? u[lane + 32 * i] : 0.f;
+        for (int64_t i0 = wid; i0 < n_items; i0 += 32) {             // 4 items in flight per warp
+            float acc[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * 8;
+                acc[e] = 0.f;
+                if (i < n_items) {
+                    const float* v = Ie + i * ldi;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (lane + 32 * q < d) acc[e] = fmaf(ur[q], __ldg(v + lane + 32 * q), acc[e]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t i = i0 + e * 8;
+                const float r = warp_sum(acc[e]);
+                if (lane == 0 && i < n_items) keys[i] = float_key(r);
+            }
+        }
+        __syncthreads();
+        const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
+        for (int q = m0 + tid; q < m1; q += 256) {
+            const int64_t item = mask_items[q];
+            if (item >= 0 && item < n_items) keys[item] = float_key(-1e10f);          // src/common/trainer.py:307
+        }
+        __syncthreads();
+        // ---- radix select of the k-th largest key
+        unsigned prefix = 0, need = (unsigned)k;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            const unsigned hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            hist[tid] = 0;
+            __syncthreads();
+            for (int64_t i = tid; i < n_items; i += 256) {
+                const unsigned key = keys[i];
+                if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned cum = 0;
+                int dgt = 255;
+                for (; dgt > 0; --dgt) {
+                    if (cum + hist[dgt] >= need) break;
+                    cum += hist[dgt];
+                }
+                s_prefix = prefix | ((unsigned)dgt << shift);
+                s_need = need - cum;
+            }
+            __syncthreads();
+            prefix = s_prefix; need = s_need;
+            __syncthreads();
+        }
+        const unsigned kth = prefix;
+        if (tid == 0) { s_count = 0; s_base = 0; n_ties = 0; }
+        __syncthreads();
+        const unsigned n_gt = (unsigned)k - need;
+        // strictly greater keys in any order; the indices of the keys equal to the k-th are collected and the `need` lowest
+        // of them taken (normally there is exactly one)
+        for (int64_t i = tid; i < n_items; i += 256) {
+            const unsigned key = keys[i];
+            if (key > kth) { unsigned pos = atomicAdd(&s_count, 1u); sel[pos] = ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)i); }
+            else if (key == kth) { unsigned pos = atomicAdd(&n_ties, 1u); if (pos < 1024u) tie_idx[pos] = (unsigned)i; }
+        }
+        __syncthreads();
+        if (n_ties <= 1024u) {
+            const unsigned nt = n_ties;
+            for (unsigned t = tid; t < nt; t += 256) {
+                const unsigned me = tie_idx[t];
+                unsigned rank = 0;
+                for (unsigned u2 = 0; u2 < nt; ++u2) rank += tie_idx[u2] < me;
+                if (rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~me);
+            }
+        } else {
+            // degenerate row (thousands of equal scores): ordered sweep, 256 items at a time
+            for (int64_t i0 = 0; i0 < n_items; i0 += 256) {
+                const int64_t i = i0 + tid;
+                const bool eq = i < n_items && keys[i] == kth;
+                const unsigned bal = __ballot_sync(0xffffffffu, eq);
+                if (lane == 0) warp_tot[wid] = __popc(bal);
+                __syncthreads();
+                unsigned off = s_base;
+                for (int w = 0; w < wid; ++w) off += warp_tot[w];
+                const unsigned rank = off + __popc(bal & ((1u << lane) - 1u));
+                if (eq && rank < need) sel[n_gt + rank] = ((uint64_t)kth << 32) | (uint32_t)(~(uint32_t)i);
+                __syncthreads();
+                if (tid == 0) { unsigned tot = 0; for (int w = 0; w < 8; ++w) tot += warp_tot[w]; s_base += tot; }
+                __syncthreads();
+                if (s_base >= need) break;
+            }
+        }
+        __syncthreads();
+        int n2 = 1;
+        while (n2 < k) n2 <<= 1;
+        for (int t = k + tid; t < n2; t += 256) sel[t] = 0;
+        cf_bitonic_desc(sel, n2);
+        for (int t = tid; t < k; t += 256) {
+            const uint64_t c = sel[t];
+            out_idx[row * k + t] = (int64_t)(uint32_t)(~(uint32_t)c) + item_offset;
+            out_val[row * k + t] = key_float((uint32_t)(c >> 32));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static inline int cf_kp(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
+static inline int cf_gw(int64_t n_items) { return n_items <= 16384 ? 1 : (n_items <= 32768 ? 2 : (n_items <= 65536 ? 4 : 8)); }
+
+constexpr size_t CF_CAT_HEADER = 1024;          // {max item norm (fp32 bits), n_items, d, KP} + padding
+
+size_t cf_catalog_bytes(int64_t n_items, int d) {
+    if (n_items <= 0 || d < 1 || d > 128) return 0;
+    const int64_t n_it = (n_items + CF_TILE - 1) / CF_TILE;
+    return CF_CAT_HEADER + (size_t)n_it * CF_TILE * cf_kp(d) * 4;
+}
+
+int cf_catalog_pack(int64_t n_items, const float* Ie, int64_t ldi, int d, void* cat, size_t cat_bytes, cudaStream_t stream) {
+    const size_t need = cf_catalog_bytes(n_items, d);
+    if (!need || !cat || cat_bytes < need || (((uintptr_t)cat) & 1023)) { set_error("catalog_pack: bad shape, or buffer null / not 1024-byte aligned / smaller than mmrec_catalog_bytes"); return MMREC_EINVAL; }
+    const int KP = cf_kp(d);
+    const int64_t n_it = (n_items + CF_TILE - 1) / CF_TILE;
+    MMREC_CUDA(cudaMemsetAsync(cat, 0, CF_CAT_HEADER, stream));
+    const int64_t threads = n_it * CF_TILE * (KP / 4);
+    cf_pack_items_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n_items, Ie, ldi, d, KP, (float*)((char*)cat + CF_CAT_HEADER),
+                                                                                  (uint32_t*)cat, threads);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}
+
+struct CfPlan {
+    int KP, gw, G;
+    int64_t n_it, rows_blk, rows_pad, n_pairs;
+    size_t off_cat, off_upk, off_unorm, off_gmax, off_thr, off_bitmap, off_flags, off_mptr, off_mcur, off_mitems, off_cub, off_keys, cub_bytes, total;
+};
+
+static CfPlan cf_plan(int64_t B, int64_t n_items, int d, int64_t mask_nnz, bool with_cat) {
+    CfPlan P;
+    P.KP = cf_kp(d);
+    P.gw = cf_gw(n_items);
+    P.n_it = (n_items + CF_TILE - 1) / CF_TILE;
+    P.G = (int)(P.n_it * (8 / P.gw));
+    // row block: group maxima + bitmap of a block stay below ~512 MB
+    const int64_t per_row = (int64_t)P.G * 4 + P.n_it * 16;
+    int64_t rb = (512ll << 20) / per_row / (2 * CF_TILE) * (2 * CF_TILE);
+    if (rb < 2 * CF_TILE) rb = 2 * CF_TILE;
+    if (rb > 65536) rb = 65536;
+    P.rows_blk = B < rb ? B : rb;
+    P.rows_pad = (P.rows_blk + 2 * CF_TILE - 1) / (2 * CF_TILE) * (2 * CF_TILE);
+    P.n_pairs = P.rows_pad / (2 * CF_TILE);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+    P.off_cat = take(with_cat ? cf_catalog_bytes(n_items, d) : 0);
+    P.off_upk = take((size_t)P.rows_pad * P.KP * 4);
+    P.off_unorm = take((size_t)P.rows_pad * 4);
+    P.off_gmax = take((size_t)P.rows_blk * P.G * 4);
+    P.off_thr = take((size_t)P.rows_pad * 4);
+    P.off_bitmap = take((size_t)P.rows_blk * P.n_it * 16);
+    P.off_flags = take((size_t)(2 * P.rows_blk + 2) * 4);            // flags [rows_blk] | counter | row_of_slot [rows_blk]   (flags + counter zeroed per block)
+    P.off_mptr = take((size_t)(B + 2) * 4);
+    P.off_mcur = take((size_t)(B + 2 > 1100 ? B + 2 : 1100) * 4);    // fill cursors, or the per-block order flags of the sorted-mask pass
+    P.off_mitems = take((size_t)(mask_nnz > 0 ? mask_nnz : 1) * 4);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int64_t)(B + 1));
+    P.cub_bytes = scan_bytes;
+    P.off_cub = take(scan_bytes);
+    P.off_keys = take((size_t)CF_EX_SLOTS * n_items * 4);
+    P.total = off + 1024;
+    return P;
+}
+
+bool score_cf_supported(int64_t B, int64_t n_items, int d, int k) {
+    if (!(B > 0 && d >= 1 && d <= 128 && k >= 1 && k <= 256 && n_items < (1ll << 31))) return false;
+    const int64_t G = (n_items + CF_TILE - 1) / CF_TILE * (8 / cf_gw(n_items));
+    return G >= 2 * (int64_t)k;                                      // enough groups for need = k + masked items (rows that want more go to the exact kernel)
+}
+
+size_t score_cf_workspace_bytes(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, bool with_cat) {
+    if (!score_cf_supported(B, n_items, d, k)) return 0;
+    return cf_plan(B, n_items, d, mask_nnz, with_cat).total;
+}
+
+static int cf_set_attrs() {
+    static bool done[64] = {false};
+    int dev = 0;
+    MMREC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {                        // the attribute is per device
+        MMREC_CUDA(cudaFuncSetAttribute(cf_pass_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(cf_pass_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(cf_pass_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(cf_pass_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(cf_pass_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MMREC_CUDA(cudaFuncSetAttribute(mask_csr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+    }
+    return MMREC_OK;
+}
+
+// returns 1 = done, 0 = unsupported shape / workspace (caller uses the unfused path), <0 error.  `cat` = a catalogue packed
+// by cf_catalog_pack for exactly (n_items, Ie, d), or NULL: then it is packed into the workspace first.
+int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie, int64_t ldi,
+             int d, const void* cat, int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int k, int64_t item_offset,
+             int64_t* out_idx, float* out_val, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!score_cf_supported(B, n_items, d, k) || !ws) return 0;
+    const CfPlan P = cf_plan(B, n_items, d, mask_nnz, cat == nullptr);
+    char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    if (ws_bytes < P.total + (size_t)(base - (char*)ws)) return 0;
+    { int rc = cf_set_attrs(); if (rc) return rc; }
+    if (!cat) {
+        int rc = cf_catalog_pack(n_items, Ie, ldi, d, base + P.off_cat, cf_catalog_bytes(n_items, d), stream);
+        if (rc) return rc;
+        cat = base + P.off_cat;
+    }
+    const uint32_t* max_norm = (const uint32_t*)cat;
+    const float* Ipk = (const float*)((const char*)cat + CF_CAT_HEADER);
+    float *Upk = (float*)(base + P.off_upk), *unorm = (float*)(base + P.off_unorm), *gmax = (float*)(base + P.off_gmax), *thr = (float*)(base + P.off_thr);
+    uint4* bitmap = (uint4*)(base + P.off_bitmap);
+    int32_t* flags = (int32_t*)(base + P.off_flags);
+    int32_t* counter = flags + P.rows_blk;
+    int32_t* row_of_slot = counter + 1;
+    int32_t *mptr = (int32_t*)(base + P.off_mptr), *mcur = (int32_t*)(base + P.off_mcur), *mitems = (int32_t*)(base + P.off_mitems);
+    unsigned* keys = (unsigned*)(base + P.off_keys);
+    const int T = 256;
+    const bool has_mask = mask_nnz > 0;
+    const bool small_mask = has_mask && B <= MC_MAX_ROWS && mask_nnz <= (1ll << 18);
+    if (has_mask && !small_mask) {
+        MMREC_CUDA(cudaMemsetAsync(mcur, 0, (size_t)(B + 2) * 4, stream));
+        mask_count_kernel<<<(unsigned)((mask_nnz + T - 1) / T), T, 0, stream>>>(mask_nnz, mask_rows, B, mcur);
+        MMREC_LAUNCH_CHECK();
+        size_t tmp = P.cub_bytes;
+        MMREC_CUDA(cub::DeviceScan::ExclusiveSum(base + P.off_cub, tmp, mcur, mptr, B + 1, stream));
+        MMREC_CUDA(cudaMemsetAsync(mcur, 0, (size_t)(B + 2) * 4, stream));
+        mask_fill_kernel<<<(unsigned)((mask_nnz + T - 1) / T), T, 0, stream>>>(mask_nnz, mask_rows, mask_cols, B, item_offset, mptr, mcur, mitems);
+        MMREC_LAUNCH_CHECK();
+    }
+    const CfSmem L = cf_smem(P.KP);
+    const int sms = sm_count();
+    for (int64_t r0 = 0; r0 < B; r0 += P.rows_blk) {
+        const int64_t nb = (B - r0) < P.rows_blk ? (B - r0) : P.rows_blk;
+        const int64_t nb_pad = (nb + 2 * CF_TILE - 1) / (2 * CF_TILE) * (2 * CF_TILE);
+        const int64_t n_pairs = nb_pad / (2 * CF_TILE);
+        const int64_t* ub = users ? users + r0 : nullptr;
+        const float* ue = users ? Ue : Ue + r0 * ldu;
+        const int32_t* mp = has_mask ? mptr + r0 : nullptr;
+        // prep: [mask CSR of the whole batch (first block, sorted case)] + user operand + zeroed flags / counter
+        const int64_t mask_blocks = (small_mask && r0 == 0) ? (mask_nnz + 1 + T - 1) / T : 0;      // <= 1025 words of mcur hold the order flags
+        const int64_t pack_threads = nb_pad * (P.KP / 4);
+        const int64_t zero_words = P.rows_blk + 1;
+        cf_prep_kernel<<<(unsigned)(mask_blocks + (pack_threads + zero_words + T - 1) / T), T, 0, stream>>>(
+            mask_blocks, mask_nnz, mask_rows, mask_cols, (int)B, item_offset, mptr, mitems, mcur, nb, ub, ue, ldu, d, P.KP, Upk, unorm,
+            pack_threads, (uint32_t*)flags, zero_words);
+        MMREC_LAUNCH_CHECK();
+        if (mask_blocks) {
+            mask_csr_small_kernel<<<1, MC_THREADS, (size_t)(B + 1 + 32) * 4, stream>>>(mask_nnz, mask_rows, mask_cols, (int)B, item_offset, mptr,
+                                                                                     mitems, mcur, (int)mask_blocks);
+            MMREC_LAUNCH_CHECK();
+        }
+        CfParams p;
+        p.Upk = Upk; p.Ipk = Ipk; p.KP = P.KP; p.n_it = (int)P.n_it; p.B = nb; p.n_items = n_items; p.n_units = n_pairs * P.n_it;
+        p.gmax = gmax; p.G = P.G; p.gw = P.gw; p.thr = thr; p.bitmap = bitmap;
+        const unsigned grid = (unsigned)(p.n_units < sms ? p.n_units : sms);
+        switch (P.gw) {
+            case 1: cf_pass_kernel<1, 8><<<grid, CF_THREADS, L.total, stream>>>(p); break;
+            case 2: cf_pass_kernel<1, 4><<<grid, CF_THREADS, L.total, stream>>>(p); break;
+            case 4: cf_pass_kernel<1, 2><<<grid, CF_THREADS, L.total, stream>>>(p); break;
+            default: cf_pass_kernel<1, 1><<<grid, CF_THREADS, L.total, stream>>>(p); break;
+        }
+        MMREC_LAUNCH_CHECK();
+        cf_thr_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, stream>>>(nb, P.G, k, gmax, unorm, max_norm, mp, thr, flags);
+        MMREC_LAUNCH_CHECK();
+        cf_pass_kernel<2, 8><<<grid, CF_THREADS, L.total, stream>>>(p);
+        MMREC_LAUNCH_CHECK();
+        cf_final_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, stream>>>(nb, (int)P.n_it, n_items, d, k, item_offset, bitmap, ub, ue, ldu, Ie, ldi, mp,
+                                                                      mitems, flags, counter, row_of_slot, out_idx + r0 * k, out_val + r0 * k);
+        MMREC_LAUNCH_CHECK();
+        cf_exact_kernel<<<CF_EX_SLOTS, 256, 0, stream>>>(ub, ue, ldu, n_items, Ie, ldi, d, k, item_offset, mp, mitems, counter, row_of_slot, keys,
+                                                         out_idx + r0 * k, out_val + r0 * k);
+        MMREC_LAUNCH_CHECK();
+    }
+    return 1;
+}
+
+// rows of the last row block that went to the exact kernel (synchronises; diagnostic)
+int64_t score_cf_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, bool with_cat) {
+    if (!score_cf_supported(B, n_items, d, k) || !ws) return -1;
+    const CfPlan P = cf_plan(B, n_items, d, mask_nnz, with_cat);
+    const char* base = (const char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+    int32_t n = 0;
+    if (cudaMemcpy(&n, base + P.off_flags + (size_t)P.rows_blk * 4, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (getenv("MMREC_DEBUG")) {
+        const int64_t nb = B % P.rows_blk ? B % P.rows_blk : P.rows_blk;
+        int32_t* h = (int32_t*)malloc((size_t)nb * 4);
+        if (h && cudaMemcpy(h, base + P.off_flags, (size_t)nb * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            long long why[4] = {0, 0, 0, 0};
+            for (int64_t i = 0; i < nb; ++i)
+                for (int b = 0; b < 4; ++b) why[b] += (h[i] >> b) & 1;
+            fprintf(stderr, "mmrec: exact-path rows %d of %lld (need > groups %lld, non-finite %lld, > %d candidates %lld, < k kept %lld)\n", n,
+                    (long long)nb, why[0], why[1], CF_CAP, why[2], why[3]);
+        }
+        free(h);
+    }
+    return n;
+}
+
+}  // namespace mmrec

@@ -48,12 +48,14 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def _ws(name: str, nbytes: int, device) -> torch.Tensor:
-    key = (name, device.index)
-    t = _ws_cache.get(key)
-    if t is None or t.numel() < nbytes:
-        t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-        _ws_cache[key] = t
-    return t
+    """Scratch for one op family, per device AND per stream (two streams never share a buffer).  A buffer that turned
+    out too small is kept alive next to its replacement: a CUDA graph captured earlier has its address baked in."""
+    key = (name, device.index, torch.cuda.current_stream(device).cuda_stream)
+    bufs = _ws_cache.setdefault(key, [])
+    if not bufs or bufs[-1].numel() < nbytes:
+        grow = int(bufs[-1].numel() * 1.5) if bufs else 0
+        bufs.append(torch.empty(max(int(nbytes), grow, 256), dtype=torch.uint8, device=device))
+    return bufs[-1]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -256,6 +258,8 @@ def propagate_layergcn(A: CSR, ego: torch.Tensor, n_layers: int) -> torch.Tensor
     1..L, gate and running sum fused into the SpMM epilogue.  (Training goes through `spmm` + torch ops so
     that autograd sees the cosine gate.)"""
     ego = _f32c(ego)
+    if n_layers <= 0:
+        return torch.zeros_like(ego)                 # the sum over layers 1..L of nothing
     acc = torch.empty_like(ego)
     x = ego
     for l in range(1, n_layers + 1):
@@ -370,13 +374,36 @@ def mask_topk(scores: torch.Tensor, mask: Optional[torch.Tensor], k: int, item_o
     return val, idx
 
 
-def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0, out=None):
+class Catalog:
+    """The item side of the scoring contraction prepared once per embedding table (`mmrec_catalog_pack_f32`): tf32
+    operand tiles + the maximum row norm of the error bound.  The reference re-reads the same `restore_item_e` for every
+    evaluation batch (`src/common/trainer.py:302-310`); a model keeps one Catalog next to its cached evaluation
+    embeddings and drops it with them.  Holds a reference to `item_e`: the pair must stay consistent."""
+
+    def __init__(self, item_e: torch.Tensor):
+        _need_cuda(item_e)
+        lib = _lib.load()
+        self.item_e = _f32c(item_e)
+        n_items, d = self.item_e.shape
+        nbytes = lib.mmrec_catalog_bytes(n_items, d)
+        if nbytes == 0:
+            raise MMRecError(f"catalog: no tensor-core path for d = {d}")
+        self.buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=item_e.device)
+        self.ptr = (self.buf.data_ptr() + 1023) // 1024 * 1024
+        check(lib.mmrec_catalog_pack_f32(n_items, _ptr(self.item_e), self.item_e.stride(0), d, self.ptr, nbytes, _stream()),
+              "mmrec_catalog_pack_f32")
+
+
+def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0, out=None, catalog: Optional[Catalog] = None):
     """Fused `full_sort_predict` + mask + top-k (`src/models/freedom.py:216-220` + `src/common/trainer.py:304-309`)
     without materialising the [B, n_items] score matrix in HBM.  Returns (values [B,k], indices int64 [B,k]); `out` =
-    (values, indices) buffers to write into (e.g. peer-mapped memory in the sharded evaluation)."""
+    (values, indices) buffers to write into (e.g. peer-mapped memory in the sharded evaluation); `catalog` = the
+    `Catalog` of exactly this `item_e` (else the item operand is packed inside the call)."""
     _need_cuda(user_e, item_e, users, mask)
     lib = _lib.load()
     user_e, item_e = _f32c(user_e), _f32c(item_e)
+    if catalog is not None and (catalog.item_e.data_ptr() != item_e.data_ptr() or catalog.item_e.shape != item_e.shape):
+        raise MMRecError("score_topk: the catalog was packed from a different item table")
     if users is not None:
         users = users.to(torch.int64).contiguous()
     B = user_e.shape[0] if users is None else users.numel()
@@ -395,16 +422,22 @@ def score_topk(user_e, item_e, users, mask, k: int, item_offset: int = 0, out=No
         m0, m1, nnz = mask[0], mask[1], mask.shape[1]
     nbytes = lib.mmrec_score_topk_workspace_bytes(B, n_items, d, k) + 4 * nnz + 4096
     ws = _ws("score_topk", nbytes, item_e.device)
-    check(lib.mmrec_score_topk_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e),
-                                   item_e.stride(0), d, nnz, _ptr(m0), _ptr(m1), k, item_offset, _ptr(idx), _ptr(val),
-                                   _ptr(ws), ws.numel(), _stream()), "mmrec_score_topk_f32")
+    _last_fused.update(ws=ws, args=(B, n_items, d, k, nnz, int(catalog is None)))
+    check(lib.mmrec_score_topk_cat_f32(B, _ptr(users), _ptr(user_e), user_e.stride(0), n_items, _ptr(item_e),
+                                       item_e.stride(0), d, None if catalog is None else catalog.ptr, nnz, _ptr(m0), _ptr(m1), k,
+                                       item_offset, _ptr(idx), _ptr(val), _ptr(ws), ws.numel(), _stream()), "mmrec_score_topk_cat_f32")
     return val, idx
 
 
-def fused_fallback_rows(B, n_items, d, k, mask_nnz, device) -> int:
-    """Diagnostic: how many rows of the last fused score_topk call went through the exact fp32 kernel."""
-    ws = _ws_cache.get(("score_topk", device.index))
-    return -1 if ws is None else int(_lib.load().mmrec_debug_fused_fallback_rows(_ptr(ws), B, n_items, d, k, mask_nnz))
+_last_fused: dict = {}
+
+
+def fused_fallback_rows(*_ignored) -> int:
+    """Diagnostic (synchronises): how many rows of the last row block of the last fused score_topk call went through the
+    exact fp32 kernel; -1 when that call did not take the fused path."""
+    if not _last_fused:
+        return -1
+    return int(_lib.load().mmrec_debug_fused_fallback_rows(_ptr(_last_fused["ws"]), *_last_fused["args"]))
 
 
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor):

@@ -28,7 +28,7 @@ def test_library_built_and_exports_every_header_symbol():
 def test_loader_binds_and_reports_version():
     from mmrec_b200 import _lib
     lib = _lib.load()
-    assert lib.mmrec_abi_version() == 1
+    assert lib.mmrec_abi_version() == _lib.ABI_VERSION == 2
     assert lib.mmrec_last_error() is not None
 
 

@@ -224,7 +224,8 @@ def test_topk_exact_on_identical_scores(dev, B, I, k):
 
 
 @pytest.mark.parametrize("B,U,I,d,k", [(128, 500, 700, 64, 50), (4096, 5000, 7000, 64, 50), (1000, 1000, 333, 64, 20),
-                                       (77, 300, 20000, 128, 50), (513, 600, 900, 32, 10), (200, 200, 500, 48, 5)])
+                                       (77, 300, 20000, 128, 50), (513, 600, 900, 32, 10), (200, 200, 500, 48, 5),
+                                       (700, 900, 40000, 64, 50), (300, 300, 70001, 96, 20)])
 @pytest.mark.parametrize("path", ["simt", "tc", "fused"])
 def test_score_and_fused_topk(dev, B, U, I, d, k, path):
     from mmrec_b200 import ops
@@ -246,10 +247,12 @@ def test_score_and_fused_topk(dev, B, U, I, d, k, path):
         v2, i2 = ops.mask_topk(Sm, mask.to(dev), k)
         if path != "fused":
             assert torch.equal(idx, i2) and torch.equal(val, v2)
-        else:   # same 3xTF32 arithmetic except for rows the filter hands to the exact fp32 kernel: near ties only
+        else:   # finalists are scored by an fp32 fmaf chain, S by 3xTF32: the same values to rounding, near ties may swap
             dif = (idx != i2).any(dim=1)
             assert dif.float().mean().item() <= 0.05
             assert (val - v2).abs().max().item() < 4e-6 * scale
+            if I >= 16 * 2 * k:                             # the certified-filter kernels ran (not the tc fallback) and served every row
+                assert ops.fused_fallback_rows() == 0
         # against the fp64 re-score: every disagreement must be a near tie, and the SETS must agree up to near ties
         refm = ref.clone(); refm[mask[0], mask[1]] = -1e10
         rv, ri = O.topk_tie_low_index(refm.numpy(), k)
@@ -280,12 +283,13 @@ def _check_near_tie(idx, ref, ri, scale):
 
 
 def test_fused_topk_edge_cases(dev):
-    """The fused tcgen05 path (forced): heavy users (more masked items than the candidate list holds -> exact kernel),
+    """The fused tcgen05 path (forced): heavy users (more masked items than there are item groups -> exact kernel),
     unsorted mask, degenerate (all-equal) scores, ragged sizes, d = 32 / 128."""
     from mmrec_b200 import ops
     ops.set_score_path("fused")
     g = torch.Generator().manual_seed(11)
-    for (B, U, I, d, k) in [(300, 400, 3000, 64, 50), (129, 200, 2049, 128, 20), (1, 10, 1500, 32, 50), (4097, 4100, 2600, 64, 50)]:
+    for (B, U, I, d, k) in [(300, 400, 3000, 64, 50), (129, 200, 2049, 128, 20), (1, 10, 1700, 32, 50), (4097, 4100, 2600, 64, 50),
+                            (257, 300, 16500, 40, 50)]:
         ue = torch.randn(U, d, generator=g) * 0.1; ie = torch.randn(I, d, generator=g) * 0.1
         users = torch.randint(0, U, (B,), generator=g)
         rows = [torch.randint(0, B, (B * 6,), generator=g)]; cols = [torch.randint(0, I, (B * 6,), generator=g)]
@@ -303,6 +307,13 @@ def test_fused_topk_edge_cases(dev):
         hit = torch.zeros(B, I, dtype=torch.bool); hit[mask[0], mask[1]] = True
         assert not hit.gather(1, idx.cpu()).any()
         assert torch.all(val[:, :-1] >= val[:, 1:])
+        # the values are the fp32 scores of the returned items
+        chk = (ue[users][:, None, :].double() * ie[idx.cpu()].double()).sum(-1)
+        assert (chk - val.cpu().double()).abs().max().item() < 2e-6 * ref[ref > -1e9].abs().max().item()
+        # a catalogue packed once gives the same answer as packing inside the call
+        cat = ops.Catalog(ie.to(dev))
+        val_c, idx_c = ops.score_topk(ue.to(dev), cat.item_e, users.to(dev), mask.to(dev), k, catalog=cat)
+        assert torch.equal(idx, idx_c) and torch.equal(val, val_c)
     # all scores equal: nothing to threshold on -> exact kernel, ties resolve to the lowest indices
     ue = torch.zeros(64, 64); ie = torch.randn(2000, 64, generator=g)
     val, idx = ops.score_topk(ue.to(dev), ie.to(dev), None, None, 50)

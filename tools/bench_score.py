@@ -31,7 +31,7 @@ for path in a.paths.split(","):
         e0.record(); val, idx = ops.score_topk(ue, ie, users, mask, 50); e1.record(); torch.cuda.synchronize()
         if r >= 3: ts.append(e0.elapsed_time(e1) * 1e3)
     us = float(np.median(ts))
-    fb = ops.fused_fallback_rows(nb, wl.I, wl.d, 50, mask.shape[1], dev) if path == "fused" else 0
+    fb = ops.fused_fallback_rows() if path in ("fused", "auto") else 0
     agree = "" if ref is None else f" rows identical to {refname}: {(idx == ref).all(dim=1).float().mean().item():.4f}"
     if ref is None: ref, refname = idx, path
     print(f"{path:6s} {us:9.1f} us/batch  {nb*wl.I/us/1e3:8.2f} G items/s  {flops/us/1e6:7.2f} TFLOP/s useful  frac={flops/us/1e6/peak:.3f}  fallback_rows={fb}{agree}")
