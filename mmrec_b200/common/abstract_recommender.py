@@ -62,14 +62,25 @@ class GeneralRecommender(AbstractRecommender):
     # ---- shared helpers for the graph models --------------------------------------------------------
     def _cached_eval_embeddings(self, compute):
         """`full_sort_predict` re-runs the whole propagation for every eval batch in the reference
-        (`freedom.py:215`), although the embeddings cannot change inside `Trainer.evaluate`.  In eval mode the
-        result is cached until the next `train()` call -- bit-identical, removes the largest item of
-        `full_sort_predict`."""
+        (`freedom.py:215`), although the embeddings cannot change inside `Trainer.evaluate`.  Under eval + no_grad the
+        result (and the packed item operand of the fused top-k, `ops.Catalog`) is kept while nothing it depends on
+        changes: the key holds the version counter of every parameter and buffer (optimizer steps, `load_state_dict`,
+        in-place edits all bump it) and the identity of the graph attributes a model names in `_eval_cache_deps`
+        (`norm_adj`, `masked_adj`, ...).  Bit-identical to recomputing; removes the largest item of
+        `full_sort_predict`.  (Writes through `.data` bypass version counters: call `train()`/`eval()`
+        or `invalidate_eval_cache()` after such an edit.)"""
         if self.training or torch.is_grad_enabled():
             return compute()
-        if self._eval_cache is None:
-            self._eval_cache = compute()
-        return self._eval_cache
+        key = (tuple((id(t), t._version) for t in self.parameters()) + tuple((id(t), t._version) for t in self.buffers()),
+               tuple(id(getattr(self, a, None)) for a in self._eval_cache_deps))
+        if self._eval_cache is None or self._eval_cache[0] != key:
+            self._eval_cache = (key, compute(), None)
+        return self._eval_cache[1]
+
+    _eval_cache_deps = ("norm_adj", "masked_adj", "forward_adj", "mm_adj", "image_adj", "text_adj", "R")
+
+    def invalidate_eval_cache(self):
+        self._eval_cache = None
 
     def train(self, mode: bool = True):
         self._eval_cache = None
@@ -80,7 +91,13 @@ class GeneralRecommender(AbstractRecommender):
         (`src/common/trainer.py:304-309`); returns the index matrix only, like the trainer keeps."""
         from .. import ops
         u, i = self._score_embeddings()
-        _, idx = ops.score_topk(u, i, interaction[0], interaction[1], k)
+        cat = None
+        c = self._eval_cache
+        if c is not None and c[1][1] is i and i.shape[1] <= 128:       # cached embeddings: their item operand is packed once
+            if c[2] is None:
+                self._eval_cache = c = (c[0], c[1], ops.Catalog(i))
+            cat, i = c[2], c[2].item_e
+        _, idx = ops.score_topk(u, i, interaction[0], interaction[1], k, catalog=cat)
         return idx
 
     def _score_embeddings(self):

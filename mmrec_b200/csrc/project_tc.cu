@@ -303,10 +303,14 @@ int project_tc(int64_t n_out, const int64_t* idx, const float* table, int64_t F,
     p.vec_ok = ((F & 3) == 0) && ((((uintptr_t)table) & 15) == 0);
     p.partial = partial; p.rows_padded = P.rows_padded;
     const PjSmem L = pj_smem(P.N, P.stages);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMREC_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+    {   // the opt-in is per device
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        MMREC_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            MMREC_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     project_tc_kernel<<<(unsigned)(P.n_tiles * P.n_splits), PJ_THREADS, L.total, stream>>>(p);
     MMREC_LAUNCH_CHECK();

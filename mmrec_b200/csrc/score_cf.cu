@@ -188,7 +188,8 @@ template <int PASS, int GPT>
 __device__ __forceinline__ void cf_epilogue(const CfParams& p, const CfSmem& L, uint32_t sbase, uint32_t tmem_base, int u0, int u1,
                                             int e, int lane) {
     const uint32_t bar = sbase + L.bars;
-    const int q = e & 3, h = (e >> 2) & 1, par = e >> 3;
+    const int q = (e + 2) & 3;                                       // = warp % 4: the TMEM lane quarter this warp may read
+    const int h = (e >> 2) & 1, par = e >> 3;
     constexpr int gpt = GPT;                                          // groups per item tile (pass 1): 8 / gw
     int cur_pair = -1;
     int64_t row = 0;

@@ -200,10 +200,14 @@ int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
     p.tiles_per_split = (int)((n_it + splits - 1) / splits);
     p.n_splits = (int)((n_it + p.tiles_per_split - 1) / p.tiles_per_split);
     const TcSmemLayout L = tc_smem_layout(KP);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMREC_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+    {   // the opt-in is per device
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        MMREC_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            MMREC_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     score_tc_kernel<<<(unsigned)(n_ut * p.n_splits), TC_THREADS, L.total, stream>>>(p);
     MMREC_LAUNCH_CHECK();

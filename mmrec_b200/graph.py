@@ -75,9 +75,14 @@ def build_mgcn_R(inter, n_users, n_items, device) -> CSR:
 class EdgePruner:
     """Degree-sensitive edge pruning of FREEDOM / LayerGCN (`freedom.py:128-162`, `layergcn.py:51-89`).
 
-    The draw stays `torch.multinomial(edge_values, keep_len)` on the device tensor -- the same call, hence the
-    same RNG stream as the reference on the same device; everything after the draw (degree recount,
-    renormalisation, symmetrisation, CSR build) runs in this library's kernels once per epoch.
+    The draw stays `torch.multinomial(edge_values, keep_len)` on the device tensor -- the same call on the same
+    weights; everything after the draw (degree recount, renormalisation, symmetrisation, CSR build) runs in this
+    library's kernels once per epoch.
+
+    Edge order: sorted, de-duplicated (user, item) pairs.  That is what the reference's `get_edge_info` yields with the
+    scipy of this image (`astype` canonicalises the COO matrix; `tests/golden/freedom_tiny.npz:edge_indices`, checked
+    bit for bit), so the same seed prunes the same edges here.  An older scipy keeps the file's row order and repeated
+    interactions: there the pruning matches in distribution only, and a repeated (u, i) counts once in the degrees.
     """
 
     def __init__(self, inter, n_users, n_items, device):
