@@ -186,6 +186,9 @@ int mmrec_score_topk_cat_f32(int64_t B, const int64_t* users, const float* Ue, i
 /* diagnostic, synchronising: rows of the last row block of the last fused call on `ws` that needed the exact kernel
  * (with_cat: the call packed its catalogue into ws, i.e. cat was NULL) */
 int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, int with_cat);
+/* tuning aid: with env MMREC_CF_TIMING set, device time in microseconds of the stages of the last fused call (host array
+ * us[cap]; stages: catalogue pack | prep + mask | pass 1 | threshold | pass 2 | finalists | exact rows); returns the count */
+int mmrec_debug_cf_timing(float* us, int cap);
 int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, const int64_t* idx,
                      int64_t* out_idx, float* out_val, void* stream);
 /* the same merge over lists left where each rank wrote them (peer-mapped memory): vals[p] / idx[p] are host

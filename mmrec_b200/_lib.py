@@ -43,6 +43,7 @@ PROTOTYPES = {
     "mmrec_catalog_pack_f32": (_i32, [_i64, _p, _i64, _i32, _p, _sz, _p]),
     "mmrec_score_topk_cat_f32": (_i32, [_i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p, _i64, _p, _p, _i32, _i64, _p, _p, _p,
                                         _sz, _p]),
+    "mmrec_debug_cf_timing": (_i32, [_p, _i32]),
     "mmrec_debug_fused_fallback_rows": (_i64, [_p, _i64, _i64, _i32, _i32, _i64, _i32]),
     "mmrec_topk_merge": (_i32, [_i32, _i64, _i32, _p, _p, _p, _p, _p]),
     "mmrec_topk_merge_peers": (_i32, [_i32, _i64, _i32, _p, _p, _i64, _i64, _p, _p, _p]),

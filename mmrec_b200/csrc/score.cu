@@ -25,6 +25,7 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
 size_t score_cf_workspace_bytes(int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, bool with_cat);
 size_t cf_catalog_bytes(int64_t n_items, int d);
 int cf_catalog_pack(int64_t n_items, const float* Ie, int64_t ldi, int d, void* cat, size_t cat_bytes, cudaStream_t stream);
+int score_cf_timing(float* us, int cap);
 int64_t score_cf_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, bool with_cat);
 
 int mask_apply(int64_t mask_nnz, const int64_t* mask_rows, const int64_t* mask_cols, int64_t row0, int64_t B,
@@ -97,6 +98,8 @@ extern "C" int mmrec_catalog_pack_f32(int64_t n_items, const float* Ie, int64_t 
     MMREC_CHECK_ARG(cf_catalog_bytes(n_items, d) > 0, "catalog_pack: d > 128 has no tensor-core path");
     return cf_catalog_pack(n_items, Ie, ldi, d, cat, cat_bytes, (cudaStream_t)stream_);
 }
+
+extern "C" int mmrec_debug_cf_timing(float* us, int cap) { return score_cf_timing(us, cap); }
 
 extern "C" int64_t mmrec_debug_fused_fallback_rows(const void* ws, int64_t B, int64_t n_items, int d, int k, int64_t mask_nnz, int with_cat) {
     return score_cf_fallback_rows(ws, B, n_items, d, k, mask_nnz, with_cat != 0);

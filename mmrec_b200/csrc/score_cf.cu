@@ -17,7 +17,7 @@
 //                       member of the true top-k has s~ >= thr = t - 2 eps'.
 //   cf_pass_kernel<2>   s~ again (same instructions, same bits); epilogue = one bit per score, s~ >= thr, 128 bits per
 //                       (row, item tile) written as one 16-byte store.  ~ (need + a few) bits per row are set.
-//   cf_final_kernel     per row (one warp): the set bits -> drop masked items -> exact fp32 score from the ORIGINAL
+//   cf_final_kernel     per row (one CTA): the set bits -> drop masked items -> exact fp32 score from the ORIGINAL
 //                       tables -> rank on (value desc, item asc) -> top-k.
 //   cf_exact_kernel     rows the filter cannot serve (need > number of groups, > CF_CAP candidates, non-finite scores):
 //                       all items in fp32 on CUDA cores + radix select; exits at once when no row is flagged.
@@ -71,6 +71,7 @@ struct CfParams {
     int64_t B, n_items, n_units;
     float* gmax; int G, gw;                     // pass 1: [B][G], G = n_it * (8 / gw)
     const float* thr; uint4* bitmap;            // pass 2: [B], [B][n_it]
+    int dbg;                                    // tuning aid (env MMREC_CF_DEBUG): 1 = epilogue skips its TMEM loads, 2 = no MMAs issued
 };
 
 __device__ __forceinline__ void cf_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -172,6 +173,7 @@ __device__ __forceinline__ void cf_mma(const CfParams& p, const CfSmem& L, uint3
                 const uint64_t bd = smem_desc(b_base + j * 2 * LBO, LBO, SBO);
                 const uint32_t a_off = (kc * (CF_KC / 4) + 2 * j) * LBO;
                 const uint32_t acc = (kc | j) ? 1u : 0u;
+                if (p.dbg & 2) continue;
                 mma_tf32(tmem_base + (buf * 2 + 0) * CF_TILE, smem_desc(sbase + L.a + a_off, LBO, SBO), bd, idesc, acc);
                 if (halves == 2)
                     mma_tf32(tmem_base + (buf * 2 + 1) * CF_TILE, smem_desc(sbase + L.a + half_bytes + a_off, LBO, SBO), bd, idesc, acc);
@@ -207,7 +209,7 @@ __device__ __forceinline__ void cf_epilogue(const CfParams& p, const CfSmem& L, 
         mbar_wait(bar + (CB_TFULL + par) * 8, ((uint32_t)t >> 1) & 1);
         fence_after_sync();
         // (a whole half beyond the batch: nothing to read, but the buffer still has to be released)
-        if ((int64_t)pair * (2 * CF_TILE) + h * CF_TILE < p.B) {
+        if ((int64_t)pair * (2 * CF_TILE) + h * CF_TILE < p.B && !(p.dbg & 1)) {
             const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (par * 2 + h) * CF_TILE;
             const int n_valid = (int)(p.n_items - (int64_t)it * CF_TILE);      // < 128 on the last tile only
             uint32_t va[16], vb[16];
@@ -527,6 +529,32 @@ __device__ __forceinline__ uint32_t cf_warp_kth(F key_at, int n, int need, uint3
     return prefix;
 }
 
+// The threshold does not have to be the exact need-th largest group maximum -- any value with at least `need` maxima at
+// or above it is certified.  So the search runs on the top CF_THR_BITS bits of the order-preserving key only (bit by
+// bit, counts by REDUX: no atomics, the values stay in registers) and takes the lower edge of that bucket: 16 bits =
+// the value to 2^-7 relative, a handful of extra candidates per row for half the dependent steps.
+constexpr int CF_THR_BITS = 16;
+template <int NV>
+__device__ __forceinline__ uint32_t cf_warp_kth_coarse(const float* __restrict__ g, int G, int need, int lane) {
+    uint32_t key[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int t = j * 32 + lane;
+        key[j] = t < G ? float_key(__ldg(g + t)) : 0u;
+    }
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int b = 31; b >= 32 - CF_THR_BITS; --b) {
+        const uint32_t cand = prefix | (1u << b);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) cnt += key[j] >= cand;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= need) prefix = cand;
+    }
+    return prefix;                                                   // <= the need-th largest key, same top bits
+}
+
 __global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int k, const float* __restrict__ gmax, const float* __restrict__ unorm,
                                                      const uint32_t* __restrict__ max_norm, const int32_t* __restrict__ mask_ptr,
                                                      float* __restrict__ thr, int32_t* __restrict__ flags) {
@@ -540,7 +568,10 @@ __global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int k, c
         return;
     }
     const float* g = gmax + row * G;
-    const uint32_t kth = cf_warp_kth([&](int t) { return float_key(__ldg(g + t)); }, G, need, hist_all[warp], lane);
+    uint32_t kth;
+    if (G <= 16 * 32) kth = cf_warp_kth_coarse<16>(g, G, need, lane);
+    else if (G <= 32 * 32) kth = cf_warp_kth_coarse<32>(g, G, need, lane);
+    else kth = cf_warp_kth([&](int t) { return float_key(__ldg(g + t)); }, G, need, hist_all[warp], lane);
     if (lane == 0) {
         const float t = key_float(kth);
         const float margin = 2.0f * CF_EPS * unorm[row] * __uint_as_float(*max_norm);
@@ -551,155 +582,118 @@ __global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int k, c
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// exact fp32 score of one (user, item) pair.  THE arithmetic of this file's results: 32 partial sums (element c goes to
-// partial c % 32, fmaf in ascending c), then the pairwise tree 16, 8, 4, 2, 1 -- what a warp computes with one lane
-// per partial and an xor butterfly (cf_exact_kernel), here by one thread.
+// exact fp32 score of one (user, item) pair.  THE arithmetic of this file's results: four fmaf chains (element c goes to
+// chain c % 4, ascending c), then (s0 + s1) + (s2 + s3).  One thread per pair, 16-byte loads when the rows allow it.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, const float* __restrict__ v, int d, bool vec_ok) {
-    float part[32];
-#pragma unroll
-    for (int L = 0; L < 32; ++L) part[L] = 0.f;
-    if (vec_ok) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {                                // d <= 128
-            if (q * 32 < d) {
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const int c = q * 32 + i4 * 4;
-                    if (c < d) {                                     // d % 4 == 0 on this path
-                        const float4 x = ldg4(v + c);
-                        const float4 uu = *reinterpret_cast<const float4*>(u_sm + c);
-                        part[i4 * 4 + 0] = fmaf(uu.x, x.x, part[i4 * 4 + 0]);
-                        part[i4 * 4 + 1] = fmaf(uu.y, x.y, part[i4 * 4 + 1]);
-                        part[i4 * 4 + 2] = fmaf(uu.z, x.z, part[i4 * 4 + 2]);
-                        part[i4 * 4 + 3] = fmaf(uu.w, x.w, part[i4 * 4 + 3]);
-                    }
-                }
-            }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (vec_ok) {                                                    // d % 4 == 0, rows 16-byte aligned
+        const int n4 = d >> 2;
+#pragma unroll 4
+        for (int i = 0; i < n4; ++i) {
+            const float4 x = ldg4(v + 4 * i);
+            const float4 uu = *reinterpret_cast<const float4*>(u_sm + 4 * i);
+            s0 = fmaf(uu.x, x.x, s0); s1 = fmaf(uu.y, x.y, s1); s2 = fmaf(uu.z, x.z, s2); s3 = fmaf(uu.w, x.w, s3);
         }
     } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int L = 0; L < 32; ++L) {
-                const int c = q * 32 + L;
-                if (c < d) part[L] = fmaf(u_sm[c], __ldg(v + c), part[L]);
-            }
+        int c = 0;
+        for (; c + 3 < d; c += 4) {
+            s0 = fmaf(u_sm[c], __ldg(v + c), s0); s1 = fmaf(u_sm[c + 1], __ldg(v + c + 1), s1);
+            s2 = fmaf(u_sm[c + 2], __ldg(v + c + 2), s2); s3 = fmaf(u_sm[c + 3], __ldg(v + c + 3), s3);
         }
+        if (c < d) s0 = fmaf(u_sm[c], __ldg(v + c), s0);
+        if (c + 1 < d) s1 = fmaf(u_sm[c + 1], __ldg(v + c + 1), s1);
+        if (c + 2 < d) s2 = fmaf(u_sm[c + 2], __ldg(v + c + 2), s2);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int L = 0; L < 32; ++L)
-            if (L < o) part[L] = part[L] + part[L + o];
-    }
-    return part[0];
+    return (s0 + s1) + (s2 + s3);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// finalists: set bits of the row's bitmap -> unmasked -> exact fp32 -> top-k in contract order.  One warp per row.
+// finalists: set bits of the row's bitmap -> unmasked -> exact fp32 -> top-k in contract order.  One CTA (4 warps) per row:
+// a row is ~60 candidates, and what bounds this kernel is the length of one row's dependent chain, so the row is spread
+// over 128 threads (one candidate each) instead of walked by one warp.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
-                                                       const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
-                                                       const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
-                                                       const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
-                                                       int32_t* __restrict__ flags, int32_t* __restrict__ counter, int32_t* __restrict__ row_of_slot,
-                                                       int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
-    __shared__ uint64_t fin_all[4][CF_CAP];
-    __shared__ __align__(16) float u_all[4][128];
-    __shared__ uint32_t hist_all[4][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row = (int64_t)blockIdx.x * 4 + warp;
-    if (row >= nb) return;
-    auto condemn = [&](int why) {                                    // the exact kernel takes the row
-        if (lane == 0) {
+constexpr int CF_FIN_THREADS = 128;
+constexpr int CF_MASK_SM = 256;                 // masked items of the row staged in shared memory (more: read from global)
+__global__ void __launch_bounds__(CF_FIN_THREADS) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
+                                                                  const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
+                                                                  const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
+                                                                  const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
+                                                                  int32_t* __restrict__ flags, int32_t* __restrict__ counter,
+                                                                  int32_t* __restrict__ row_of_slot, int64_t* __restrict__ out_idx,
+                                                                  float* __restrict__ out_val) {
+    __shared__ uint64_t comp[CF_CAP];
+    __shared__ int32_t cand[CF_CAP];
+    __shared__ __align__(16) float u_sm[128];
+    __shared__ int32_t mask_sm[CF_MASK_SM];
+    __shared__ int n_sh, kept_sh;
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x;
+    auto condemn = [&](int why) {                                    // the exact kernel takes the row (block-uniform call)
+        if (tid == 0) {
             if (why) flags[row] = why;
             row_of_slot[atomicAdd(counter, 1)] = (int32_t)row;
         }
     };
     if (flags[row]) { condemn(0); return; }
-    uint64_t* fin = fin_all[warp];
-    float* u_sm = u_all[warp];
-    const float* u = Ue + (users ? users[row] : row) * ldu;
-    for (int c = lane; c < 128; c += 32) u_sm[c] = c < d ? __ldg(u + c) : 0.f;
     const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
-    // 1. the set bits, in ascending item order per lane; positions from a running warp prefix
+    {
+        const float* u = Ue + (users ? users[row] : row) * ldu;
+        u_sm[tid] = tid < d ? __ldg(u + tid) : 0.f;                    // (CF_FIN_THREADS == 128 >= d)
+        for (int q = tid; q < m1 - m0 && q < CF_MASK_SM; q += CF_FIN_THREADS) mask_sm[q] = __ldg(mask_items + m0 + q);
+        if (tid == 0) { n_sh = 0; kept_sh = 0; }
+    }
+    __syncthreads();
+    // 1. the set bits of the row: one 128-bit word (= one item tile) per thread, list position from a shared counter
     const uint4* bm = bitmap + row * n_it;
-    int n = 0;
-    bool over = false;
-    for (int w0 = 0; w0 < n_it; w0 += 32) {
-        const int wi = w0 + lane;
-        uint4 b = make_uint4(0u, 0u, 0u, 0u);
-        if (wi < n_it) b = __ldg(bm + wi);
+    for (int wi = tid; wi < n_it; wi += CF_FIN_THREADS) {
+        const uint4 b = __ldg(bm + wi);
         const int mine = __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-        int incl = mine;
+        if (mine) {
+            int pos = atomicAdd(&n_sh, mine);
+            const uint32_t ws[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        int pos = n + incl - mine;
-        n += __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t ws[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t x = ws[q];
-            while (x) {
-                const int j = __clz(x);                              // bit (31 - j) <-> column 32 q + j of the tile
-                x &= ~(0x80000000u >> j);
-                if (pos < CF_CAP) fin[pos] = (uint32_t)(wi * CF_TILE + q * 32 + j);
-                else over = true;
-                ++pos;
+            for (int q = 0; q < 4; ++q) {
+                uint32_t x = ws[q];
+                while (x) {
+                    const int j = __clz(x);                          // bit (31 - j) <-> column 32 q + j of the tile
+                    x &= ~(0x80000000u >> j);
+                    if (pos < CF_CAP) cand[pos] = wi * CF_TILE + q * 32 + j;
+                    ++pos;
+                }
             }
         }
     }
-    over = __any_sync(0xffffffffu, over);
-    if (over) { condemn(4); return; }
-    __syncwarp();
-    // 2. masked train positives out, exact fp32 score in
+    __syncthreads();
+    const int n = n_sh;
+    if (n > CF_CAP) { condemn(4); return; }
+    // 2. masked train positives out, exact fp32 score in: one candidate per thread
     const bool vec_ok = (ldi & 3) == 0 && (d & 3) == 0 && ((((uintptr_t)Ie) & 15) == 0);
     int kept = 0;
-    for (int t0 = 0; t0 < n; t0 += 32) {
-        const int t = t0 + lane;
-        uint64_t comp = 0;                                           // 0 sorts last: a dropped candidate
-        if (t < n) {
-            const int item = (int)(uint32_t)fin[t];
-            bool keep = item < n_items;
-            for (int qd = m0; qd < m1; ++qd) keep &= (__ldg(mask_items + qd) != item);
-            if (keep) {
-                const float s = cf_dot_thread(u_sm, Ie + (int64_t)item * ldi, d, vec_ok);
-                comp = ((uint64_t)float_key(s) << 32) | (uint32_t)(~(uint32_t)item);
-            }
+    for (int t = tid; t < n; t += CF_FIN_THREADS) {
+        const int item = cand[t];
+        bool keep = item < n_items;
+        const int msm = (m1 - m0) < CF_MASK_SM ? (m1 - m0) : CF_MASK_SM;
+        for (int q = 0; q < msm; ++q) keep &= (mask_sm[q] != item);
+        for (int q = m0 + CF_MASK_SM; q < m1; ++q) keep &= (__ldg(mask_items + q) != item);
+        uint64_t c = 0;                                              // 0 sorts last: a dropped candidate
+        if (keep) {
+            const float sc = cf_dot_thread(u_sm, Ie + (int64_t)item * ldi, d, vec_ok);
+            c = ((uint64_t)float_key(sc) << 32) | (uint32_t)(~(uint32_t)item);
+            ++kept;
         }
-        kept += __popc(__ballot_sync(0xffffffffu, comp != 0));
-        __syncwarp();
-        if (t < n) fin[t] = comp;
+        comp[t] = c;
     }
-    __syncwarp();
-    if (kept < k) { condemn(8); return; }                            // (cannot happen for finite scores: the threshold is certified)
-    // 3. rank.  Few finalists (the usual case): all against all.  Many: first the k-th largest value key by a warp radix
-    //    select, then only the composites at or above it (k plus ties on the value).
-    int m = n;
-    if (n > 96) {
-        const uint32_t kth = cf_warp_kth([&](int t) { return (uint32_t)(fin[t] >> 32); }, n, k, hist_all[warp], lane);
-        m = 0;
-        for (int t0 = 0; t0 < n; t0 += 32) {
-            const int t = t0 + lane;
-            const uint64_t c = t < n ? fin[t] : 0;
-            const bool keep = t < n && c != 0 && (uint32_t)(c >> 32) >= kth;
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            __syncwarp();
-            if (keep) fin[m + __popc(bal & ((1u << lane) - 1u))] = c;     // in place: writes never pass the reads
-            m += __popc(bal);
-            __syncwarp();
-        }
-    }
-    // composites are unique (item index in the low word): rank = number of larger composites = output position
-    for (int t = lane; t < m; t += 32) {
-        const uint64_t me = fin[t];
+    if (kept) atomicAdd(&kept_sh, kept);
+    __syncthreads();
+    if (kept_sh < k) { condemn(8); return; }                         // (cannot happen for finite scores: the threshold is certified)
+    // 3. rank: composites are unique (item index in the low word), rank = number of larger composites = output position
+    for (int t = tid; t < n; t += CF_FIN_THREADS) {
+        const uint64_t me = comp[t];
         if (me == 0) continue;
         int rank = 0;
-        for (int u2 = 0; u2 < m; ++u2) rank += fin[u2] > me;
+#pragma unroll 4
+        for (int u2 = 0; u2 < n; ++u2) rank += comp[u2] > me;
         if (rank < k) {
             out_idx[row * k + rank] = (int64_t)(uint32_t)(~(uint32_t)me) + item_offset;
             out_val[row * k + rank] = key_float((uint32_t)(me >> 32));
@@ -737,37 +731,19 @@ __global__ void __launch_bounds__(256) cf_exact_kernel(const int64_t* __restrict
     __shared__ unsigned tie_idx[1024];
     __shared__ unsigned s_prefix, s_need, s_count, s_base, n_ties;
     __shared__ unsigned warp_tot[8];
+    __shared__ __align__(16) float u_ex[128];
     const int n_flagged = *counter;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned* keys = keys_all + (int64_t)blockIdx.x * n_items;
     for (int fr = blockIdx.x; fr < n_flagged; fr += gridDim.x) {
         const int64_t row = row_of_slot[fr];
         __syncthreads();
-        // ---- keys: one warp per item, lane L sums the elements L, L + 32, ... (fmaf), xor butterfly: cf_dot_thread's bits
+        // ---- keys: one thread per item, cf_dot_thread's arithmetic (the row gets the same bits whichever kernel served it)
         const float* u = Ue + (users ? users[row] : row) * ldu;
-        float ur[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ur[i] = (lane + 32 * i < d) ? u[lane + 32 * i] : 0.f;
-        for (int64_t i0 = wid; i0 < n_items; i0 += 32) {             // 4 items in flight per warp
-            float acc[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t i = i0 + e * 8;
-                acc[e] = 0.f;
-                if (i < n_items) {
-                    const float* v = Ie + i * ldi;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (lane + 32 * q < d) acc[e] = fmaf(ur[q], __ldg(v + lane + 32 * q), acc[e]);
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t i = i0 + e * 8;
-                const float r = warp_sum(acc[e]);
-                if (lane == 0 && i < n_items) keys[i] = float_key(r);
-            }
-        }
+        if (tid < 128) u_ex[tid] = tid < d ? u[tid] : 0.f;
+        __syncthreads();
+        const bool vec_ok = (ldi & 3) == 0 && (d & 3) == 0 && ((((uintptr_t)Ie) & 15) == 0);
+        for (int64_t i = tid; i < n_items; i += 256) keys[i] = float_key(cf_dot_thread(u_ex, Ie + i * ldi, d, vec_ok));
         __syncthreads();
         const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
         for (int q = m0 + tid; q < m1; q += 256) {
@@ -947,6 +923,26 @@ static int cf_set_attrs() {
     return MMREC_OK;
 }
 
+// Stage timing (tuning aid): with env MMREC_CF_TIMING set, the stages of the LAST score_cf call are bracketed by CUDA events
+// (not under stream capture); mmrec_debug_cf_timing reads them back in microseconds.
+static cudaEvent_t g_cf_ev[10];
+static int g_cf_nev = 0, g_cf_timing = -1;
+static inline void cf_mark(cudaStream_t stream) {
+    if (g_cf_timing <= 0 || g_cf_nev >= 10) return;
+    if (!g_cf_ev[g_cf_nev]) cudaEventCreate(&g_cf_ev[g_cf_nev]);
+    cudaEventRecord(g_cf_ev[g_cf_nev++], stream);
+}
+int score_cf_timing(float* us, int cap) {
+    int n = 0;
+    for (int i = 0; i + 1 < g_cf_nev && n < cap; ++i) {
+        cudaEventSynchronize(g_cf_ev[i + 1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_cf_ev[i], g_cf_ev[i + 1]);
+        us[n++] = ms * 1000.f;
+    }
+    return n;
+}
+
 // returns 1 = done, 0 = unsupported shape / workspace (caller uses the unfused path), <0 error.  `cat` = a catalogue packed
 // by cf_catalog_pack for exactly (n_items, Ie, d), or NULL: then it is packed into the workspace first.
 int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int64_t n_items, const float* Ie, int64_t ldi,
@@ -957,11 +953,15 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
     char* base = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
     if (ws_bytes < P.total + (size_t)(base - (char*)ws)) return 0;
     { int rc = cf_set_attrs(); if (rc) return rc; }
+    if (g_cf_timing < 0) g_cf_timing = getenv("MMREC_CF_TIMING") ? 1 : 0;
+    g_cf_nev = 0;
+    cf_mark(stream);                                                  // stages: pack | prep + mask | pass 1 | thr | pass 2 | final | exact
     if (!cat) {
         int rc = cf_catalog_pack(n_items, Ie, ldi, d, base + P.off_cat, cf_catalog_bytes(n_items, d), stream);
         if (rc) return rc;
         cat = base + P.off_cat;
     }
+    cf_mark(stream);
     const uint32_t* max_norm = (const uint32_t*)cat;
     const float* Ipk = (const float*)((const char*)cat + CF_CAT_HEADER);
     float *Upk = (float*)(base + P.off_upk), *unorm = (float*)(base + P.off_unorm), *gmax = (float*)(base + P.off_gmax), *thr = (float*)(base + P.off_thr);
@@ -1006,9 +1006,11 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
                                                                                      mitems, mcur, (int)mask_blocks);
             MMREC_LAUNCH_CHECK();
         }
+        cf_mark(stream);
         CfParams p;
         p.Upk = Upk; p.Ipk = Ipk; p.KP = P.KP; p.n_it = (int)P.n_it; p.B = nb; p.n_items = n_items; p.n_units = n_pairs * P.n_it;
         p.gmax = gmax; p.G = P.G; p.gw = P.gw; p.thr = thr; p.bitmap = bitmap;
+        { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MMREC_CF_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
         const unsigned grid = (unsigned)(p.n_units < sms ? p.n_units : sms);
         switch (P.gw) {
             case 1: cf_pass_kernel<1, 8><<<grid, CF_THREADS, L.total, stream>>>(p); break;
@@ -1017,16 +1019,21 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
             default: cf_pass_kernel<1, 1><<<grid, CF_THREADS, L.total, stream>>>(p); break;
         }
         MMREC_LAUNCH_CHECK();
+        cf_mark(stream);
         cf_thr_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, stream>>>(nb, P.G, k, gmax, unorm, max_norm, mp, thr, flags);
         MMREC_LAUNCH_CHECK();
+        cf_mark(stream);
         cf_pass_kernel<2, 8><<<grid, CF_THREADS, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
-        cf_final_kernel<<<(unsigned)((nb + 3) / 4), 128, 0, stream>>>(nb, (int)P.n_it, n_items, d, k, item_offset, bitmap, ub, ue, ldu, Ie, ldi, mp,
+        cf_mark(stream);
+        cf_final_kernel<<<(unsigned)nb, CF_FIN_THREADS, 0, stream>>>(nb, (int)P.n_it, n_items, d, k, item_offset, bitmap, ub, ue, ldu, Ie, ldi, mp,
                                                                       mitems, flags, counter, row_of_slot, out_idx + r0 * k, out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
+        cf_mark(stream);
         cf_exact_kernel<<<CF_EX_SLOTS, 256, 0, stream>>>(ub, ue, ldu, n_items, Ie, ldi, d, k, item_offset, mp, mitems, counter, row_of_slot, keys,
                                                          out_idx + r0 * k, out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
+        cf_mark(stream);
     }
     return 1;
 }

@@ -440,6 +440,15 @@ def fused_fallback_rows(*_ignored) -> int:
     return int(_lib.load().mmrec_debug_fused_fallback_rows(_ptr(_last_fused["ws"]), *_last_fused["args"]))
 
 
+def fused_stage_times():
+    """Tuning aid: device microseconds of the stages of the last fused score_topk call (env MMREC_CF_TIMING must be set
+    before the first call): [catalogue pack, prep + mask, pass 1, threshold, pass 2, finalists, exact rows]."""
+    import ctypes
+    buf = (ctypes.c_float * 16)()
+    n = _lib.load().mmrec_debug_cf_timing(ctypes.cast(buf, ctypes.c_void_p), 16)
+    return [float(buf[i]) for i in range(n)]
+
+
 def topk_merge(vals: torch.Tensor, idx: torch.Tensor):
     """Merge per-shard top-k lists [parts, B, k] into the global top-k [B, k] (SURVEY.md 8e eval collective)."""
     _need_cuda(vals, idx)

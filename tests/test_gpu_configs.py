@@ -93,9 +93,9 @@ def test_config_size_projection_vs_oracle(dev, name):
     W = torch.randn(d, F, generator=gen) / F ** 0.5
     b = torch.randn(d, generator=gen) * 0.1
     y = ops.project(X.to(dev), W.to(dev), b.to(dev))
-    assert rel(y, O.project(X, W, b)) < 1e-5
+    assert rel(y, O.project(X, W, b)) < 5e-5                                        # bar: 1e-4 (3xTF32 over F = 4096 terms)
     idx = torch.randint(0, I, (2048,), generator=gen)                               # the calculate_loss gather (freedom.py:205-209)
-    assert rel(ops.project(X.to(dev), W.to(dev), b.to(dev), idx=idx.to(dev)), O.project(X, W, b, idx=idx)) < 1e-5
+    assert rel(ops.project(X.to(dev), W.to(dev), b.to(dev), idx=idx.to(dev)), O.project(X, W, b, idx=idx)) < 5e-5
 
 
 def test_fused_topk_config5_shard_shape(dev):

@@ -34,5 +34,7 @@ for path in a.paths.split(","):
     fb = ops.fused_fallback_rows() if path in ("fused", "auto") else 0
     agree = "" if ref is None else f" rows identical to {refname}: {(idx == ref).all(dim=1).float().mean().item():.4f}"
     if ref is None: ref, refname = idx, path
+    if os.environ.get("MMREC_CF_TIMING") and path in ("auto", "fused"):
+        print("   stages us [pack, prep+mask, pass1, thr, pass2, final, exact]:", [round(x, 1) for x in ops.fused_stage_times()])
     print(f"{path:6s} {us:9.1f} us/batch  {nb*wl.I/us/1e3:8.2f} G items/s  {flops/us/1e6:7.2f} TFLOP/s useful  frac={flops/us/1e6/peak:.3f}  fallback_rows={fb}{agree}")
 ops.set_score_path("auto")
