@@ -589,11 +589,17 @@ __device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, c
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     if (vec_ok) {                                                    // d % 4 == 0, rows 16-byte aligned
         const int n4 = d >> 2;
-#pragma unroll 4
-        for (int i = 0; i < n4; ++i) {
-            const float4 x = ldg4(v + 4 * i);
-            const float4 uu = *reinterpret_cast<const float4*>(u_sm + 4 * i);
-            s0 = fmaf(uu.x, x.x, s0); s1 = fmaf(uu.y, x.y, s1); s2 = fmaf(uu.z, x.z, s2); s3 = fmaf(uu.w, x.w, s3);
+        for (int i0 = 0; i0 < n4; i0 += 8) {                         // 8 x 16 bytes of the item row in flight
+            float4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = i0 + i < n4 ? ldg4(v + 4 * (i0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i0 + i < n4) {
+                    const float4 uu = *reinterpret_cast<const float4*>(u_sm + 4 * (i0 + i));
+                    s0 = fmaf(uu.x, x[i].x, s0); s1 = fmaf(uu.y, x[i].y, s1); s2 = fmaf(uu.z, x[i].z, s2); s3 = fmaf(uu.w, x[i].w, s3);
+                }
+            }
         }
     } else {
         int c = 0;
@@ -616,12 +622,12 @@ __device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, c
 constexpr int CF_FIN_THREADS = 128;
 constexpr int CF_MASK_SM = 256;                 // masked items of the row staged in shared memory (more: read from global)
 __global__ void __launch_bounds__(CF_FIN_THREADS) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
-                                                                  const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
-                                                                  const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
-                                                                  const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
-                                                                  int32_t* __restrict__ flags, int32_t* __restrict__ counter,
-                                                                  int32_t* __restrict__ row_of_slot, int64_t* __restrict__ out_idx,
-                                                                  float* __restrict__ out_val) {
+                                                                      const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
+                                                                      const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
+                                                                      const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
+                                                                      int32_t* __restrict__ flags, int32_t* __restrict__ counter,
+                                                                      int32_t* __restrict__ row_of_slot, int64_t* __restrict__ out_idx,
+                                                                      float* __restrict__ out_val) {
     __shared__ uint64_t comp[CF_CAP];
     __shared__ int32_t cand[CF_CAP];
     __shared__ __align__(16) float u_sm[128];
@@ -635,19 +641,24 @@ __global__ void __launch_bounds__(CF_FIN_THREADS) cf_final_kernel(int64_t nb, in
             row_of_slot[atomicAdd(counter, 1)] = (int32_t)row;
         }
     };
-    if (flags[row]) { condemn(0); return; }
-    const int m0 = mask_ptr ? mask_ptr[row] : 0, m1 = mask_ptr ? mask_ptr[row + 1] : 0;
+    // everything that depends on the row number only is requested at once (one memory round trip, not four)
+    const int flagged = __ldg(flags + row);
+    const int m0 = mask_ptr ? __ldg(mask_ptr + row) : 0, m1 = mask_ptr ? __ldg(mask_ptr + row + 1) : 0;
+    const int64_t urow = users ? __ldg(users + row) : row;
+    const uint4* bm = bitmap + row * n_it;
+    uint4 b0 = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < n_it) b0 = __ldg(bm + tid);
+    if (flagged) { condemn(0); return; }
     {
-        const float* u = Ue + (users ? users[row] : row) * ldu;
+        const float* u = Ue + urow * ldu;
         u_sm[tid] = tid < d ? __ldg(u + tid) : 0.f;                    // (CF_FIN_THREADS == 128 >= d)
         for (int q = tid; q < m1 - m0 && q < CF_MASK_SM; q += CF_FIN_THREADS) mask_sm[q] = __ldg(mask_items + m0 + q);
         if (tid == 0) { n_sh = 0; kept_sh = 0; }
     }
     __syncthreads();
     // 1. the set bits of the row: one 128-bit word (= one item tile) per thread, list position from a shared counter
-    const uint4* bm = bitmap + row * n_it;
     for (int wi = tid; wi < n_it; wi += CF_FIN_THREADS) {
-        const uint4 b = __ldg(bm + wi);
+        const uint4 b = wi == tid ? b0 : __ldg(bm + wi);
         const int mine = __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
         if (mine) {
             int pos = atomicAdd(&n_sh, mine);

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 700 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "score or fused or topk or full_size" > gpurun_out/${tag}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_pytest.log; tail -12 gpurun_out/${tag}_pytest.log | cut -c1-250
 timeout 500 python -m pytest tests/test_gpu_configs.py -x -q -m gpu > gpurun_out/${tag}_configs.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_configs.log; tail -12 gpurun_out/${tag}_configs.log | cut -c1-250
 MMREC_DEBUG=1 timeout 200 python tools/bench_score.py --paths auto,tc > gpurun_out/${tag}_score.log 2>&1; tail -4 gpurun_out/${tag}_score.log
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_launches.csv python tools/bench_score.py --paths auto --reps 2 > /dev/null 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 200 --csv --log-file gpurun_out/${tag}_launches.csv python tools/bench_score.py --paths auto --reps 2 > /dev/null 2>&1
 python - <<PY
 import csv, collections
 rows=[r for r in csv.reader(open("gpurun_out/${tag}_launches.csv")) if len(r)>10 and r[0].isdigit()]
