@@ -17,7 +17,7 @@
 //                       member of the true top-k has s~ >= thr = t - 2 eps'.
 //   cf_pass_kernel<2>   s~ again (same instructions, same bits); epilogue = one bit per score, s~ >= thr, 128 bits per
 //                       (row, item tile) written as one 16-byte store.  ~ (need + a few) bits per row are set.
-//   cf_final_kernel     per row (one CTA): the set bits -> drop masked items -> exact fp32 score from the ORIGINAL
+//   cf_final_kernel     per row (one warp): the set bits -> drop masked items -> exact fp32 score from the ORIGINAL
 //                       tables -> rank on (value desc, item asc) -> top-k.
 //   cf_exact_kernel     rows the filter cannot serve (need > number of groups, > CF_CAP candidates, non-finite scores):
 //                       all items in fp32 on CUDA cores + radix select; exits at once when no row is flagged.
@@ -542,9 +542,16 @@ __device__ __forceinline__ uint32_t cf_warp_kth_coarse(const float* __restrict__
         const int t = j * 32 + lane;
         key[j] = t < G ? float_key(__ldg(g + t)) : 0u;
     }
-    uint32_t prefix = 0;
+    // bits above the first one in which the row's largest and smallest key differ are common to all keys: nothing to search
+    uint32_t kmax = 0u, kmin = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { kmax = max(kmax, key[j]); if (j * 32 + lane < G) kmin = min(kmin, key[j]); }
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    const int top = 31 - __clz((kmax ^ kmin) | (1u << (32 - CF_THR_BITS)));    // >= the lowest searched bit
+    uint32_t prefix = top >= 31 ? 0u : (kmax & ~((2u << top) - 1u));
 #pragma unroll 1
-    for (int b = 31; b >= 32 - CF_THR_BITS; --b) {
+    for (int b = top; b >= 32 - CF_THR_BITS; --b) {
         const uint32_t cand = prefix | (1u << b);
         int cnt = 0;
 #pragma unroll
@@ -615,53 +622,108 @@ __device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, c
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// finalists: set bits of the row's bitmap -> unmasked -> exact fp32 -> top-k in contract order.  One CTA (4 warps) per row:
-// a row is ~60 candidates, and what bounds this kernel is the length of one row's dependent chain, so the row is spread
-// over 128 threads (one candidate each) instead of walked by one warp.
+// finalists: set bits of the row's bitmap -> unmasked -> exact fp32 -> top-k in contract order.  One warp per row, written
+// for instruction count (the kernel is issue-bound at large batches: ~70 candidates per row, 20,000 rows):
+//   * the set bits come out in ascending item order (lane = bitmap word, positions by a warp prefix sum);
+//   * the mask is applied from the mask's side: lane q looks its masked item up in the sorted candidate list (binary
+//     search), O(m log n) instead of n x m comparisons;
+//   * one exact dot product per lane and round (cf_dot_thread);
+//   * ranking counts, per element, the larger 32-bit value keys (one LDS broadcast feeds up to four elements of the
+//     lane); equal values are ordered by item index = list position in a second pass that runs only when the rank sum
+//     shows that two candidates share a value.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int CF_FIN_THREADS = 128;
-constexpr int CF_MASK_SM = 256;                 // masked items of the row staged in shared memory (more: read from global)
-__global__ void __launch_bounds__(CF_FIN_THREADS) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
-                                                                      const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
-                                                                      const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
-                                                                      const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
-                                                                      int32_t* __restrict__ flags, int32_t* __restrict__ counter,
-                                                                      int32_t* __restrict__ row_of_slot, int64_t* __restrict__ out_idx,
-                                                                      float* __restrict__ out_val) {
-    __shared__ uint64_t comp[CF_CAP];
-    __shared__ int32_t cand[CF_CAP];
-    __shared__ __align__(16) float u_sm[128];
-    __shared__ int32_t mask_sm[CF_MASK_SM];
-    __shared__ int n_sh, kept_sh;
-    const int tid = threadIdx.x;
-    const int64_t row = blockIdx.x;
-    auto condemn = [&](int why) {                                    // the exact kernel takes the row (block-uniform call)
-        if (tid == 0) {
+template <int E>
+__device__ __forceinline__ void cf_rank_sweeps(const int32_t* cand, const uint32_t* keys, int n, int kept, int k, int lane, int64_t row,
+                                               int64_t item_offset, int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    for (int e0 = 0; e0 * 32 < n; e0 += E) {
+        uint32_t mk[E];
+        int rk[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { const int t = (e0 + e) * 32 + lane; mk[e] = t < n ? keys[t] : 0u; rk[e] = 0; }
+#pragma unroll 2
+        for (int u2 = 0; u2 < n; ++u2) {
+            const uint32_t ku = keys[u2];                            // broadcast
+#pragma unroll
+            for (int e = 0; e < E; ++e) rk[e] += ku > mk[e];
+        }
+        // all value keys distinct <=> the ranks of the live elements are a permutation of 0 .. kept-1 (checkable when one
+        // sweep covers the list; with several sweeps the tie pass always runs)
+        bool tie = n > 32 * E;
+        if (!tie) {
+            int sr = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) sr += mk[e] != 0u ? rk[e] : 0;
+            tie = __reduce_add_sync(0xffffffffu, sr) != kept * (kept - 1) / 2;
+        }
+        if (tie) {                                                   // equal values: lower item index (= list position) first
+            for (int u2 = 0; u2 < n; ++u2) {
+                const uint32_t ku = keys[u2];
+#pragma unroll
+                for (int e = 0; e < E; ++e) rk[e] += (ku == mk[e]) && (u2 < (e0 + e) * 32 + lane);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (mk[e] != 0u && rk[e] < k) {
+                out_idx[row * k + rk[e]] = (int64_t)cand[(e0 + e) * 32 + lane] + item_offset;
+                out_val[row * k + rk[e]] = key_float(mk[e]);
+            }
+        }
+    }
+}
+
+constexpr int CF_FIN_WARPS = 4;
+__global__ void __launch_bounds__(32 * CF_FIN_WARPS) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
+                                                                     const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
+                                                                     const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
+                                                                     const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
+                                                                     int32_t* __restrict__ flags, int32_t* __restrict__ counter,
+                                                                     int32_t* __restrict__ row_of_slot, int64_t* __restrict__ out_idx,
+                                                                     float* __restrict__ out_val) {
+    __shared__ int32_t cand_all[CF_FIN_WARPS][CF_CAP];
+    __shared__ uint32_t key_all[CF_FIN_WARPS][CF_CAP];
+    __shared__ __align__(16) float u_all[CF_FIN_WARPS][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * CF_FIN_WARPS + warp;
+    if (row >= nb) return;
+    auto condemn = [&](int why) {                                    // the exact kernel takes the row
+        if (lane == 0) {
             if (why) flags[row] = why;
             row_of_slot[atomicAdd(counter, 1)] = (int32_t)row;
         }
     };
-    // everything that depends on the row number only is requested at once (one memory round trip, not four)
+    // everything that depends on the row number only is requested at once
     const int flagged = __ldg(flags + row);
     const int m0 = mask_ptr ? __ldg(mask_ptr + row) : 0, m1 = mask_ptr ? __ldg(mask_ptr + row + 1) : 0;
     const int64_t urow = users ? __ldg(users + row) : row;
     const uint4* bm = bitmap + row * n_it;
     uint4 b0 = make_uint4(0u, 0u, 0u, 0u);
-    if (tid < n_it) b0 = __ldg(bm + tid);
+    if (lane < n_it) b0 = __ldg(bm + lane);
     if (flagged) { condemn(0); return; }
+    int32_t* cand = cand_all[warp];
+    uint32_t* keys = key_all[warp];
+    float* u_sm = u_all[warp];
     {
         const float* u = Ue + urow * ldu;
-        u_sm[tid] = tid < d ? __ldg(u + tid) : 0.f;                    // (CF_FIN_THREADS == 128 >= d)
-        for (int q = tid; q < m1 - m0 && q < CF_MASK_SM; q += CF_FIN_THREADS) mask_sm[q] = __ldg(mask_items + m0 + q);
-        if (tid == 0) { n_sh = 0; kept_sh = 0; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) u_sm[c * 32 + lane] = c * 32 + lane < d ? __ldg(u + c * 32 + lane) : 0.f;
     }
-    __syncthreads();
-    // 1. the set bits of the row: one 128-bit word (= one item tile) per thread, list position from a shared counter
-    for (int wi = tid; wi < n_it; wi += CF_FIN_THREADS) {
-        const uint4 b = wi == tid ? b0 : __ldg(bm + wi);
+    // 1. set bits -> candidate list in ascending item order; keys[] = 1 marks a live candidate
+    int n = 0;
+    for (int w0 = 0; w0 < n_it; w0 += 32) {
+        const int wi = w0 + lane;
+        uint4 b = b0;
+        if (w0 > 0) { b = make_uint4(0u, 0u, 0u, 0u); if (wi < n_it) b = __ldg(bm + wi); }
         const int mine = __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int pos = n + incl - mine;
+        n += __shfl_sync(0xffffffffu, incl, 31);
         if (mine) {
-            int pos = atomicAdd(&n_sh, mine);
             const uint32_t ws[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -669,47 +731,48 @@ __global__ void __launch_bounds__(CF_FIN_THREADS) cf_final_kernel(int64_t nb, in
                 while (x) {
                     const int j = __clz(x);                          // bit (31 - j) <-> column 32 q + j of the tile
                     x &= ~(0x80000000u >> j);
-                    if (pos < CF_CAP) cand[pos] = wi * CF_TILE + q * 32 + j;
+                    if (pos < CF_CAP) { cand[pos] = wi * CF_TILE + q * 32 + j; keys[pos] = 1u; }
                     ++pos;
                 }
             }
         }
     }
-    __syncthreads();
-    const int n = n_sh;
     if (n > CF_CAP) { condemn(4); return; }
-    // 2. masked train positives out, exact fp32 score in: one candidate per thread
+    __syncwarp();
+    // 2. masked train positives out: each masked item is looked up in the sorted list, its key becomes 0 (= dropped)
+    for (int q0 = m0; q0 < m1; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < m1) {
+            const int item = __ldg(mask_items + q);
+            int lo = 0, hi = n;                                      // first position with cand >= item
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cand[mid] < item) lo = mid + 1; else hi = mid;
+            }
+            if (lo < n && cand[lo] == item) keys[lo] = 0u;
+        }
+    }
+    __syncwarp();
+    // 3. exact fp32 scores (float_key of a real score is never 0; -NaN would be: such a candidate is dropped)
     const bool vec_ok = (ldi & 3) == 0 && (d & 3) == 0 && ((((uintptr_t)Ie) & 15) == 0);
     int kept = 0;
-    for (int t = tid; t < n; t += CF_FIN_THREADS) {
-        const int item = cand[t];
-        bool keep = item < n_items;
-        const int msm = (m1 - m0) < CF_MASK_SM ? (m1 - m0) : CF_MASK_SM;
-        for (int q = 0; q < msm; ++q) keep &= (mask_sm[q] != item);
-        for (int q = m0 + CF_MASK_SM; q < m1; ++q) keep &= (__ldg(mask_items + q) != item);
-        uint64_t c = 0;                                              // 0 sorts last: a dropped candidate
-        if (keep) {
-            const float sc = cf_dot_thread(u_sm, Ie + (int64_t)item * ldi, d, vec_ok);
-            c = ((uint64_t)float_key(sc) << 32) | (uint32_t)(~(uint32_t)item);
-            ++kept;
-        }
-        comp[t] = c;
-    }
-    if (kept) atomicAdd(&kept_sh, kept);
-    __syncthreads();
-    if (kept_sh < k) { condemn(8); return; }                         // (cannot happen for finite scores: the threshold is certified)
-    // 3. rank: composites are unique (item index in the low word), rank = number of larger composites = output position
-    for (int t = tid; t < n; t += CF_FIN_THREADS) {
-        const uint64_t me = comp[t];
-        if (me == 0) continue;
-        int rank = 0;
-#pragma unroll 4
-        for (int u2 = 0; u2 < n; ++u2) rank += comp[u2] > me;
-        if (rank < k) {
-            out_idx[row * k + rank] = (int64_t)(uint32_t)(~(uint32_t)me) + item_offset;
-            out_val[row * k + rank] = key_float((uint32_t)(me >> 32));
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int t = t0 + lane;
+        if (t < n && keys[t] != 0u) {
+            const int item = cand[t];
+            uint32_t key = 0u;
+            if (item < n_items) key = float_key(cf_dot_thread(u_sm, Ie + (int64_t)item * ldi, d, vec_ok));
+            kept += key != 0u;
+            keys[t] = key;
         }
     }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    __syncwarp();
+    if (kept < k) { condemn(8); return; }                            // (cannot happen for finite scores: the threshold is certified)
+    // 4. rank = number of candidates with a larger value key; E elements of this lane per sweep of the list
+    if (n <= 64) cf_rank_sweeps<2>(cand, keys, n, kept, k, lane, row, item_offset, out_idx, out_val);
+    else if (n <= 96) cf_rank_sweeps<3>(cand, keys, n, kept, k, lane, row, item_offset, out_idx, out_val);
+    else cf_rank_sweeps<4>(cand, keys, n, kept, k, lane, row, item_offset, out_idx, out_val);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1037,7 +1100,7 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
         cf_pass_kernel<2, 8><<<grid, CF_THREADS, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
-        cf_final_kernel<<<(unsigned)nb, CF_FIN_THREADS, 0, stream>>>(nb, (int)P.n_it, n_items, d, k, item_offset, bitmap, ub, ue, ldu, Ie, ldi, mp,
+        cf_final_kernel<<<(unsigned)((nb + CF_FIN_WARPS - 1) / CF_FIN_WARPS), 32 * CF_FIN_WARPS, 0, stream>>>(nb, (int)P.n_it, n_items, d, k, item_offset, bitmap, ub, ue, ldu, Ie, ldi, mp,
                                                                       mitems, flags, counter, row_of_slot, out_idx + r0 * k, out_val + r0 * k);
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
