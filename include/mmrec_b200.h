@@ -192,23 +192,41 @@ int mmrec_debug_cf_timing(float* us, int cap);
 int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, const int64_t* idx,
                      int64_t* out_idx, float* out_val, void* stream);
 /* the same merge over lists left where each rank wrote them (peer-mapped memory): vals[p] / idx[p] are host
- * arrays of `parts` (<= 16) device pointers to [B, k] lists; an index becomes idx * idx_mul + p * idx_add
- * (round-robin item shards: idx_mul = world, idx_add = 1).  The caller synchronises the ranks before the call. */
+ * arrays of `parts` (<= 16, parts * k <= 1024) device pointers to [B, k] lists, each sorted (value desc, index asc); an
+ * index becomes idx * idx_mul + p * idx_add (round-robin item shards: idx_mul = world, idx_add = 1; must stay below
+ * 2^32).  Only rows [row0, row0 + n_rows) are merged, into out_idx / out_val [n_rows, k]: in the sharded evaluation
+ * every rank merges its own slice of the batch.  The caller synchronises the ranks before the call. */
 int mmrec_topk_merge_peers(int parts, int64_t B, int k, const void* const* vals, const void* const* idx,
-                           int64_t idx_mul, int64_t idx_add, int64_t* out_idx, float* out_val, void* stream);
+                           int64_t idx_mul, int64_t idx_add, int64_t row0, int64_t n_rows,
+                           int64_t* out_idx, float* out_val, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  user-embedding exchange of the item-sharded propagation, over peer memory (no reference counterpart:
  * the reference is single-GPU, src/utils/configurator.py:114-118; the sum it distributes is the user half of
  * `torch.sparse.mm(adj, ego)`, src/models/freedom.py:172, plus the layer mean of freedom.py:175-176).
+ *
+ * mmrec_peer_sum_f32 (all ranks read all partials; right for world = 2):
  *   parts   host array of `world` device pointers, rank order: partial user sums R_g E_Ig, [n] floats each,
  *           peer-mapped (CUDA IPC / symmetric memory) -- the caller synchronises the ranks before the call
  *   sum_out = sum over ranks in rank order (identical bits on every rank), may be NULL
  *   acc_out = (acc_in + sum) / acc_div, may be NULL (acc_in NULL = 0; in place allowed)
  *   n % 4 == 0, all pointers 16-byte aligned, world <= 16.
+ *
+ * mmrec_peer_reduce_push_f32 (reduce-scatter + all-gather in one kernel; what scales to 8 GPUs): rank `rank` owns the
+ *   slice [rank * per, (rank + 1) * per) of the n / 4 float4 elements, per = ceil(n / 4 / world).  It sums that slice of
+ *   all partials in rank order and stores the result into the same slice of every dst[p] (peer-mapped, its own
+ *   included): a non-final layer stores the sum and, if acc_in, acc_out = acc_in + sum; the final layer stores
+ *   (acc_in + sum) / acc_div.  acc_in / acc_out hold THIS RANK'S SLICE only (per float4, may alias).  The caller
+ *   synchronises the ranks before (partials complete) and after (stores visible) the call.
+ *
+ * mmrec_peer_gather_f32: dst[p * n_each + i] = src[p][i] -- all-gather of a sharded table by peer loads (the item-id
+ *   embeddings the item-item layer of the sharded FREEDOM needs, src/models/freedom.py:166-167).
  */
 int mmrec_peer_sum_f32(int64_t n, int world, const void* const* parts, const float* acc_in,
                        float* acc_out, float acc_div, float* sum_out, void* stream);
+int mmrec_peer_reduce_push_f32(int64_t n, int world, int rank, const void* const* parts, void* const* dst,
+                               const float* acc_in, float* acc_out, float acc_div, int final_layer, void* stream);
+int mmrec_peer_gather_f32(int64_t n_each, int world, const void* const* src, float* dst, void* stream);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,55 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(int64_t n4, int world, co
     }
 }
 
+
+// Reduce-scatter + all-gather form of the same exchange (what scales: every rank READS (world-1)/world of one partial
+// and WRITES (world-1)/world of the result over NVLink, instead of reading world-1 whole partials).  Rank `rank` owns
+// the slice [lo4, hi4) of the float4 range: it sums that slice of all partials in rank order -- each element is summed
+// exactly once, by its owner, so every rank ends up with identical bits -- and pushes the result into the same slice of
+// every rank's `dst` buffer (its own included).  The layer-mean accumulator lives sliced as well: `acc` is this rank's
+// slice only; a non-final layer does acc += sum and pushes the sum (the next layer's E_U), the final layer pushes
+// (acc + sum) / div (the propagated user table).  The caller synchronises the ranks before (partials complete) and
+// after (pushes visible) the call.
+__global__ void __launch_bounds__(256) peer_reduce_push_kernel(int64_t lo4, int64_t hi4, int world, const PeerParts parts, const PeerParts dst,
+                                                               const float4* __restrict__ acc_in, float4* __restrict__ acc_out, float div,
+                                                               int final_layer) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi4; i += stride) {
+        float4 v[PEER_MAX];
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            if (r < world) v[r] = parts.p[r][i];                     // all peer loads in flight before the first add
+        float4 s = v[0];
+#pragma unroll
+        for (int r = 1; r < PEER_MAX; ++r)
+            if (r < world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        float4 out = s;
+        if (acc_in) {
+            float4 a = acc_in[i - lo4];
+            a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+            if (final_layer) {
+                if (div != 1.0f) { a.x = __fdiv_rn(a.x, div); a.y = __fdiv_rn(a.y, div); a.z = __fdiv_rn(a.z, div); a.w = __fdiv_rn(a.w, div); }
+                out = a;
+            } else if (acc_out) {
+                acc_out[i - lo4] = a;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            if (r < world) const_cast<float4*>(dst.p[r])[i] = out;
+    }
+}
+
+// dst[p * n4 + i] = src[p][i]: the shards of a table read straight from the peers that own them (all-gather by P2P loads)
+__global__ void __launch_bounds__(256) peer_gather_kernel(int64_t n4, int world, const PeerParts src, float4* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total = n4 * world;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int p = (int)(i / n4);
+        dst[i] = src.p[p][i - (int64_t)p * n4];
+    }
+}
+
 }  // namespace mmrec
 
 using namespace mmrec;
@@ -56,6 +105,55 @@ extern "C" int mmrec_peer_sum_f32(int64_t n, int world, const void* const* parts
     const int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
     peer_sum_kernel<<<(unsigned)grid, 256, 0, stream>>>(n4, world, P, (const float4*)acc_in, (float4*)acc_out, acc_div, (float4*)sum_out);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}
+
+extern "C" int mmrec_peer_reduce_push_f32(int64_t n, int world, int rank, const void* const* parts, void* const* dst, const float* acc_in,
+                                          float* acc_out, float acc_div, int final_layer, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(n >= 0 && world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world && parts && dst,
+                    "peer_reduce_push: bad sizes (1 <= world <= 16, 0 <= rank < world)");
+    MMREC_CHECK_ARG((n & 3) == 0, "peer_reduce_push: n must be a multiple of 4 floats");
+    MMREC_CHECK_ARG(acc_div != 0.0f, "peer_reduce_push: acc_div == 0");
+    if (n == 0) return MMREC_OK;
+    PeerParts P, D;
+    for (int r = 0; r < PEER_MAX; ++r) { P.p[r] = nullptr; D.p[r] = nullptr; }
+    for (int r = 0; r < world; ++r) {
+        MMREC_CHECK_ARG(parts[r] && dst[r] && ((((uintptr_t)parts[r]) | ((uintptr_t)dst[r])) & 15) == 0,
+                        "peer_reduce_push: buffer pointers must be non-null and 16-byte aligned");
+        P.p[r] = (const float4*)parts[r]; D.p[r] = (const float4*)dst[r];
+    }
+    MMREC_CHECK_ARG(((((uintptr_t)acc_in) | ((uintptr_t)acc_out)) & 15) == 0, "peer_reduce_push: 16-byte alignment");
+    const int64_t n4 = n / 4;
+    const int64_t per = (n4 + world - 1) / world;                     // slice of this rank (the accumulator holds `per` float4)
+    const int64_t lo4 = per * rank < n4 ? per * rank : n4, hi4 = lo4 + per < n4 ? lo4 + per : n4;
+    if (hi4 <= lo4) return MMREC_OK;
+    int64_t grid = (hi4 - lo4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    peer_reduce_push_kernel<<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, world, P, D, (const float4*)acc_in, (float4*)acc_out, acc_div,
+                                                                 final_layer);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}
+
+extern "C" int mmrec_peer_gather_f32(int64_t n_each, int world, const void* const* src, float* dst, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(n_each >= 0 && world >= 1 && world <= PEER_MAX && src && dst, "peer_gather: bad sizes (1 <= world <= 16)");
+    MMREC_CHECK_ARG((n_each & 3) == 0 && (((uintptr_t)dst) & 15) == 0, "peer_gather: n_each must be a multiple of 4 floats, dst 16-byte aligned");
+    if (n_each == 0) return MMREC_OK;
+    PeerParts S;
+    for (int r = 0; r < PEER_MAX; ++r) S.p[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        MMREC_CHECK_ARG(src[r] && (((uintptr_t)src[r]) & 15) == 0, "peer_gather: source pointers must be non-null and 16-byte aligned");
+        S.p[r] = (const float4*)src[r];
+    }
+    const int64_t n4 = n_each / 4;
+    int64_t grid = (n4 * world + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    peer_gather_kernel<<<(unsigned)grid, 256, 0, stream>>>(n4, world, S, (float4*)dst);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }

@@ -545,7 +545,10 @@ __device__ __forceinline__ uint32_t cf_warp_kth_coarse(const float* __restrict__
     // bits above the first one in which the row's largest and smallest key differ are common to all keys: nothing to search
     uint32_t kmax = 0u, kmin = 0xffffffffu;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) { kmax = max(kmax, key[j]); if (j * 32 + lane < G) kmin = min(kmin, key[j]); }
+    for (int j = 0; j < NV; ++j) {                                   // (-inf = a group of padding columns: not part of the range)
+        kmax = max(kmax, key[j]);
+        if (j * 32 + lane < G && key[j] > 0x007fffffu) kmin = min(kmin, key[j]);
+    }
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     kmin = __reduce_min_sync(0xffffffffu, kmin);
     const int top = 31 - __clz((kmax ^ kmin) | (1u << (32 - CF_THR_BITS)));    // >= the lowest searched bit
@@ -562,7 +565,7 @@ __device__ __forceinline__ uint32_t cf_warp_kth_coarse(const float* __restrict__
     return prefix;                                                   // <= the need-th largest key, same top bits
 }
 
-__global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int k, const float* __restrict__ gmax, const float* __restrict__ unorm,
+__global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int G_valid, int k, const float* __restrict__ gmax, const float* __restrict__ unorm,
                                                      const uint32_t* __restrict__ max_norm, const int32_t* __restrict__ mask_ptr,
                                                      float* __restrict__ thr, int32_t* __restrict__ flags) {
     __shared__ uint32_t hist_all[8][256];
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int k, c
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= nb) return;
     const int need = k + (mask_ptr ? mask_ptr[row + 1] - mask_ptr[row] : 0);
-    if (need > G) {                                                  // more finalists wanted than there are groups: exact kernel
+    if (need > G_valid) {                                            // more finalists wanted than there are (non-padding) groups: exact kernel
         if (lane == 0) { thr[row] = INFINITY; flags[row] = 1; }
         return;
     }
@@ -640,9 +643,18 @@ __device__ __forceinline__ void cf_rank_sweeps(const int32_t* cand, const uint32
         int rk[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) { const int t = (e0 + e) * 32 + lane; mk[e] = t < n ? keys[t] : 0u; rk[e] = 0; }
-#pragma unroll 2
-        for (int u2 = 0; u2 < n; ++u2) {
-            const uint32_t ku = keys[u2];                            // broadcast
+        int u2 = 0;
+        for (; u2 + 8 <= n; u2 += 8) {                               // 8 broadcast loads in flight, then the compares
+            uint32_t ku[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ku[i] = keys[u2 + i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int e = 0; e < E; ++e) rk[e] += ku[i] > mk[e];
+        }
+        for (; u2 < n; ++u2) {
+            const uint32_t ku = keys[u2];
 #pragma unroll
             for (int e = 0; e < E; ++e) rk[e] += ku > mk[e];
         }
@@ -1094,7 +1106,7 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
         }
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
-        cf_thr_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, stream>>>(nb, P.G, k, gmax, unorm, max_norm, mp, thr, flags);
+        cf_thr_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, stream>>>(nb, P.G, (int)((n_items + 16 * P.gw - 1) / (16 * P.gw)), k, gmax, unorm, max_norm, mp, thr, flags);
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
         cf_pass_kernel<2, 8><<<grid, CF_THREADS, L.total, stream>>>(p);

@@ -168,46 +168,51 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_merge_kernel(int parts, int
 
 // The same merge with the lists left where the ranks wrote them: list `p` is [B, k] behind vals[p] / idx[p] (peer-mapped
 // memory in the item-sharded evaluation), and a local item id becomes the global one as idx * idx_mul + p * idx_add
-// (round-robin shards: idx_mul = world, idx_add = 1; pass 1, 0 for ids that are global already).
+// (round-robin shards: idx_mul = world, idx_add = 1; pass 1, 0 for ids that are global already).  Rows [row0, row0 +
+// n_rows) only: in the sharded evaluation every rank merges its own slice of the batch.
+//
+// One warp per row.  Every list arrives sorted on the composite (value desc, global item asc) -- a list's local order is
+// its global order, the relabelling is monotone -- so the rank of an element is the sum over the lists of the number of
+// larger composites there, found by binary search: O(parts log k) per element instead of comparing all pairs.
 constexpr int MERGE_MAX_PEERS = 16;
+constexpr int MERGE_WARPS = 4;
+constexpr int MERGE_WARP_CAP = 1024;    // parts * k one warp handles
 struct MergePeers { const float* v[MERGE_MAX_PEERS]; const int64_t* i[MERGE_MAX_PEERS]; };
 
-__global__ void __launch_bounds__(TOPK_THREADS) topk_merge_peers_kernel(int parts, int64_t B, int k, const MergePeers src, int64_t idx_mul,
-                                                                        int64_t idx_add, int64_t* __restrict__ out_idx,
-                                                                        float* __restrict__ out_val) {
-    extern __shared__ uint64_t cand[];   // n2 composites (value key, ~rank) + n2 int64 indices
-    __shared__ int slot_of_rank[MERGE_MAX_PEERS * TOPK_MAXK > 4096 ? 4096 : MERGE_MAX_PEERS * TOPK_MAXK];
+__global__ void __launch_bounds__(32 * MERGE_WARPS) topk_merge_peers_kernel(int parts, int64_t B, int k, const MergePeers src, int64_t idx_mul,
+                                                                            int64_t idx_add, int64_t row0, int64_t n_rows,
+                                                                            int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    __shared__ uint64_t comp_all[MERGE_WARPS][MERGE_WARP_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * MERGE_WARPS + warp;
+    if (r >= n_rows) return;
+    const int64_t b = row0 + r;
+    uint64_t* comp = comp_all[warp];
     const int n = parts * k;
-    int n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    int64_t* cidx = reinterpret_cast<int64_t*>(cand + n2);
-    const int64_t b = blockIdx.x;
-    for (int t = threadIdx.x; t < n; t += TOPK_THREADS) {
-        const int part = t / k, j = t % k;
-        cidx[t] = src.i[part][b * k + j] * idx_mul + part * idx_add;
+    for (int t = lane; t < n; t += 32) {
+        const int p = t / k, j = t - p * k;
+        const int64_t gi = src.i[p][b * k + j] * idx_mul + p * idx_add;               // < 2^32 (checked by the host)
+        comp[t] = ((uint64_t)float_key(src.v[p][b * k + j]) << 32) | (uint32_t)(~(uint32_t)gi);
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < n2; t += TOPK_THREADS) {
-        if (t < n) {
-            const int part = t / k, j = t % k;
-            const float v = src.v[part][b * k + j];
-            const int64_t me = cidx[t];
-            unsigned rank = 0;
-            for (int u = 0; u < n; ++u) rank += (cidx[u] < me) || (cidx[u] == me && u < t);
-            cand[t] = ((uint64_t)float_key(v) << 32) | (uint32_t)(~rank);
-        } else {
-            cand[t] = 0;
+    __syncwarp();
+    for (int t = lane; t < n; t += 32) {
+        const uint64_t me = comp[t];
+        const int p = t / k, j = t - p * k;
+        int rank = j;                                                // its own list: the j elements before it
+        for (int q = 0; q < parts && rank < k; ++q) {
+            if (q == p) continue;
+            const uint64_t* lst = comp + q * k;
+            int lo = 0, hi = k;                                      // first position whose composite is < me
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (lst[mid] > me) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
         }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < n; t += TOPK_THREADS) slot_of_rank[(uint32_t)(~(uint32_t)cand[t])] = t;
-    __syncthreads();
-    bitonic_desc(cand, n2);
-    for (int t = threadIdx.x; t < k; t += TOPK_THREADS) {
-        const uint64_t c = cand[t];
-        const int slot = slot_of_rank[(uint32_t)(~(uint32_t)c)];
-        out_idx[b * k + t] = cidx[slot];
-        out_val[b * k + t] = key_float((uint32_t)(c >> 32));
+        if (rank < k) {
+            out_idx[r * k + rank] = (int64_t)(uint32_t)(~(uint32_t)me);
+            out_val[r * k + rank] = key_float((uint32_t)(me >> 32));
+        }
     }
 }
 
@@ -263,11 +268,12 @@ extern "C" int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, 
 }
 
 extern "C" int mmrec_topk_merge_peers(int parts, int64_t B, int k, const void* const* vals, const void* const* idx, int64_t idx_mul,
-                                      int64_t idx_add, int64_t* out_idx, float* out_val, void* stream_) {
+                                      int64_t idx_add, int64_t row0, int64_t n_rows, int64_t* out_idx, float* out_val, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    MMREC_CHECK_ARG(parts >= 1 && parts <= MERGE_MAX_PEERS && B >= 0 && k >= 1 && (int64_t)parts * k <= 4096,
-                    "topk_merge_peers: need parts <= 16 and parts*k <= 4096");
-    if (B == 0) return MMREC_OK;
+    MMREC_CHECK_ARG(parts >= 1 && parts <= MERGE_MAX_PEERS && B >= 0 && k >= 1 && (int64_t)parts * k <= MERGE_WARP_CAP,
+                    "topk_merge_peers: need parts <= 16 and parts*k <= 1024");
+    MMREC_CHECK_ARG(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= B, "topk_merge_peers: row range outside the batch");
+    if (B == 0 || n_rows == 0) return MMREC_OK;
     MMREC_CHECK_ARG(vals && idx && out_idx && out_val, "topk_merge_peers: null pointer");
     MergePeers src;
     for (int p = 0; p < MERGE_MAX_PEERS; ++p) { src.v[p] = nullptr; src.i[p] = nullptr; }
@@ -275,11 +281,8 @@ extern "C" int mmrec_topk_merge_peers(int parts, int64_t B, int k, const void* c
         MMREC_CHECK_ARG(vals[p] && idx[p], "topk_merge_peers: null list pointer");
         src.v[p] = (const float*)vals[p]; src.i[p] = (const int64_t*)idx[p];
     }
-    int n = parts * k, n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    const size_t smem = (size_t)n2 * 16;
-    MMREC_CUDA(cudaFuncSetAttribute(topk_merge_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    topk_merge_peers_kernel<<<(unsigned)B, TOPK_THREADS, smem, stream>>>(parts, B, k, src, idx_mul, idx_add, out_idx, out_val);
+    topk_merge_peers_kernel<<<(unsigned)((n_rows + MERGE_WARPS - 1) / MERGE_WARPS), 32 * MERGE_WARPS, 0, stream>>>(
+        parts, B, k, src, idx_mul, idx_add, row0, n_rows, out_idx, out_val);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }

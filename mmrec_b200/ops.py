@@ -461,30 +461,54 @@ def topk_merge(vals: torch.Tensor, idx: torch.Tensor):
     return out_v, out_i
 
 
-def topk_merge_peers(val_ptrs, idx_ptrs, B, k, device, idx_mul=1, idx_add=0):
-    """`topk_merge` over lists left where each rank wrote them: raw device addresses of `parts` [B, k] value (fp32) and
-    index (int64) lists, rank order; index -> idx * idx_mul + part * idx_add (round-robin shards: world, 1)."""
+def _ptr_array(ptrs):
     import ctypes
+    arr = (ctypes.c_void_p * len(ptrs))(*[int(x) for x in ptrs])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def topk_merge_peers(val_ptrs, idx_ptrs, B, k, device, idx_mul=1, idx_add=0, row0=0, n_rows=None):
+    """`topk_merge` over lists left where each rank wrote them: raw device addresses of `parts` [B, k] value (fp32) and
+    index (int64) lists, rank order; index -> idx * idx_mul + part * idx_add (round-robin shards: world, 1).  Rows
+    [row0, row0 + n_rows) only (default: all): returns ([n_rows, k] values, indices)."""
     lib = _lib.load()
-    parts = len(val_ptrs)
-    va = (ctypes.c_void_p * parts)(*[int(x) for x in val_ptrs])
-    ia = (ctypes.c_void_p * parts)(*[int(x) for x in idx_ptrs])
-    out_i = torch.empty(B, k, dtype=torch.int64, device=device)
-    out_v = torch.empty(B, k, dtype=torch.float32, device=device)
-    check(lib.mmrec_topk_merge_peers(parts, B, k, ctypes.cast(va, ctypes.c_void_p), ctypes.cast(ia, ctypes.c_void_p), int(idx_mul),
-                                     int(idx_add), _ptr(out_i), _ptr(out_v), _stream()), "mmrec_topk_merge_peers")
+    n_rows = B - row0 if n_rows is None else n_rows
+    va, vap = _ptr_array(val_ptrs)
+    ia, iap = _ptr_array(idx_ptrs)
+    out_i = torch.empty(n_rows, k, dtype=torch.int64, device=device)
+    out_v = torch.empty(n_rows, k, dtype=torch.float32, device=device)
+    check(lib.mmrec_topk_merge_peers(len(val_ptrs), B, k, vap, iap, int(idx_mul), int(idx_add), int(row0), int(n_rows), _ptr(out_i),
+                                     _ptr(out_v), _stream()), "mmrec_topk_merge_peers")
     return out_v, out_i
 
 
 def peer_sum(part_ptrs, n, acc_in=None, acc_out=None, acc_div=1.0, sum_out=None):
     """K4: `sum_out = sum_r parts[r]` (rank order), `acc_out = (acc_in + sum) / acc_div` -- the user-embedding exchange of
     the item-sharded propagation as one pass over peer-mapped buffers (`part_ptrs`: raw device addresses, rank order)."""
-    import ctypes
     lib = _lib.load()
-    arr = (ctypes.c_void_p * len(part_ptrs))(*[int(x) for x in part_ptrs])
-    check(lib.mmrec_peer_sum_f32(int(n), len(part_ptrs), ctypes.cast(arr, ctypes.c_void_p), _ptr(acc_in), _ptr(acc_out), float(acc_div),
+    arr, arrp = _ptr_array(part_ptrs)
+    check(lib.mmrec_peer_sum_f32(int(n), len(part_ptrs), arrp, _ptr(acc_in), _ptr(acc_out), float(acc_div),
                                  _ptr(sum_out), _stream()), "mmrec_peer_sum_f32")
     return sum_out, acc_out
+
+
+def peer_reduce_push(part_ptrs, dst_ptrs, n, rank, acc_in=None, acc_out=None, acc_div=1.0, final_layer=False):
+    """K4, reduce-scatter + all-gather form (`mmrec_peer_reduce_push_f32`): this rank sums ITS slice of all partials and
+    stores the result (final layer: `(acc + sum) / acc_div`) into that slice of every rank's destination buffer;
+    `acc_in` / `acc_out` hold this rank's slice of the running layer sum."""
+    lib = _lib.load()
+    pa, pap = _ptr_array(part_ptrs)
+    da, dap = _ptr_array(dst_ptrs)
+    check(lib.mmrec_peer_reduce_push_f32(int(n), len(part_ptrs), int(rank), pap, dap, _ptr(acc_in), _ptr(acc_out), float(acc_div),
+                                         int(bool(final_layer)), _stream()), "mmrec_peer_reduce_push_f32")
+
+
+def peer_gather(src_ptrs, n_each, dst: torch.Tensor):
+    """`dst[p * n_each + i] = src[p][i]`: all-gather of a sharded table by peer loads (`mmrec_peer_gather_f32`)."""
+    lib = _lib.load()
+    sa, sap = _ptr_array(src_ptrs)
+    check(lib.mmrec_peer_gather_f32(int(n_each), len(src_ptrs), sap, _ptr(dst), _stream()), "mmrec_peer_gather_f32")
+    return dst
 
 
 def bipartite_norm(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, eps: float = 1e-7) -> torch.Tensor:

@@ -52,6 +52,21 @@ class ItemShard:
     def to_global(self, local_idx):
         return local_idx * self.world + self.rank
 
+    def mm_csr(self, row, col, val, device):
+        """This rank's rows of an item-item matrix (global COO, e.g. FREEDOM's mm_adj) as a CSR over LOCAL rows and
+        RANK-MAJOR columns: global item j sits at (j % world) * n_local + j // world, the layout `mmrec_peer_gather_f32`
+        produces.  Needs equally sized shards."""
+        from .ops import CSR
+        if self.n_items % self.world:
+            raise ValueError("mm_csr: n_items must be a multiple of the world size (equal shards)")
+        row, col = np.asarray(row, dtype=np.int64), np.asarray(col, dtype=np.int64)
+        mine = (row % self.world) == self.rank
+        r = row[mine] // self.world
+        c = (col[mine] % self.world) * self.n_local + col[mine] // self.world
+        return CSR.from_coo(torch.from_numpy(r).to(device), torch.from_numpy(c).to(device),
+                            torch.from_numpy(np.asarray(val, dtype=np.float32)[mine]).to(device), self.n_local,
+                            self.world * self.n_local, sum_duplicates=True)
+
     def csrs(self, device):
         """(users x local items, local items x users) as device CSRs."""
         from .ops import CSR
@@ -95,20 +110,55 @@ def propagate_mean_sharded(a_ui, a_iu, user_emb, item_emb_local, n_layers, spmm=
     return acc_u, acc_i
 
 
-class PeerExchange:
-    """Per-layer partial-sum buffers that every rank has mapped (torch symmetric memory: CUDA IPC over NVLink) plus the
-    device-side barrier between the ranks' streams.  `PeerExchange.create` returns None when this torch build / box cannot
-    provide it -- the caller then keeps the NCCL all-reduce formulation."""
+def mm_layer_sharded(shard: ItemShard, mm_local, item_emb_local, i_acc, spmm=_cuda_spmm, group=None):
+    """The item-item layer of the sharded FREEDOM in the NCCL / gloo formulation: all-gather of the layer-0 item rows
+    (rank-major, what `ItemShard.mm_csr` indexes), then `i_g + mm_adj @ E_I` locally (`src/models/freedom.py:166-167,178`)."""
+    world = shard.world
+    allrows = torch.empty(world * shard.n_local, item_emb_local.shape[1], dtype=item_emb_local.dtype, device=item_emb_local.device)
+    dist.all_gather_into_tensor(allrows, item_emb_local.contiguous(), group=group)
+    _, out = spmm(mm_local, allrows, acc_in=i_acc, acc_div=1.0, want_y=False)
+    return out
 
-    def __init__(self, hdl, buf, n_users, d, n_layers, rank, world, topk_rows, k):
+
+class PeerExchange:
+    """Buffers that every rank has mapped (torch symmetric memory: CUDA IPC over NVLink) plus the device-side barrier
+    between the ranks' streams.  One allocation, fp32 words:
+        parts[l]  [U, d]   this rank's partial user sums of layer l+1 (written by its user-side SpMM)
+        gath[l]   [U, d]   the reduced user table of layer l+1: every slice is stored here by the rank that owns it
+        items     [I_local, d]  this rank's layer-0 item embeddings (read by the peers for the item-item layer)
+        top-k lists  values fp32 [rows, k], indices int64 [rows, k]
+    `PeerExchange.create` returns None when this torch build / box cannot provide it -- the caller then keeps the NCCL
+    formulation."""
+
+    def __init__(self, hdl, buf, n_users, d, n_layers, n_local, rank, world, topk_rows, k):
         self.hdl, self.buf, self.n, self.rank, self.world = hdl, buf, n_users * d, rank, world
-        self.n_layers, self.k, self.topk_rows = n_layers, k, topk_rows
-        self.parts = [buf[l * self.n:(l + 1) * self.n].view(n_users, d) for l in range(n_layers)]
-        self.ptrs = [[int(p) + l * self.n * 4 for p in hdl.buffer_ptrs] for l in range(n_layers)]
-        # top-k lists of the evaluation, one region per user row: values fp32 [rows, k] then indices int64 [rows, k]
-        # (the buffer is fp32-typed; 8-byte alignment of the index region holds because n_layers * n and rows * k are even)
-        self.val_off = n_layers * self.n
+        self.n_layers, self.k, self.topk_rows, self.n_users, self.d, self.n_local = n_layers, k, topk_rows, n_users, d, n_local
+        n = self.n
+        self.parts = [buf[l * n:(l + 1) * n].view(n_users, d) for l in range(n_layers)]
+        self.part_ptrs = [[int(p) + 4 * l * n for p in hdl.buffer_ptrs] for l in range(n_layers)]
+        g0 = n_layers * n
+        self.gath = [buf[g0 + l * n: g0 + (l + 1) * n].view(n_users, d) for l in range(n_layers)]
+        self.gath_ptrs = [[int(p) + 4 * (g0 + l * n) for p in hdl.buffer_ptrs] for l in range(n_layers)]
+        i0 = 2 * n_layers * n
+        self.items = buf[i0: i0 + n_local * d].view(n_local, d)
+        self.item_ptrs = [int(p) + 4 * i0 for p in hdl.buffer_ptrs]
+        # top-k lists of the evaluation (8-byte alignment of the index region: every offset before it is even)
+        self.val_off = i0 + n_local * d + ((n_local * d) & 1)
         self.idx_off = self.val_off + topk_rows * k + ((topk_rows * k) & 1)
+        # this rank's slice of the running layer sum (mmrec_peer_reduce_push_f32: per float4 elements)
+        n4 = n // 4
+        self.per4 = (n4 + world - 1) // world
+        self.lo = min(self.per4 * rank, n4) * 4
+        self.hi = min(self.lo + self.per4 * 4, n)
+        self.acc = torch.empty(self.per4 * 4, dtype=torch.float32, device=buf.device)
+        self._chan = 0
+
+    @staticmethod
+    def words(n_users, d, n_layers, n_local, k):
+        n = n_users * d
+        w = 2 * n_layers * n + n_local * d + ((n_local * d) & 1)
+        w += n_users * k + ((n_users * k) & 1) + 2 * n_users * k
+        return w
 
     def topk_lists(self, row0, nrows):
         """(values, indices) views of this rank's list region for user rows [row0, row0 + nrows), and the peers' raw
@@ -121,55 +171,79 @@ class PeerExchange:
         return v, i, vp, ip
 
     @staticmethod
-    def create(n_users, d, n_layers, device, group=None, k=50):
+    def create(n_users, d, n_layers, n_local, device, group=None, k=50):
         try:
             import torch.distributed._symmetric_memory as symm
             grp = group or dist.group.WORLD
-            n = n_users * d
-            words = n_layers * n + n_users * k + ((n_users * k) & 1) + 2 * n_users * k
-            if (n_layers * n) & 1:
-                return None                                          # (index region would lose its 8-byte alignment)
-            buf = symm.empty(words, dtype=torch.float32, device=device)
+            if (n_users * d) % 4:
+                return None
+            buf = symm.empty(PeerExchange.words(n_users, d, n_layers, n_local, k), dtype=torch.float32, device=device)
             hdl = symm.rendezvous(buf, grp)
             buf.zero_()
-            px = PeerExchange(hdl, buf, n_users, d, n_layers, dist.get_rank(grp), dist.get_world_size(grp), n_users, k)
-            px.barrier(0)
+            px = PeerExchange(hdl, buf, n_users, d, n_layers, n_local, dist.get_rank(grp), dist.get_world_size(grp), n_users, k)
+            px.barrier()
             torch.cuda.synchronize(device)
             return px
         except Exception:                                            # noqa: BLE001
             return None
 
-    def barrier(self, channel):
-        self.hdl.barrier(channel=channel)
+    def barrier(self):
+        """Device-side barrier of all ranks on the current stream.  Successive barriers rotate over the signal channels
+        (every rank issues them in the same order, so a channel is never shared by two barriers in flight)."""
+        self.hdl.barrier(channel=self._chan)
+        self._chan = (self._chan + 1) % 8
 
 
-def propagate_mean_sharded_p2p(a_ui, a_iu, user_emb, item_emb_local, n_layers, px: PeerExchange):
-    """`propagate_mean_sharded` with the all-reduce replaced by this library's kernel over peer memory: the user-side
-    SpMM writes its partial into the symmetric buffer, the item-side SpMM runs while the peers finish theirs, one
-    device barrier, then `mmrec_peer_sum_f32` reads all partials over NVLink and applies the layer-mean epilogue.
-    Same sums in the same (rank) order on every rank."""
+def propagate_mean_sharded_p2p(a_ui, a_iu, user_emb, item_emb_local, n_layers, px: PeerExchange, mm_local=None):
+    """`propagate_mean_sharded` with the all-reduce replaced by this library's kernel over peer memory, in the
+    reduce-scatter + all-gather form: the user-side SpMM writes its partial into the symmetric buffer, the item-side SpMM
+    runs meanwhile on a second stream; barrier; `mmrec_peer_reduce_push_f32` sums THIS rank's 1/world slice of all
+    partials (rank order) and stores it into every rank's reduced table; barrier.  Per layer and rank (world-1)/world of
+    [U, d] is read and as much written over NVLink.  The running layer sum of the users lives sliced (each rank its
+    slice), the final layer stores (acc + sum) / (L + 1) -- the propagated user table -- instead of the sum.
+
+    `mm_local` (FREEDOM's item-item layer, `src/models/freedom.py:166-167,178`): CSR of this rank's rows of mm_adj with
+    rank-major columns (`ItemShard.mm_csr`); the layer-0 item embeddings are gathered from the peers that own them
+    (`mmrec_peer_gather_f32`) and `i_g += mm_adj @ E_I`.  Returns (u_g [U, d] -- a view of the exchange buffer, valid
+    until the next call --, i_g [I_local, d])."""
     from . import ops
     U, d = user_emb.shape
+    dev = user_emb.device
     eu, ei = user_emb, item_emb_local
-    acc_u = user_emb.clone()
     acc_i = item_emb_local.clone()
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    ei_all = None
+    if mm_local is not None:                                         # publish the layer-0 item rows for the peers' gathers
+        px.items.copy_(item_emb_local)
+    ue_flat = user_emb.reshape(-1)
     for l in range(1, n_layers + 1):
         last = l == n_layers
         div = float(n_layers + 1) if last else 1.0
         # the two SpMMs of a layer read only layer l-1: side by side on two streams (fork / join with events, so the pair
         # is also a valid CUDA-graph capture)
-        main = torch.cuda.current_stream()
-        side = _side_stream(user_emb.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             ei_next, acc_i = _cuda_spmm(a_iu, eu, acc_in=acc_i, acc_div=div, want_y=not last)
         ops.spmm_raw(a_ui, ei, Y=px.parts[l - 1])                    # R_g E_Ig -> peer-visible partial of layer l
-        px.barrier(l - 1)                                            # every rank's partial of layer l is complete
-        eu_next = None if last else torch.empty(U, d, dtype=torch.float32, device=user_emb.device)
-        ops.peer_sum(px.ptrs[l - 1], U * d, acc_in=acc_u, acc_out=acc_u, acc_div=div, sum_out=eu_next)
+        px.barrier()                                                 # every rank's partial of layer l is complete
+        if l == 1 and mm_local is not None:                          # (the peers' item rows are published as well)
+            ei_all = torch.empty(px.world * px.n_local, d, dtype=torch.float32, device=dev)
+            ops.peer_gather(px.item_ptrs, px.n_local * d, ei_all)
+        acc_in = ue_flat[px.lo:px.hi] if l == 1 else px.acc
+        ops.peer_reduce_push(px.part_ptrs[l - 1], px.gath_ptrs[l - 1], U * d, px.rank, acc_in=acc_in, acc_out=px.acc, acc_div=div,
+                             final_layer=last)
+        px.barrier()                                                 # every slice of the reduced table has landed
         main.wait_stream(side)
-        eu, ei = eu_next, ei_next
-    return acc_u, acc_i
+        eu, ei = px.gath[l - 1], ei_next
+    u_g = px.gath[n_layers - 1] if n_layers > 0 else user_emb
+    if mm_local is not None:
+        if ei_all is None:                                           # n_layers == 0
+            px.barrier()
+            ei_all = torch.empty(px.world * px.n_local, d, dtype=torch.float32, device=dev)
+            ops.peer_gather(px.item_ptrs, px.n_local * d, ei_all)
+        ops.spmm_raw(mm_local, ei_all, acc_in=acc_i, acc_out=acc_i)  # i_g + mm_adj @ E_I  (freedom.py:178)
+    return u_g, acc_i
 
 
 _side = {}
@@ -182,16 +256,26 @@ def _side_stream(device):
     return _side[key]
 
 
-def score_topk_sharded_p2p(shard: ItemShard, user_e, item_e_local, users, lmask, k, px: PeerExchange, row0, channel):
-    """`score_topk_sharded` without a collective: the fused score+top-k kernel writes this rank's (value, local item)
-    lists straight into peer-mapped memory, one device barrier, then every rank merges all ranks' lists in place
-    (`mmrec_topk_merge_peers`, which also relabels local -> global item ids).  `lmask` is the output of `local_mask`."""
+def merge_rows(B, world, rank):
+    """Rows of a B-row batch that rank `rank` merges: a contiguous slice."""
+    per = (B + world - 1) // world
+    lo = min(per * rank, B)
+    return lo, min(lo + per, B) - lo
+
+
+def score_topk_sharded_p2p(shard: ItemShard, user_e, item_e_local, users, lmask, k, px: PeerExchange, row0, catalog=None):
+    """`score_topk_sharded` without a collective: the fused score+top-k kernels write this rank's (value, local item)
+    lists straight into peer-mapped memory, one device barrier, then every rank merges ITS slice of the batch rows from
+    all ranks' lists (`mmrec_topk_merge_peers`, which also relabels local -> global item ids).  Returns (values, indices,
+    first row, rows) of that slice; `lmask` is the output of `local_mask`."""
     from . import ops
     B = users.numel()
     v, i, vp, ip = px.topk_lists(row0, B)
-    ops.score_topk(user_e, item_e_local, users, lmask, k, out=(v, i))
-    px.barrier(channel)
-    return ops.topk_merge_peers(vp, ip, B, k, user_e.device, idx_mul=shard.world, idx_add=1)
+    ops.score_topk(user_e, item_e_local, users, lmask, k, out=(v, i), catalog=catalog)
+    px.barrier()
+    lo, cnt = merge_rows(B, shard.world, shard.rank)
+    mv, mi = ops.topk_merge_peers(vp, ip, B, k, user_e.device, idx_mul=shard.world, idx_add=1, row0=lo, n_rows=cnt)
+    return mv, mi, lo, cnt
 
 
 def local_mask(shard: ItemShard, mask):
@@ -225,6 +309,55 @@ def score_topk_sharded(shard: ItemShard, user_e, item_e_local, users, mask, k, s
 
 
 # ------------------------------------------------------------------------------------------------------
+# single-GPU comparison of the sharded result (the correctness oracle for multi-GPU = the 1-GPU kernels)
+# ------------------------------------------------------------------------------------------------------
+def parity_vs_single_gpu(wl, shard, u_g, i_g, eval_out, batches, kr, kc, kv, n_layers, k, dev):
+    """Every rank recomputes the whole (unsharded) problem with the single-GPU kernels on its own device and compares:
+    user table and its item shard (relative error, bar 1e-4), and its slice of every batch's merged top-k (index
+    mismatches must be near ties under an fp64 re-score of the single-GPU embeddings).  Returns a dict of plain numbers,
+    reduced over ranks (max of errors, sum of counts)."""
+    from . import graph, ops
+    from .ops import CSR
+    U, I = wl.U, wl.I
+    adj = graph.build_norm_adj((wl.tr_u, wl.tr_i), U, I, dev)
+    ego = torch.from_numpy(np.concatenate([wl.user_emb, wl.item_emb])).to(dev)
+    all_emb = ops.propagate_mean(adj, ego, n_layers)
+    u_ref, i_ref = all_emb[:U], all_emb[U:]
+    if kr is not None:
+        mm = CSR.from_coo(torch.from_numpy(kr).to(dev), torch.from_numpy(kc).to(dev), torch.from_numpy(kv).to(dev), I, I)
+        i_ref = ops.spmm(mm, ego[U:], base=i_ref)
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+    u_err = rel(u_g, u_ref)
+    i_err = rel(i_g, i_ref[torch.from_numpy(shard.local_items).to(dev)])
+    rows = mism = non_tie = 0
+    i64 = i_ref.double()
+    for (users, mask, _), (mv, mi, lo, cnt) in zip(batches, eval_out):
+        if cnt == 0:
+            continue
+        us = users[lo:lo + cnt]
+        sel = (mask[0] >= lo) & (mask[0] < lo + cnt)
+        m = torch.stack([mask[0][sel] - lo, mask[1][sel]])
+        _, ref_idx = ops.score_topk(u_ref, i_ref, us, m, k)
+        rows += cnt
+        bad = (ref_idx != mi).any(dim=1).nonzero().flatten()
+        mism += int(bad.numel())
+        if bad.numel():                                             # near-tie rule on an fp64 re-score of the reference embeddings
+            s = u_ref[us[bad]].double() @ i64.t()
+            scale = s.abs().max().item()
+            got, want = s.gather(1, mi[bad]), s.gather(1, ref_idx[bad])
+            non_tie += int(((got - want).abs().max(dim=1).values > 4e-6 * scale).sum().item())
+    t = torch.tensor([u_err, i_err], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c = torch.tensor([rows, mism, non_tie], device=dev, dtype=torch.float64)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    u_err, i_err = t.tolist()
+    rows, mism, non_tie = [int(x) for x in c.tolist()]
+    return {"vs": "single-GPU kernels on the unsharded problem (every rank, own device)", "user_emb_rel_err": u_err,
+            "item_emb_rel_err": i_err, "topk_rows_checked": rows, "topk_rows_with_index_mismatch": mism,
+            "topk_rows_beyond_near_tie": non_tie, "ok": bool(u_err < 1e-4 and i_err < 1e-4 and non_tie == 0 and rows > 0)}
+
+
+# ------------------------------------------------------------------------------------------------------
 # bench driver for N > 1 (weak scaling: every rank keeps 7,000 items and ~160k edges as N grows)
 # ------------------------------------------------------------------------------------------------------
 def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
@@ -234,6 +367,8 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     U, I, d = wl.U, wl.I, wl.d
     shard = ItemShard(wl.tr_u, wl.tr_i, U, I, rank, world)
     a_ui, a_iu = shard.csrs(dev)
+    kr, kc, kv = wl.knn_coo()
+    mm_local = shard.mm_csr(kr, kc, kv, dev)                        # FREEDOM's item-item layer: this rank's rows, rank-major columns
     ue = torch.from_numpy(wl.user_emb).to(dev)
     ie = torch.from_numpy(wl.item_emb[shard.local_items]).to(dev)
     batches = []
@@ -242,38 +377,51 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
         m = torch.from_numpy(wl.eval_mask(lo, hi)).to(dev)
         batches.append((torch.arange(lo, hi, device=dev), m, local_mask(shard, m)))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    edges_local = wl.n_layers * 2 * shard.nnz
+    edges_local = wl.n_layers * 2 * shard.nnz + mm_local.nnz
     ev = lambda: torch.cuda.Event(enable_timing=True)
     tA = tC = 0.0
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     state = {}
 
-    px = None if os.environ.get("MMREC_EXCHANGE", "p2p") == "nccl" else PeerExchange.create(U, d, wl.n_layers, dev)
+    px = None if os.environ.get("MMREC_EXCHANGE", "p2p") == "nccl" else PeerExchange.create(U, d, wl.n_layers, shard.n_local, dev, k=TOPK)
     have = torch.tensor([1.0 if px is not None else 0.0], device=dev)
     dist.all_reduce(have, op=dist.ReduceOp.MIN)
     if have.item() == 0.0:
         px = None
-    exchange = ("mmrec_peer_sum_f32 / mmrec_topk_merge_peers over symmetric memory (P2P loads), no collective on the data path"
-                if px is not None else "NCCL all-reduce + all-gather")
+    exchange = ("mmrec_peer_reduce_push_f32 (reduce-scatter + all-gather over symmetric memory: each rank sums its 1/N slice of the partials "
+                "and stores it to every peer), mmrec_peer_gather_f32 for the item-item layer, mmrec_topk_merge_peers on 1/N of the rows; "
+                "no NCCL collective on the data path" if px is not None else "NCCL all-reduce + all-gather")
 
     def prop(u_in, i_in):
         if px is not None:
-            return propagate_mean_sharded_p2p(a_ui, a_iu, u_in, i_in, wl.n_layers, px)
-        return propagate_mean_sharded(a_ui, a_iu, u_in, i_in, wl.n_layers)
+            return propagate_mean_sharded_p2p(a_ui, a_iu, u_in, i_in, wl.n_layers, px, mm_local=mm_local)
+        u, i = propagate_mean_sharded(a_ui, a_iu, u_in, i_in, wl.n_layers)
+        return u, mm_layer_sharded(shard, mm_local, i_in, i)
 
     def sec_a():
         return prop(ue, ie)
 
-    def score_batch(bi, u_g, i_g, users, lm):
+    def score_batch(bi, u_g, i_g, users, lm, cat=None):
         if px is not None:
-            return score_topk_sharded_p2p(shard, u_g, i_g, users, lm, TOPK, px, bi * EVAL_BATCH, wl.n_layers + bi % 4)
-        return score_topk_sharded(shard, u_g, i_g, users, lm, TOPK, mask_is_local=True)
+            return score_topk_sharded_p2p(shard, u_g, i_g, users, lm, TOPK, px, bi * EVAL_BATCH, catalog=cat)
+        v, i = score_topk_sharded(shard, u_g, i_g, users, lm, TOPK, mask_is_local=True)
+        return v, i, 0, users.numel()
 
     def sec_c():
-        return [score_batch(bi, state["u"], state["i"], users, lm) for bi, (users, _, lm) in enumerate(batches)]
+        cat = ops.Catalog(state["i"])                               # the shard's item operand: packed once per evaluation
+        return [score_batch(bi, state["u"], cat.item_e, users, lm, cat) for bi, (users, _, lm) in enumerate(batches)]
 
-    # Both sections (kernels of 5-70 us, NCCL collectives included) are captured once into CUDA graphs and replayed,
-    # as in the single-GPU arm; if this torch/NCCL build refuses to capture a collective the arm runs them eagerly.
+    # ---- parity first: the sharded result against the single-GPU kernels, on every rank
+    with torch.no_grad():
+        state["u"], state["i"] = sec_a()
+        out_c = sec_c()
+        torch.cuda.synchronize(); dist.barrier()
+        parity = parity_vs_single_gpu(wl, shard, state["u"], state["i"], out_c, batches, kr, kc, kv, wl.n_layers, TOPK, dev)
+        del out_c
+    torch.cuda.synchronize(); dist.barrier()
+
+    # Both sections (kernels of 5-70 us, barriers / collectives included) are captured once into CUDA graphs and replayed,
+    # as in the single-GPU arm; if this torch/NCCL build refuses to capture something the arm runs them eagerly.
     graphs, n_launch, mode = {}, {"a": 0, "c": 0}, "cuda graphs"
     side = torch.cuda.Stream()
     with torch.cuda.stream(side), torch.no_grad():
@@ -324,17 +472,15 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             if step >= args.warmup:
                 tA += e[0].elapsed_time(e[1]); tC += e[2].elapsed_time(e[3])
                 launches += (n_launch["a"] + n_launch["c"]) if graphs else ops.launch_count() - l0
-    u_g, i_g = state["u"], state["i"]
-    launches0, launches1 = 0, launches
     dist.barrier()
-    # ---- e2e
     # ---- e2e: the same calls with pinned HOST buffers, copies inside the timed region
     ue_h = torch.from_numpy(wl.user_emb).pin_memory()
     ie_h = torch.from_numpy(wl.item_emb[shard.local_items]).pin_memory()
     out_u = torch.empty(U, d).pin_memory(); out_i = torch.empty(shard.n_local, d).pin_memory()
     users_h = [b[0].cpu().pin_memory() for b in batches]
     masks_h = [b[2].cpu().pin_memory() for b in batches]             # this rank's share of the mask
-    out_idx = [torch.empty(b[0].numel(), TOPK, dtype=torch.int64).pin_memory() for b in batches]
+    out_idx = [torch.empty(merge_rows(b[0].numel(), world, rank)[1] if px is not None else b[0].numel(), TOPK, dtype=torch.int64).pin_memory()
+               for b in batches]
     eA = eC = 0.0
     with torch.no_grad():
         for step in range(args.warmup + args.steps):
@@ -347,9 +493,10 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             out_u.copy_(u_g, non_blocking=True); out_i.copy_(i_g, non_blocking=True)
             e[1].record()
             e[2].record()
+            cat = ops.Catalog(i_g)
             for bi, (uh, mh, oh) in enumerate(zip(users_h, masks_h, out_idx)):
-                _, idx = score_batch(bi, u_g, i_g, uh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True))
-                oh.copy_(idx, non_blocking=True)
+                res = score_batch(bi, u_g, cat.item_e, uh.to(dev, non_blocking=True), mh.to(dev, non_blocking=True), cat)
+                oh.copy_(res[1], non_blocking=True)
             e[3].record()
             torch.cuda.synchronize()
             if step >= args.warmup:
@@ -359,43 +506,52 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     d2h = (out_u.numel() + out_i.numel()) * 4 + sum(o.numel() * 8 for o in out_idx)
     t = torch.tensor([tA, tC, eA, eC], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)                          # device time of the slowest rank
-    e_all = torch.tensor([float(edges_local), float(launches1 - launches0)], device=dev, dtype=torch.float64)
-    dist.all_reduce(e_all, op=dist.ReduceOp.SUM)                      # units processed / kernels launched by all ranks
+    e_all = torch.tensor([float(edges_local), float(launches), float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+    dist.all_reduce(e_all, op=dist.ReduceOp.SUM)                      # units processed / kernels launched / bytes copied by all ranks
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         K = args.steps
         msA, msC = t[0].item() / K, t[1].item() / K
         edges = e_all[0].item()
         pk = peaks()
-        algo_bytes = wl.n_layers * (a_ui.algorithmic_bytes(d) + a_iu.algorithmic_bytes(d)) * world
+        algo_bytes = (wl.n_layers * (a_ui.algorithmic_bytes(d) + a_iu.algorithmic_bytes(d)) + mm_local.algorithmic_bytes(d)) * world
+        nvl_bytes = wl.n_layers * 2 * (world - 1) / world * U * d * 4 + (world - 1) * shard.n_local * d * 4   # per rank: slices read + pushed, item rows gathered
         print(json.dumps({
             "metric": "graph-prop edges/sec (+ full-catalog scored-items/sec in extra) @ d=64",
             "value": edges / (msA * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": msA + msC, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"FREEDOM synthetic {wl.name} x{world} items: {U} users, {I} items ({I // world} per GPU), "
-                                   f"{len(wl.tr_u)} train edges, d={d}, {wl.n_layers} UI layers, top-{TOPK} over all users",
+                                   f"{len(wl.tr_u)} train edges, d={d}, {wl.n_layers} UI layers + 1 mm layer, top-{TOPK} over all users, "
+                                   f"eval batch {EVAL_BATCH}",
                        "l2": "flushed (512 MiB write) before every step",
-                       "parallelism": f"item-sharded x{world}: all-reduce of user embeddings per layer, top-k all-gather + merge",
+                       "parallelism": f"item-sharded x{world}: per layer reduce-scatter + all-gather of the user table, item rows gathered once "
+                                      f"for the item-item layer, per-user top-k merge on 1/{world} of the rows per rank",
                        "launch": mode, "user_exchange": exchange},
-            "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U * I / (msC * 1e-3)},
-            "roofline": {"kernel": "spmm_vec_kernel<64> (per rank: 2 per layer)", "bound": "hbm",
+            "parity": parity,
+            "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U * I / (msC * 1e-3),
+                      "nvlink_bytes_per_rank_per_step_prop": nvl_bytes,
+                      "limiting_collective": "per-layer user-table exchange (2 device barriers + (N-1)/N of [U, d] read and written per rank)"},
+            "roofline": {"kernel": "spmm_vec_kernel<64> (per rank: 2 per UI layer + 1 item-item layer)", "bound": "hbm",
                          "achieved": algo_bytes / (msA * 1e-3) / 1e9 / world, "peak": pk["hbm_gbs"], "unit": "GB/s per GPU",
                          "frac": algo_bytes / (msA * 1e-3) / 1e9 / world / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
-                         "note": "includes the per-layer NCCL all-reduce of the [U,d] user partials"},
+                         "note": "time includes the per-layer exchange of the user table over NVLink (peer memory), see extra"},
             "gpu_launches": int(e_all[1].item()), "clocks": clocks,
-            "e2e": {"value": edges / (t[2].item() / K * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(h2d) * world,
-                    "d2h_bytes_per_step": int(d2h) * world, "prop_ms": t[2].item() / K, "score_topk_ms": t[3].item() / K,
+            "e2e": {"value": edges / (t[2].item() / K * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(e_all[2].item()),
+                    "d2h_bytes_per_step": int(e_all[3].item()), "prop_ms": t[2].item() / K, "score_topk_ms": t[3].item() / K,
                     "scored_items_per_sec": U * I / (t[3].item() / K * 1e-3)},
         }))
-    # Shut down: the captured graphs hold NCCL work, drop them before the process group; a watchdog guarantees the
-    # exit (rank 0 has printed its line) should the teardown of this torch/NCCL build block.
-    import sys, threading
+    # Shut down in order: the captured graphs hold the barrier / collective work, drop them before the process group.  The
+    # daemon timer only fires if the teardown of this torch/NCCL build blocks (rank 0 has printed its line by then).
+    import sys
+    import threading
     sys.stdout.flush()
     graphs = None
     state.clear()
     torch.cuda.synchronize()
     dist.barrier()
-    threading.Timer(20.0, lambda: os._exit(0)).start()
+    watchdog = threading.Timer(30.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
     dist.destroy_process_group()
-    os._exit(0)
+    watchdog.cancel()

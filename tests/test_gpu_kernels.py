@@ -426,9 +426,74 @@ def test_topk_merge_peers_matches_contiguous_merge(dev, world, B, k):
     g = torch.Generator().manual_seed(world * 1000 + B)
     vals = torch.sort((torch.randint(0, 40, (world, B, k), generator=g).float() / 8.0), dim=-1, descending=True).values   # many ties
     idx = torch.stack([torch.stack([torch.randperm(5000, generator=g)[:k] for _ in range(B)]) for _ in range(world)])
+    for p in range(world):                                  # input contract: equal values inside a list come in ascending index order
+        for b in range(B):
+            for x in vals[p, b].unique():
+                sel = (vals[p, b] == x).nonzero().flatten()
+                idx[p, b, sel] = torch.sort(idx[p, b, sel]).values
     vd = [vals[p].contiguous().to(dev) for p in range(world)]
     idd = [idx[p].contiguous().to(dev) for p in range(world)]
     v1, i1 = ops.topk_merge_peers([t.data_ptr() for t in vd], [t.data_ptr() for t in idd], B, k, dev, idx_mul=world, idx_add=1)
     glob = torch.stack([idd[p] * world + p for p in range(world)])
     v2, i2 = ops.topk_merge(torch.stack(vd), glob)
     assert torch.equal(v1, v2) and torch.equal(i1, i2)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_peer_reduce_push_equals_peer_sum(dev, world):
+    """mmrec_peer_reduce_push_f32 on one device, the `world` ranks played in turn: every rank sums its slice in rank order and
+    stores it into every destination, so after all ranks ran every destination holds the rank-order sum (bit-identical to
+    mmrec_peer_sum_f32), and the sliced accumulator reproduces the layer-mean epilogue."""
+    from mmrec_b200 import ops
+    g = torch.Generator(device=dev); g.manual_seed(10 + world)
+    n = 4 * 1531                                            # not a multiple of world * 4: ragged last slice
+    parts = [torch.randn(n, device=dev, generator=g) for _ in range(world)]
+    acc0 = torch.randn(n, device=dev, generator=g)
+    ref = parts[0].clone()
+    for p in parts[1:]:
+        ref = ref + p
+    per = ((n // 4 + world - 1) // world) * 4
+    for final in (False, True):
+        dst = [torch.full((n,), float("nan"), device=dev) for _ in range(world)]
+        accs = []
+        for r in range(world):
+            lo, hi = min(per * r, n), min(per * r + per, n)
+            acc = torch.zeros(per, device=dev)
+            ops.peer_reduce_push([p.data_ptr() for p in parts], [t.data_ptr() for t in dst], n, r, acc_in=acc0[lo:hi].contiguous(),
+                                 acc_out=acc, acc_div=4.0, final_layer=final)
+            accs.append((lo, hi, acc))
+        want = (acc0 + ref) / 4.0 if final else ref
+        for t in dst:
+            assert torch.equal(t, want)
+        if not final:
+            for lo, hi, acc in accs:
+                assert torch.equal(acc[:hi - lo], (acc0 + ref)[lo:hi])
+
+
+def test_peer_gather_and_row_range_merge(dev):
+    from mmrec_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    world, n_each = 3, 4 * 77
+    src = [torch.randn(n_each, generator=g).to(dev) for _ in range(world)]
+    dst = torch.empty(world * n_each, device=dev)
+    ops.peer_gather([t.data_ptr() for t in src], n_each, dst)
+    assert torch.equal(dst, torch.cat(src))
+    # merge of a row range == the same rows of the full merge
+    B, k = 37, 20
+    vals = torch.sort(torch.randint(0, 30, (world, B, k), generator=g).float() / 4.0, dim=-1, descending=True).values
+    idx = torch.stack([torch.stack([torch.sort(torch.randperm(900, generator=g)[:k]).values for _ in range(B)]) for _ in range(world)])
+    # (within a list equal values must come in ascending index order: sort the indices inside runs of equal values)
+    for p in range(world):
+        for b in range(B):
+            v = vals[p, b]
+            for x in v.unique():
+                sel = (v == x).nonzero().flatten()
+                idx[p, b, sel] = torch.sort(idx[p, b, sel]).values
+    vd = [vals[p].contiguous().to(dev) for p in range(world)]
+    idd = [idx[p].contiguous().to(dev) for p in range(world)]
+    fv, fi = ops.topk_merge_peers([t.data_ptr() for t in vd], [t.data_ptr() for t in idd], B, k, dev, idx_mul=world, idx_add=1)
+    rv, ri = ops.topk_merge_peers([t.data_ptr() for t in vd], [t.data_ptr() for t in idd], B, k, dev, idx_mul=world, idx_add=1, row0=11, n_rows=9)
+    assert torch.equal(rv, fv[11:20]) and torch.equal(ri, fi[11:20])
+    glob = torch.stack([idd[p] * world + p for p in range(world)])
+    v2, i2 = ops.topk_merge(torch.stack(vd), glob)
+    assert torch.equal(fv, v2) and torch.equal(fi, i2)
