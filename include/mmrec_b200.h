@@ -228,6 +228,18 @@ int mmrec_peer_reduce_push_f32(int64_t n, int world, int rank, const void* const
                                const float* acc_in, float* acc_out, float acc_div, int final_layer, void* stream);
 int mmrec_peer_gather_f32(int64_t n_each, int world, const void* const* src, float* dst, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * f2  evaluator on the device.   Replaces the host loop that builds the hit matrix from `.cpu().numpy()` of the index
+ * matrix and the metric functions (src/utils/topk_evaluator.py:70-102, src/utils/metrics.py:12-105).
+ *   topk_idx  int64 [n_users, K]  the trainer's index matrix (K = max(topk) <= 128)
+ *   pos_ptr   int64 [n_users + 1], pos_items int64 sorted ascending per user: the ground-truth items
+ *   disc      float64 [K] = 1 / log2(j + 2);  idcg_all float64 [K] = cumsum(disc)      (computed by the host, as numpy does)
+ *   sums      float64 [4, K], ADDED to: per position j the sum over users of recall / ndcg / precision / map at j + 1
+ *             (zero it before the first batch; divide by the number of users afterwards)
+ * ------------------------------------------------------------------------------------------- */
+int mmrec_topk_metrics_f64(int64_t n_users, int K, const int64_t* topk_idx, const int64_t* pos_ptr, const int64_t* pos_items,
+                           const double* disc, const double* idcg_all, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

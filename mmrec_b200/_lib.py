@@ -49,6 +49,7 @@ PROTOTYPES = {
     "mmrec_topk_merge_peers": (_i32, [_i32, _i64, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "mmrec_peer_reduce_push_f32": (_i32, [_i64, _i32, _i32, _p, _p, _p, _p, _f32, _i32, _p]),
     "mmrec_peer_gather_f32": (_i32, [_i64, _i32, _p, _p, _p]),
+    "mmrec_topk_metrics_f64": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "mmrec_peer_sum_f32": (_i32, [_i64, _i32, _p, _p, _p, _f32, _p, _p]),
 }
 

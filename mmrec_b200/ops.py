@@ -511,6 +511,20 @@ def peer_gather(src_ptrs, n_each, dst: torch.Tensor):
     return dst
 
 
+def topk_metric_sums(topk_idx: torch.Tensor, pos_ptr: torch.Tensor, pos_items: torch.Tensor, disc: torch.Tensor, idcg_all: torch.Tensor,
+                     sums: torch.Tensor):
+    """f2: adds, per position j < K, the sum over the rows of `topk_idx` of recall / ndcg / precision / map at j + 1 to `sums`
+    [4, K] float64 (`mmrec_topk_metrics_f64`; src/utils/topk_evaluator.py:70-102 + src/utils/metrics.py:12-105 on the device)."""
+    _need_cuda(topk_idx, pos_ptr, pos_items, disc, idcg_all, sums)
+    lib = _lib.load()
+    n, K = topk_idx.shape
+    assert topk_idx.dtype == torch.int64 and topk_idx.is_contiguous() and pos_ptr.dtype == torch.int64 and pos_items.dtype == torch.int64
+    assert sums.dtype == torch.float64 and sums.shape == (4, K) and sums.is_contiguous() and disc.dtype == torch.float64
+    check(lib.mmrec_topk_metrics_f64(n, K, _ptr(topk_idx), _ptr(pos_ptr), _ptr(pos_items), _ptr(disc), _ptr(idcg_all), _ptr(sums),
+                                     _stream()), "mmrec_topk_metrics_f64")
+    return sums
+
+
 def bipartite_norm(users: torch.Tensor, items: torch.Tensor, n_users: int, n_items: int, eps: float = 1e-7) -> torch.Tensor:
     """fp32 1/sqrt((d_u+eps)(d_i+eps)) per edge, as `_normalize_adj_m` (`src/models/freedom.py:145-154`)."""
     _need_cuda(users, items)

@@ -65,7 +65,40 @@ class TopKEvaluator(object):
             if k <= 0:
                 raise ValueError("topk must be a positive integer or a list of positive integers, but get `{}`".format(k))
 
+    def _evaluate_on_device(self, batch_matrix_list, eval_data):
+        """f2: the hit matrix and the metric sums are computed where the index matrix lives (`mmrec_topk_metrics_f64`);
+        4 x K float64 sums come back instead of the [n_users, K] matrix.  `recall2` (a ratio of sums over users) and
+        K > 128 take the host route."""
+        from .. import ops
+        dev = batch_matrix_list[0].device
+        cache = getattr(eval_data, "_pos_csr_dev", None)
+        if cache is None or cache[0] != dev:
+            pos = eval_data.get_eval_items()
+            lens = np.array([len(p) for p in pos], dtype=np.int64)
+            ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            items = np.concatenate([np.sort(np.asarray(p, dtype=np.int64)) for p in pos]) if len(pos) else np.zeros(0, np.int64)
+            cache = (dev, torch.from_numpy(ptr).to(dev), torch.from_numpy(items).to(dev))
+            eval_data._pos_csr_dev = cache
+        _, ptr, items = cache
+        K = batch_matrix_list[0].shape[1]
+        disc = 1.0 / np.log2(np.arange(1, K + 1) + 1.0)
+        disc_d, idcg_d = torch.from_numpy(disc).to(dev), torch.from_numpy(np.cumsum(disc)).to(dev)
+        sums = torch.zeros(4, K, dtype=torch.float64, device=dev)
+        row = 0
+        for m in batch_matrix_list:
+            m = m.contiguous()
+            ops.topk_metric_sums(m, ptr[row:row + m.shape[0] + 1], items, disc_d, idcg_d, sums)
+            row += m.shape[0]
+        assert row == ptr.numel() - 1
+        mean = (sums / row).cpu().numpy()
+        rows = {"recall": 0, "ndcg": 1, "precision": 2, "map": 3}
+        return {"{}@{}".format(m, k): round(float(mean[rows[m], k - 1]), 4) for m in self.metrics for k in self.topk}
+
     def evaluate(self, batch_matrix_list, eval_data, is_test=False, idx=0):
+        if (len(batch_matrix_list) and batch_matrix_list[0].is_cuda and batch_matrix_list[0].shape[1] <= 128
+                and all(m in ("recall", "ndcg", "precision", "map") for m in self.metrics)
+                and self.config["device_evaluator"] is not False):
+            return self._evaluate_on_device(batch_matrix_list, eval_data)
         pos_items = eval_data.get_eval_items()
         pos_len = np.asarray(eval_data.get_eval_len_list())
         topk_index = torch.cat(batch_matrix_list, dim=0).cpu().numpy()

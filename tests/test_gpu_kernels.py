@@ -497,3 +497,48 @@ def test_peer_gather_and_row_range_merge(dev):
     glob = torch.stack([idd[p] * world + p for p in range(world)])
     v2, i2 = ops.topk_merge(torch.stack(vd), glob)
     assert torch.equal(fv, v2) and torch.equal(fi, i2)
+
+
+def test_device_evaluator_matches_host_metrics(dev):
+    """f2: mmrec_topk_metrics_f64 (hit matrix + Recall / NDCG / Precision / MAP sums on the device) against the numpy
+    implementation of the reference's metric definitions (mmrec_b200/utils/topk_evaluator.py, pinned to the reference's
+    numbers by tests/test_oracle_golden.py)."""
+    from mmrec_b200.utils import topk_evaluator as TE
+
+    class Loader:
+        def __init__(self, pos):
+            self.pos = pos
+
+        def get_eval_items(self):
+            return self.pos
+
+        def get_eval_len_list(self):
+            return np.array([len(p) for p in self.pos], dtype=np.int64)
+
+    rng = np.random.default_rng(0)
+    n, I, K = 3001, 900, 50
+    pos = [rng.choice(I, size=rng.integers(1, 70), replace=False).astype(np.int64) for _ in range(n)]
+    topk = np.stack([rng.permutation(I)[:K] for _ in range(n)]).astype(np.int64)
+    for u in range(0, n, 7):                                # some users with many hits, some with a full list of hits
+        h = min(len(pos[u]), K)
+        topk[u, :h] = pos[u][:h]
+    cfg = {"metrics": ["Recall", "NDCG", "Precision", "MAP"], "topk": [5, 10, 20, 50], "device_evaluator": None}
+    ev = TE.TopKEvaluator(cfg)
+    batches = [torch.from_numpy(topk[lo:lo + 1024]).to(dev) for lo in range(0, n, 1024)]
+    got = ev.evaluate(batches, Loader(pos))
+    want = ev.evaluate([b.cpu() for b in batches], Loader(pos))
+    assert got.keys() == want.keys()
+    for key in want:
+        assert abs(got[key] - want[key]) <= 1.0001e-4, (key, got[key], want[key])      # both rounded to 4 decimals
+    # un-rounded: float64 sums in a different order
+    from mmrec_b200 import ops
+    hit = TE.hit_matrix(topk, pos)
+    pos_len = np.array([len(p) for p in pos])
+    disc = 1.0 / np.log2(np.arange(1, K + 1) + 1.0)
+    ptr = torch.from_numpy(np.concatenate([[0], np.cumsum(pos_len)])).to(dev)
+    items = torch.from_numpy(np.concatenate([np.sort(p) for p in pos])).to(dev)
+    sums = torch.zeros(4, K, dtype=torch.float64, device=dev)
+    ops.topk_metric_sums(torch.from_numpy(topk).to(dev), ptr, items, torch.from_numpy(disc).to(dev), torch.from_numpy(np.cumsum(disc)).to(dev), sums)
+    mean = (sums / n).cpu().numpy()
+    for row, fn in enumerate((TE.recall_, TE.ndcg_, TE.precision_, TE.map_)):
+        np.testing.assert_allclose(mean[row], fn(hit, pos_len), rtol=1e-12, atol=1e-14)
