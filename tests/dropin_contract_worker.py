@@ -1,0 +1,122 @@
+"""Worker of tests/test_dropin_contract.py (own process: it imports the UNMODIFIED reference from /root/reference/src).
+
+INTEGRATION.md section 2 claims that `mmrec_b200.models.FREEDOM` is a drop-in under the reference's own `quick_start` /
+`Trainer` / dataloaders.  This proves the claim without a GPU: the reference's Config, RecDataset, TrainDataLoader,
+EvalDataLoader and Trainer are built exactly as `src/utils/quick_start.py:26-74` builds them, the model class is OURS, and the
+kernels behind `mmrec_b200.ops` are replaced by oracle-backed CPU stand-ins (test infrastructure: the product has no CPU
+path).  `Trainer.evaluate` (the reference's: full_sort_predict -> in-place mask -> torch.topk -> its own TopKEvaluator) must
+return the metrics recorded from the reference's own model, and one `calculate_loss` through `Trainer._train_epoch`'s call
+path must return the recorded loss."""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+class CpuCSR:
+    """Stand-in for ops.CSR: a coalesced torch sparse matrix on the CPU."""
+
+    def __init__(self, t, symmetric=False):
+        self.t_, self.n_rows, self.n_cols, self.nnz, self.symmetric = t, t.shape[0], t.shape[1], t._nnz(), symmetric
+
+    @staticmethod
+    def from_coo(row, col, val, n_rows, n_cols, sum_duplicates=True, symmetric=False, seg=None, light_max=None):
+        val = torch.ones(row.numel(), dtype=torch.float32) if val is None else val.to(torch.float32)
+        t = torch.sparse_coo_tensor(torch.stack([row.to(torch.int64), col.to(torch.int64)]), val, (n_rows, n_cols))
+        return CpuCSR(t.coalesce() if sum_duplicates else t.coalesce(), symmetric)
+
+    @staticmethod
+    def from_torch_sparse(t, symmetric=False):
+        return CpuCSR(t.coalesce(), symmetric)
+
+    def coo(self):
+        i = self.t_.indices()
+        return i[0], i[1], self.t_.values()
+
+    def t(self):
+        return self if self.symmetric else CpuCSR(self.t_.t().coalesce())
+
+
+def install_cpu_ops():
+    from oracle import mmrec_oracle as O
+    from mmrec_b200 import graph, ops
+    ops.CSR = graph.CSR = CpuCSR
+    ops.propagate_mean = lambda A, ego, n_layers: O.propagate_mean(A.t_, ego, n_layers)
+    ops.spmm = lambda A, X, base=None: torch.sparse.mm(A.t_, X) if base is None else base + torch.sparse.mm(A.t_, X)
+    ops.project = lambda table, weight, bias=None, idx=None, l2_normalize=False: O.project(table, weight, bias, idx=idx, l2_normalize=l2_normalize)
+    ops.score = lambda u, i, users=None: O.full_sort_scores(u, i, users if users is not None else torch.arange(u.shape[0]))
+
+    def bipartite_norm(users, items, n_users, n_items, eps=1e-7):
+        return O.normalize_adj_m(torch.stack([users, items]), n_users, n_items)
+    ops.bipartite_norm = bipartite_norm
+
+
+def main():
+    import ref_loader
+    from mmrec_b200.utils import synth
+    ref_loader.install()
+    tmp = tempfile.mkdtemp(prefix="mmrec_contract_")
+    data = ref_loader.run_dir(tmp)
+    u, i, e, d, f = synth.SHAPES["tiny"]
+    g = synth.make_graph(u, i, e, seed=0)
+    v, t = synth.make_features(i, f, seed=1)
+    synth.write_dataset(data, "tiny", g, v, t)
+    # --- the reference's own harness (src/utils/quick_start.py:26-74)
+    from utils.configurator import Config
+    from utils.dataset import RecDataset
+    from utils.dataloader import TrainDataLoader, EvalDataLoader
+    from utils.utils import init_seed
+    from common.trainer import Trainer
+    config = Config("FREEDOM", "tiny", {"gpu_id": 0, "use_gpu": False, "n_ui_layers": 3})
+    config["inter_file_name"] = "tiny.inter"
+    config["USER_ID_FIELD"], config["ITEM_ID_FIELD"] = "userID", "itemID"
+    config["vision_feature_file"], config["text_feature_file"] = "image_feat.npy", "text_feat.npy"
+    for k in config["hyper_parameters"]:
+        if isinstance(config[k], list):
+            config[k] = config[k][0]
+    dataset = RecDataset(config)
+    str(dataset)
+    tr, va, te = dataset.split()
+    str(tr), str(va), str(te)
+    train_data = TrainDataLoader(config, tr, batch_size=config["train_batch_size"], shuffle=True)
+    valid_data = EvalDataLoader(config, va, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    test_data = EvalDataLoader(config, te, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    init_seed(config["seed"])
+    train_data.pretrain_setup()
+    # --- OUR model class, the way utils.get_model would return it from src/models/freedom.py
+    install_cpu_ops()
+    from mmrec_b200.models.freedom import FREEDOM
+    model = FREEDOM(config, train_data).to(config["device"])
+    gold = np.load(os.path.join(HERE, "golden", "freedom_tiny.npz"), allow_pickle=True)
+    sd = model.state_dict()
+    init_identical = all(np.array_equal(sd[k[len("param0."):]].numpy(), gold[k]) for k in gold.files if k.startswith("param0."))
+    trainer = Trainer(config, model)
+    valid = trainer.evaluate(valid_data)
+    test = trainer.evaluate(test_data, is_test=True)
+    names = [str(x) for x in gold["metric_names"]]
+    want_valid = dict(zip(names, [float(x) for x in gold["metric_values"]]))
+    want_test = dict(zip(names, [float(x) for x in gold["test_metric_values"]]))
+    # --- one loss through the call the reference's _train_epoch makes (src/common/trainer.py:147-153), on the recorded batch
+    from mmrec_b200 import graph
+    model.train()
+    model.masked_adj = model.pruner.adj_from_keep(torch.from_numpy(gold["prune_keep_idx"]))
+    loss = model.calculate_loss(torch.from_numpy(gold["batch"]))
+    loss = sum(loss) if isinstance(loss, tuple) else loss
+    loss.backward()                                                 # autograd-connected to the parameters (the optimiser steps on them)
+    has_grads = all(p.grad is not None for p in model.parameters())
+    out = {"init_identical": bool(init_identical), "valid": {k: float(v) for k, v in valid.items()}, "want_valid": want_valid,
+           "test": {k: float(v) for k, v in test.items()}, "want_test": want_test, "loss": float(loss.item()),
+           "want_loss": float(np.asarray(gold["loss"]).sum()), "has_grads": bool(has_grads)}
+    print("CONTRACT " + json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

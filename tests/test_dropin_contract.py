@@ -1,0 +1,28 @@
+"""INTEGRATION.md section 2, executed: our FREEDOM class under the REFERENCE's own Config / RecDataset / dataloaders / Trainer
+(imported unmodified from /root/reference/src), kernels replaced by oracle-backed CPU stand-ins.  Runs in the build
+container only (the GPU box has no /root/reference)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+def test_our_model_class_under_the_reference_trainer():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_contract_worker.py")], capture_output=True, text=True,
+                         timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("CONTRACT ")]
+    assert out.returncode == 0 and lines, out.stdout[-3000:] + out.stderr[-3000:]
+    r = json.loads(lines[-1][len("CONTRACT "):])
+    assert r["init_identical"], "init_seed(999) must reproduce the reference's initial weights under the reference's harness"
+    assert r["valid"].keys() == r["want_valid"].keys()
+    for k, v in r["want_valid"].items():
+        assert abs(r["valid"][k] - v) < 1e-9, (k, r["valid"][k], v)
+    for k, v in r["want_test"].items():
+        assert abs(r["test"][k] - v) < 1e-9, (k, r["test"][k], v)
+    assert abs(r["loss"] - r["want_loss"]) <= 1e-5 * abs(r["want_loss"])
+    assert r["has_grads"]
