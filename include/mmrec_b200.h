@@ -195,10 +195,12 @@ int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, const int64
  * arrays of `parts` (<= 16, parts * k <= 1024) device pointers to [B, k] lists, each sorted (value desc, index asc); an
  * index becomes idx * idx_mul + p * idx_add (round-robin item shards: idx_mul = world, idx_add = 1; must stay below
  * 2^32).  Only rows [row0, row0 + n_rows) are merged, into out_idx / out_val [n_rows, k]: in the sharded evaluation
- * every rank merges its own slice of the batch.  The caller synchronises the ranks before the call. */
+ * every rank merges its own slice of the batch.  The ranks must be synchronised before the lists are read: either by
+ * the caller, or inside the kernel when `flags` / `state` / `rank` are given (see mmrec_peer_exchange_f32). */
 int mmrec_topk_merge_peers(int parts, int64_t B, int k, const void* const* vals, const void* const* idx,
                            int64_t idx_mul, int64_t idx_add, int64_t row0, int64_t n_rows,
-                           int64_t* out_idx, float* out_val, void* stream);
+                           int64_t* out_idx, float* out_val,
+                           void* const* flags /* nullable */, int32_t* state /* nullable */, int rank, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  user-embedding exchange of the item-sharded propagation, over peer memory (no reference counterpart:
@@ -227,6 +229,16 @@ int mmrec_peer_sum_f32(int64_t n, int world, const void* const* parts, const flo
 int mmrec_peer_reduce_push_f32(int64_t n, int world, int rank, const void* const* parts, void* const* dst,
                                const float* acc_in, float* acc_out, float acc_div, int final_layer, void* stream);
 int mmrec_peer_gather_f32(int64_t n_each, int world, const void* const* src, float* dst, void* stream);
+/* The same with both synchronisations INSIDE the kernel -- one launch per layer: wait until every rank's partial is
+ * complete, reduce my slice, store it to every rank, wait until every rank's stores have landed.
+ *   flags  host array of `world` device pointers to each rank's flag array (int32[2 * world], peer-mapped, zero at start)
+ *   state  this rank's int32[4] in ordinary device memory, zero at start: {calls completed, release word, block counter, -}
+ * Calls are numbered on the device (state[0]), so the launch can be replayed from a CUDA graph; every rank must issue
+ * the same sequence of calls that use the same flags (mmrec_peer_exchange_f32, mmrec_peer_barrier, mmrec_topk_merge_peers
+ * with flags).  A rank that never arrives makes the others trap after 4 s instead of hanging. */
+int mmrec_peer_exchange_f32(int64_t n, int world, int rank, const void* const* parts, void* const* dst, void* const* flags,
+                            int32_t* state, const float* acc_in, float* acc_out, float acc_div, int final_layer, void* stream);
+int mmrec_peer_barrier(int world, int rank, void* const* flags, int32_t* state, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * f2  evaluator on the device.   Replaces the host loop that builds the hit matrix from `.cpu().numpy()` of the index

@@ -46,7 +46,9 @@ PROTOTYPES = {
     "mmrec_debug_cf_timing": (_i32, [_p, _i32]),
     "mmrec_debug_fused_fallback_rows": (_i64, [_p, _i64, _i64, _i32, _i32, _i64, _i32]),
     "mmrec_topk_merge": (_i32, [_i32, _i64, _i32, _p, _p, _p, _p, _p]),
-    "mmrec_topk_merge_peers": (_i32, [_i32, _i64, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
+    "mmrec_topk_merge_peers": (_i32, [_i32, _i64, _i32, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i32, _p]),
+    "mmrec_peer_exchange_f32": (_i32, [_i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _f32, _i32, _p]),
+    "mmrec_peer_barrier": (_i32, [_i32, _i32, _p, _p, _p]),
     "mmrec_peer_reduce_push_f32": (_i32, [_i64, _i32, _i32, _p, _p, _p, _p, _f32, _i32, _p]),
     "mmrec_peer_gather_f32": (_i32, [_i64, _i32, _p, _p, _p]),
     "mmrec_topk_metrics_f64": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),

@@ -6,11 +6,10 @@
 // mean epilogue (`acc_out = (acc_in + sum) / div`) in the same pass -- the all-reduce, the `acc + part` pass and
 // the final division of the NCCL formulation collapse into one read of (world) x [U, d] and two writes.
 // HBM/NVLink-bound: 4 n (world + 1 + writes) bytes per launch, no reuse.
-#include "common.cuh"
+#include "peer_sync.cuh"
 
 namespace mmrec {
 
-constexpr int PEER_MAX = 16;
 struct PeerParts { const float4* p[PEER_MAX]; };
 
 __global__ void __launch_bounds__(256) peer_sum_kernel(int64_t n4, int world, const PeerParts parts, const float4* __restrict__ acc_in,
@@ -69,6 +68,47 @@ __global__ void __launch_bounds__(256) peer_reduce_push_kernel(int64_t lo4, int6
         for (int r = 0; r < PEER_MAX; ++r)
             if (r < world) const_cast<float4*>(dst.p[r])[i] = out;
     }
+}
+
+// mmrec_peer_reduce_push_f32 with both barriers inside: ONE launch per layer does "wait until every rank's partial is
+// complete -> reduce my slice -> store it to every rank -> wait until every rank's slices have landed".
+__global__ void __launch_bounds__(256) peer_exchange_kernel(int64_t lo4, int64_t hi4, int world, int rank, const PeerParts parts,
+                                                            const PeerParts dst, const PeerFlags flags, int* __restrict__ state,
+                                                            const float4* __restrict__ acc_in, float4* __restrict__ acc_out, float div,
+                                                            int final_layer) {
+    const int epoch = peer_enter(flags, state, rank, world);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi4; i += stride) {
+        float4 v[PEER_MAX];
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            if (r < world) v[r] = __ldcv(parts.p[r] + i);            // (volatile: never a stale line of an earlier call)
+        float4 s = v[0];
+#pragma unroll
+        for (int r = 1; r < PEER_MAX; ++r)
+            if (r < world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        float4 out = s;
+        if (acc_in) {
+            float4 a = acc_in[i - lo4];
+            a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+            if (final_layer) {
+                if (div != 1.0f) { a.x = __fdiv_rn(a.x, div); a.y = __fdiv_rn(a.y, div); a.z = __fdiv_rn(a.z, div); a.w = __fdiv_rn(a.w, div); }
+                out = a;
+            } else if (acc_out) {
+                acc_out[i - lo4] = a;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < PEER_MAX; ++r)
+            if (r < world) const_cast<float4*>(dst.p[r])[i] = out;
+    }
+    peer_leave(flags, state, rank, world, epoch, true);
+}
+
+// barrier-only kernel on the same flags (e.g. before gathers / merges that read what the peers wrote)
+__global__ void peer_barrier_kernel(int world, int rank, const PeerFlags flags, int* __restrict__ state) {
+    const int epoch = peer_enter(flags, state, rank, world);
+    peer_leave(flags, state, rank, world, epoch, false);
 }
 
 // dst[p * n4 + i] = src[p][i]: the shards of a table read straight from the peers that own them (all-gather by P2P loads)
@@ -154,6 +194,50 @@ extern "C" int mmrec_peer_gather_f32(int64_t n_each, int world, const void* cons
     const int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
     peer_gather_kernel<<<(unsigned)grid, 256, 0, stream>>>(n4, world, S, (float4*)dst);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}
+
+extern "C" int mmrec_peer_exchange_f32(int64_t n, int world, int rank, const void* const* parts, void* const* dst, void* const* flags,
+                                       int32_t* state, const float* acc_in, float* acc_out, float acc_div, int final_layer, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(n >= 0 && world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world && parts && dst && flags && state,
+                    "peer_exchange: bad sizes (1 <= world <= 16, 0 <= rank < world) or null pointer");
+    MMREC_CHECK_ARG((n & 3) == 0, "peer_exchange: n must be a multiple of 4 floats");
+    MMREC_CHECK_ARG(acc_div != 0.0f, "peer_exchange: acc_div == 0");
+    PeerParts P, D;
+    PeerFlags F;
+    for (int r = 0; r < PEER_MAX; ++r) { P.p[r] = nullptr; D.p[r] = nullptr; F.f[r] = nullptr; }
+    for (int r = 0; r < world; ++r) {
+        MMREC_CHECK_ARG(parts[r] && dst[r] && flags[r] && ((((uintptr_t)parts[r]) | ((uintptr_t)dst[r])) & 15) == 0 && (((uintptr_t)flags[r]) & 3) == 0,
+                        "peer_exchange: buffer pointers must be non-null and aligned (16 bytes data, 4 bytes flags)");
+        P.p[r] = (const float4*)parts[r]; D.p[r] = (const float4*)dst[r]; F.f[r] = (int*)flags[r];
+    }
+    MMREC_CHECK_ARG(((((uintptr_t)acc_in) | ((uintptr_t)acc_out)) & 15) == 0, "peer_exchange: 16-byte alignment");
+    const int64_t n4 = n / 4;
+    const int64_t per = (n4 + world - 1) / world;
+    const int64_t lo4 = per * rank < n4 ? per * rank : n4, hi4 = lo4 + per < n4 ? lo4 + per : n4;
+    // every block must be resident: the blocks wait for block 0's handshake (one wave, at most 4 blocks per SM)
+    int64_t grid = (hi4 - lo4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    peer_exchange_kernel<<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, world, rank, P, D, F, state, (const float4*)acc_in, (float4*)acc_out,
+                                                             acc_div, final_layer);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}
+
+extern "C" int mmrec_peer_barrier(int world, int rank, void* const* flags, int32_t* state, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(world >= 1 && world <= PEER_MAX && rank >= 0 && rank < world && flags && state, "peer_barrier: bad arguments");
+    PeerFlags F;
+    for (int r = 0; r < PEER_MAX; ++r) F.f[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        MMREC_CHECK_ARG(flags[r], "peer_barrier: null flag pointer");
+        F.f[r] = (int*)flags[r];
+    }
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(world, rank, F, state);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }

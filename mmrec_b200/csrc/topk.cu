@@ -7,7 +7,7 @@
 // index order (block-wide ordered compaction), then a bitonic sort on the composite (key, ~index) puts the
 // k winners in contract order.  (A warp-per-row streaming filter with bitonic compaction was measured 2.5x
 // slower at 7k items: the compaction sorts dominate.)
-#include "common.cuh"
+#include "peer_sync.cuh"
 
 namespace mmrec {
 
@@ -179,20 +179,16 @@ constexpr int MERGE_WARPS = 4;
 constexpr int MERGE_WARP_CAP = 1024;    // parts * k one warp handles
 struct MergePeers { const float* v[MERGE_MAX_PEERS]; const int64_t* i[MERGE_MAX_PEERS]; };
 
-__global__ void __launch_bounds__(32 * MERGE_WARPS) topk_merge_peers_kernel(int parts, int64_t B, int k, const MergePeers src, int64_t idx_mul,
-                                                                            int64_t idx_add, int64_t row0, int64_t n_rows,
-                                                                            int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
-    __shared__ uint64_t comp_all[MERGE_WARPS][MERGE_WARP_CAP];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r = (int64_t)blockIdx.x * MERGE_WARPS + warp;
-    if (r >= n_rows) return;
-    const int64_t b = row0 + r;
-    uint64_t* comp = comp_all[warp];
+__device__ __forceinline__ void topk_merge_row(int parts, int k, const MergePeers& src, int64_t idx_mul, int64_t idx_add, int64_t b, int64_t r,
+                                               uint64_t* comp, int lane, bool fresh, int64_t* __restrict__ out_idx, float* __restrict__ out_val) {
     const int n = parts * k;
     for (int t = lane; t < n; t += 32) {
         const int p = t / k, j = t - p * k;
-        const int64_t gi = src.i[p][b * k + j] * idx_mul + p * idx_add;               // < 2^32 (checked by the host)
-        comp[t] = ((uint64_t)float_key(src.v[p][b * k + j]) << 32) | (uint32_t)(~(uint32_t)gi);
+        // (`fresh`: the lists were written by other GPUs moments ago -- bypass any cached line of an earlier batch)
+        const int64_t li = fresh ? __ldcv(src.i[p] + b * k + j) : src.i[p][b * k + j];
+        const float lv = fresh ? __ldcv(src.v[p] + b * k + j) : src.v[p][b * k + j];
+        const int64_t gi = li * idx_mul + p * idx_add;                                 // < 2^32 (checked by the host)
+        comp[t] = ((uint64_t)float_key(lv) << 32) | (uint32_t)(~(uint32_t)gi);
     }
     __syncwarp();
     for (int t = lane; t < n; t += 32) {
@@ -214,6 +210,19 @@ __global__ void __launch_bounds__(32 * MERGE_WARPS) topk_merge_peers_kernel(int 
             out_val[r * k + rank] = key_float((uint32_t)(me >> 32));
         }
     }
+}
+
+__global__ void __launch_bounds__(32 * MERGE_WARPS) topk_merge_peers_kernel(int parts, int64_t B, int k, const MergePeers src, int64_t idx_mul,
+                                                                            int64_t idx_add, int64_t row0, int64_t n_rows,
+                                                                            int64_t* __restrict__ out_idx, float* __restrict__ out_val,
+                                                                            const PeerFlags flags, int* __restrict__ state, int rank) {
+    __shared__ uint64_t comp_all[MERGE_WARPS][MERGE_WARP_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // with flags: the wait for "every rank has written its lists" happens here instead of in a barrier launch
+    const int epoch = state ? peer_enter(flags, state, rank, parts) : 0;
+    const int64_t r = (int64_t)blockIdx.x * MERGE_WARPS + warp;
+    if (r < n_rows) topk_merge_row(parts, k, src, idx_mul, idx_add, row0 + r, r, comp_all[warp], lane, state != nullptr, out_idx, out_val);
+    if (state) peer_leave(flags, state, rank, parts, epoch, false);
 }
 
 }  // namespace mmrec
@@ -268,21 +277,27 @@ extern "C" int mmrec_topk_merge(int parts, int64_t B, int k, const float* vals, 
 }
 
 extern "C" int mmrec_topk_merge_peers(int parts, int64_t B, int k, const void* const* vals, const void* const* idx, int64_t idx_mul,
-                                      int64_t idx_add, int64_t row0, int64_t n_rows, int64_t* out_idx, float* out_val, void* stream_) {
+                                      int64_t idx_add, int64_t row0, int64_t n_rows, int64_t* out_idx, float* out_val,
+                                      void* const* flags, int32_t* state, int rank, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MMREC_CHECK_ARG(parts >= 1 && parts <= MERGE_MAX_PEERS && B >= 0 && k >= 1 && (int64_t)parts * k <= MERGE_WARP_CAP,
                     "topk_merge_peers: need parts <= 16 and parts*k <= 1024");
     MMREC_CHECK_ARG(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= B, "topk_merge_peers: row range outside the batch");
-    if (B == 0 || n_rows == 0) return MMREC_OK;
-    MMREC_CHECK_ARG(vals && idx && out_idx && out_val, "topk_merge_peers: null pointer");
+    MMREC_CHECK_ARG((flags == nullptr) == (state == nullptr) && (!flags || (rank >= 0 && rank < parts)), "topk_merge_peers: flags / state / rank");
+    if (B == 0 || (n_rows == 0 && !flags)) return MMREC_OK;
+    MMREC_CHECK_ARG(vals && idx && (n_rows == 0 || (out_idx && out_val)), "topk_merge_peers: null pointer");
     MergePeers src;
-    for (int p = 0; p < MERGE_MAX_PEERS; ++p) { src.v[p] = nullptr; src.i[p] = nullptr; }
+    PeerFlags F;
+    for (int p = 0; p < MERGE_MAX_PEERS; ++p) { src.v[p] = nullptr; src.i[p] = nullptr; F.f[p] = nullptr; }
     for (int p = 0; p < parts; ++p) {
-        MMREC_CHECK_ARG(vals[p] && idx[p], "topk_merge_peers: null list pointer");
+        MMREC_CHECK_ARG(vals[p] && idx[p] && (!flags || flags[p]), "topk_merge_peers: null list / flag pointer");
         src.v[p] = (const float*)vals[p]; src.i[p] = (const int64_t*)idx[p];
+        if (flags) F.f[p] = (int*)flags[p];
     }
-    topk_merge_peers_kernel<<<(unsigned)((n_rows + MERGE_WARPS - 1) / MERGE_WARPS), 32 * MERGE_WARPS, 0, stream>>>(
-        parts, B, k, src, idx_mul, idx_add, row0, n_rows, out_idx, out_val);
+    int64_t grid = (n_rows + MERGE_WARPS - 1) / MERGE_WARPS;
+    if (grid < 1) grid = 1;                                          // (a rank without rows still takes part in the barrier)
+    topk_merge_peers_kernel<<<(unsigned)grid, 32 * MERGE_WARPS, 0, stream>>>(parts, B, k, src, idx_mul, idx_add, row0, n_rows, out_idx, out_val,
+                                                                           F, state, rank);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }

@@ -467,18 +467,23 @@ def _ptr_array(ptrs):
     return arr, ctypes.cast(arr, ctypes.c_void_p)
 
 
-def topk_merge_peers(val_ptrs, idx_ptrs, B, k, device, idx_mul=1, idx_add=0, row0=0, n_rows=None):
+def topk_merge_peers(val_ptrs, idx_ptrs, B, k, device, idx_mul=1, idx_add=0, row0=0, n_rows=None, sync=None):
     """`topk_merge` over lists left where each rank wrote them: raw device addresses of `parts` [B, k] value (fp32) and
     index (int64) lists, rank order; index -> idx * idx_mul + part * idx_add (round-robin shards: world, 1).  Rows
-    [row0, row0 + n_rows) only (default: all): returns ([n_rows, k] values, indices)."""
+    [row0, row0 + n_rows) only (default: all): returns ([n_rows, k] values, indices).  `sync` = (flag_ptrs, state, rank):
+    the ranks are synchronised inside the kernel (before the lists are read) instead of by a barrier launch."""
     lib = _lib.load()
     n_rows = B - row0 if n_rows is None else n_rows
     va, vap = _ptr_array(val_ptrs)
     ia, iap = _ptr_array(idx_ptrs)
     out_i = torch.empty(n_rows, k, dtype=torch.int64, device=device)
     out_v = torch.empty(n_rows, k, dtype=torch.float32, device=device)
+    fa = fap = None
+    if sync is not None:
+        fa, fap = _ptr_array(sync[0])
     check(lib.mmrec_topk_merge_peers(len(val_ptrs), B, k, vap, iap, int(idx_mul), int(idx_add), int(row0), int(n_rows), _ptr(out_i),
-                                     _ptr(out_v), _stream()), "mmrec_topk_merge_peers")
+                                     _ptr(out_v), fap, None if sync is None else _ptr(sync[1]), 0 if sync is None else int(sync[2]),
+                                     _stream()), "mmrec_topk_merge_peers")
     return out_v, out_i
 
 
@@ -501,6 +506,22 @@ def peer_reduce_push(part_ptrs, dst_ptrs, n, rank, acc_in=None, acc_out=None, ac
     da, dap = _ptr_array(dst_ptrs)
     check(lib.mmrec_peer_reduce_push_f32(int(n), len(part_ptrs), int(rank), pap, dap, _ptr(acc_in), _ptr(acc_out), float(acc_div),
                                          int(bool(final_layer)), _stream()), "mmrec_peer_reduce_push_f32")
+
+
+def peer_exchange(part_ptrs, dst_ptrs, flag_ptrs, state, n, rank, acc_in=None, acc_out=None, acc_div=1.0, final_layer=False):
+    """`peer_reduce_push` with both rank synchronisations inside the kernel (`mmrec_peer_exchange_f32`): one launch per layer."""
+    lib = _lib.load()
+    pa, pap = _ptr_array(part_ptrs)
+    da, dap = _ptr_array(dst_ptrs)
+    fa, fap = _ptr_array(flag_ptrs)
+    check(lib.mmrec_peer_exchange_f32(int(n), len(part_ptrs), int(rank), pap, dap, fap, _ptr(state), _ptr(acc_in), _ptr(acc_out),
+                                      float(acc_div), int(bool(final_layer)), _stream()), "mmrec_peer_exchange_f32")
+
+
+def peer_barrier(flag_ptrs, state, rank):
+    """Device-side barrier of the ranks on the current stream over the same flags (`mmrec_peer_barrier`)."""
+    fa, fap = _ptr_array(flag_ptrs)
+    check(_lib.load().mmrec_peer_barrier(len(flag_ptrs), int(rank), fap, _ptr(state), _stream()), "mmrec_peer_barrier")
 
 
 def peer_gather(src_ptrs, n_each, dst: torch.Tensor):

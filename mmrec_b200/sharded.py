@@ -152,13 +152,19 @@ class PeerExchange:
         self.hi = min(self.lo + self.per4 * 4, n)
         self.acc = torch.empty(self.per4 * 4, dtype=torch.float32, device=buf.device)
         self._chan = 0
+        # flags of the in-kernel barriers (mmrec_peer_exchange_f32 & co): 2 * world ints per rank at the end of the buffer,
+        # and this rank's call counter / release word / block counter in ordinary device memory
+        self.flag_off = self.idx_off + 2 * topk_rows * k
+        self.flag_ptrs = [int(p) + 4 * self.flag_off for p in hdl.buffer_ptrs]
+        self.state = torch.zeros(4, dtype=torch.int32, device=buf.device)
+        self.sync_in_kernel = os.environ.get("MMREC_PEER_SYNC", "kernel") != "launch"
 
     @staticmethod
     def words(n_users, d, n_layers, n_local, k):
         n = n_users * d
         w = 2 * n_layers * n + n_local * d + ((n_local * d) & 1)
         w += n_users * k + ((n_users * k) & 1) + 2 * n_users * k
-        return w
+        return w + 2 * 16                                            # + the barrier flags (2 * world ints, world <= 16)
 
     def topk_lists(self, row0, nrows):
         """(values, indices) views of this rank's list region for user rows [row0, row0 + nrows), and the peers' raw
@@ -226,20 +232,28 @@ def propagate_mean_sharded_p2p(a_ui, a_iu, user_emb, item_emb_local, n_layers, p
         with torch.cuda.stream(side):
             ei_next, acc_i = _cuda_spmm(a_iu, eu, acc_in=acc_i, acc_div=div, want_y=not last)
         ops.spmm_raw(a_ui, ei, Y=px.parts[l - 1])                    # R_g E_Ig -> peer-visible partial of layer l
-        px.barrier()                                                 # every rank's partial of layer l is complete
-        if l == 1 and mm_local is not None:                          # (the peers' item rows are published as well)
+        acc_in = ue_flat[px.lo:px.hi] if l == 1 else px.acc
+        if px.sync_in_kernel:
+            # one launch: wait for every rank's partial, reduce my slice, store it to every rank, wait for every rank's stores
+            ops.peer_exchange(px.part_ptrs[l - 1], px.gath_ptrs[l - 1], px.flag_ptrs, px.state, U * d, px.rank, acc_in=acc_in,
+                              acc_out=px.acc, acc_div=div, final_layer=last)
+        else:
+            px.barrier()                                             # every rank's partial of layer l is complete
+            ops.peer_reduce_push(px.part_ptrs[l - 1], px.gath_ptrs[l - 1], U * d, px.rank, acc_in=acc_in, acc_out=px.acc, acc_div=div,
+                                 final_layer=last)
+            px.barrier()                                             # every slice of the reduced table has landed
+        if l == 1 and mm_local is not None:                          # (the peers published their item rows before that exchange)
             ei_all = torch.empty(px.world * px.n_local, d, dtype=torch.float32, device=dev)
             ops.peer_gather(px.item_ptrs, px.n_local * d, ei_all)
-        acc_in = ue_flat[px.lo:px.hi] if l == 1 else px.acc
-        ops.peer_reduce_push(px.part_ptrs[l - 1], px.gath_ptrs[l - 1], U * d, px.rank, acc_in=acc_in, acc_out=px.acc, acc_div=div,
-                             final_layer=last)
-        px.barrier()                                                 # every slice of the reduced table has landed
         main.wait_stream(side)
         eu, ei = px.gath[l - 1], ei_next
     u_g = px.gath[n_layers - 1] if n_layers > 0 else user_emb
     if mm_local is not None:
         if ei_all is None:                                           # n_layers == 0
-            px.barrier()
+            if px.sync_in_kernel:
+                ops.peer_barrier(px.flag_ptrs, px.state, px.rank)
+            else:
+                px.barrier()
             ei_all = torch.empty(px.world * px.n_local, d, dtype=torch.float32, device=dev)
             ops.peer_gather(px.item_ptrs, px.n_local * d, ei_all)
         ops.spmm_raw(mm_local, ei_all, acc_in=acc_i, acc_out=acc_i)  # i_g + mm_adj @ E_I  (freedom.py:178)
@@ -272,9 +286,13 @@ def score_topk_sharded_p2p(shard: ItemShard, user_e, item_e_local, users, lmask,
     B = users.numel()
     v, i, vp, ip = px.topk_lists(row0, B)
     ops.score_topk(user_e, item_e_local, users, lmask, k, out=(v, i), catalog=catalog)
-    px.barrier()
     lo, cnt = merge_rows(B, shard.world, shard.rank)
-    mv, mi = ops.topk_merge_peers(vp, ip, B, k, user_e.device, idx_mul=shard.world, idx_add=1, row0=lo, n_rows=cnt)
+    sync = None
+    if px.sync_in_kernel:
+        sync = (px.flag_ptrs, px.state, px.rank)                    # the merge kernel waits for the peers' lists itself
+    else:
+        px.barrier()
+    mv, mi = ops.topk_merge_peers(vp, ip, B, k, user_e.device, idx_mul=shard.world, idx_add=1, row0=lo, n_rows=cnt, sync=sync)
     return mv, mi, lo, cnt
 
 

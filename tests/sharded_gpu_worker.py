@@ -27,8 +27,11 @@ def main():
     mm_local = shard.mm_csr(kr, kc, kv, dev)
     ue = torch.from_numpy(wl.user_emb).to(dev)
     ie = torch.from_numpy(wl.item_emb[shard.local_items]).to(dev)
-    px = sharded.PeerExchange.create(U, d, wl.n_layers, shard.n_local, dev, k=k)
-    have = torch.tensor([1.0 if px is not None else 0.0], device=dev)
+    px = sharded.PeerExchange.create(U, d, wl.n_layers, shard.n_local, dev, k=k)           # barriers inside the kernels
+    px2 = sharded.PeerExchange.create(U, d, wl.n_layers, shard.n_local, dev, k=k)          # barriers as separate launches
+    if px2 is not None:
+        px2.sync_in_kernel = False
+    have = torch.tensor([1.0 if (px is not None and px2 is not None) else 0.0], device=dev)
     dist.all_reduce(have, op=dist.ReduceOp.MIN)
     batches = []
     for lo in range(0, U, 1024):
@@ -36,12 +39,13 @@ def main():
         m = torch.from_numpy(wl.eval_mask(lo, hi)).to(dev)
         batches.append((torch.arange(lo, hi, device=dev), m, sharded.local_mask(shard, m)))
     results = {}
-    for name in (["p2p"] if have.item() else []) + ["nccl"]:
+    for name in (["p2p", "p2p_launch_sync"] if have.item() else []) + ["nccl"]:
         with torch.no_grad():
-            for rep in range(2):                                     # twice: buffers are reused across calls
-                if name == "p2p":
-                    u_g, i_g = sharded.propagate_mean_sharded_p2p(a_ui, a_iu, ue, ie, wl.n_layers, px, mm_local=mm_local)
-                    out = [sharded.score_topk_sharded_p2p(shard, u_g, i_g, users, lm, k, px, bi * 1024) for bi, (users, _, lm) in enumerate(batches)]
+            for rep in range(3):                                     # repeatedly: buffers and barrier flags are reused across calls
+                if name.startswith("p2p"):
+                    x = px if name == "p2p" else px2
+                    u_g, i_g = sharded.propagate_mean_sharded_p2p(a_ui, a_iu, ue, ie, wl.n_layers, x, mm_local=mm_local)
+                    out = [sharded.score_topk_sharded_p2p(shard, u_g, i_g, users, lm, k, x, bi * 1024) for bi, (users, _, lm) in enumerate(batches)]
                 else:
                     u_g, i_g = sharded.propagate_mean_sharded(a_ui, a_iu, ue, ie, wl.n_layers)
                     i_g = sharded.mm_layer_sharded(shard, mm_local, ie, i_g)

@@ -48,11 +48,11 @@ def test_argument_errors_without_a_gpu():
     assert lib.mmrec_peer_sum_f32(6, 2, ctypes.cast(two, ctypes.c_void_p), None, None, 1.0, None, None) == -1
     assert b"peer_sum" in lib.mmrec_last_error()
     assert lib.mmrec_topk_merge_peers(17, 4, 10, ctypes.cast(two, ctypes.c_void_p), ctypes.cast(two, ctypes.c_void_p), 1, 0, 0, 4,
-                                      None, None, None) == -1                          # more than 16 lists
+                                      None, None, None, None, 0, None) == -1           # more than 16 lists
     assert lib.mmrec_topk_merge_peers(2, 4, 10, ctypes.cast(two, ctypes.c_void_p), ctypes.cast(two, ctypes.c_void_p), 2, 1, 3, 2,
-                                      None, None, None) == -1                          # row range outside the batch
+                                      None, None, None, None, 0, None) == -1           # row range outside the batch
     assert lib.mmrec_topk_merge_peers(2, 0, 10, ctypes.cast(two, ctypes.c_void_p), ctypes.cast(two, ctypes.c_void_p), 2, 1, 0, 0,
-                                      None, None, None) == 0                           # B == 0: nothing to do
+                                      None, None, None, None, 0, None) == 0            # B == 0: nothing to do
     assert lib.mmrec_peer_reduce_push_f32(8, 2, 2, ctypes.cast(two, ctypes.c_void_p), ctypes.cast(two, ctypes.c_void_p), None, None, 1.0, 0,
                                           None) == -1                                  # rank outside the world
     assert lib.mmrec_peer_gather_f32(6, 2, ctypes.cast(two, ctypes.c_void_p), None, None) == -1
