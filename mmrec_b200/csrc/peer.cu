@@ -217,9 +217,11 @@ extern "C" int mmrec_peer_exchange_f32(int64_t n, int world, int rank, const voi
     const int64_t n4 = n / 4;
     const int64_t per = (n4 + world - 1) / world;
     const int64_t lo4 = per * rank < n4 ? per * rank : n4, hi4 = lo4 + per < n4 ? lo4 + per : n4;
-    // every block must be resident: the blocks wait for block 0's handshake (one wave, at most 4 blocks per SM)
+    // The blocks wait for block 0's handshake with the peers, i.e. they sit on their SMs while the item-side SpMM of the
+    // same layer runs on the other stream: a few dozen blocks saturate one NVLink direction (256 threads x 16 B x the
+    // loads in flight each) and leave the rest of the GPU to that SpMM.
     int64_t grid = (hi4 - lo4 + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 4;
+    const int64_t cap = (hi4 - lo4) * 16 > (64ll << 20) ? (int64_t)sm_count() : 48;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     peer_exchange_kernel<<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, world, rank, P, D, F, state, (const float4*)acc_in, (float4*)acc_out,

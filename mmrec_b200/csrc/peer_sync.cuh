@@ -40,6 +40,7 @@ __device__ __forceinline__ void peer_barrier(const PeerFlags& F, int b, int rank
     for (int p = 0; p < world; ++p) {
         unsigned spins = 0;
         while (ld_acquire_sys(F.f[rank] + b * world + p) < epoch) {
+            __nanosleep(40);
             if ((++spins & 0xfffu) == 0 && peer_now_ns() - t0 > 4000000000ull) {
                 printf("mmrec: peer barrier %d timed out (rank %d waiting for rank %d, epoch %d)\n", b, rank, p, epoch);
                 __trap();
@@ -59,6 +60,7 @@ __device__ __forceinline__ int peer_enter(const PeerFlags& F, int* state, int ra
             const unsigned long long t0 = peer_now_ns();
             unsigned spins = 0;
             while (ld_acquire_gpu(state + 1) < e) {
+                __nanosleep(200);                                    // (hundreds of blocks poll this word: keep them off the L2 port)
                 if ((++spins & 0xfffu) == 0 && peer_now_ns() - t0 > 4000000000ull) { printf("mmrec: peer_enter timed out\n"); __trap(); }
             }
         }

@@ -157,7 +157,10 @@ class PeerExchange:
         self.flag_off = self.idx_off + 2 * topk_rows * k
         self.flag_ptrs = [int(p) + 4 * self.flag_off for p in hdl.buffer_ptrs]
         self.state = torch.zeros(4, dtype=torch.int32, device=buf.device)
-        self.sync_in_kernel = os.environ.get("MMREC_PEER_SYNC", "kernel") != "launch"
+        # measured at N = 2 (baby x2, profiles/): barriers as separate launches 0.165 ms per propagation, inside the
+        # kernels 0.21-0.25 ms (the handshake at system scope inside a kernel that also holds SMs costs more than the two
+        # launches it saves) -> launches are the default, MMREC_PEER_SYNC=kernel selects the fused form
+        self.sync_in_kernel = os.environ.get("MMREC_PEER_SYNC", "launch") == "kernel"
 
     @staticmethod
     def words(n_users, d, n_layers, n_local, k):

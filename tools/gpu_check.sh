@@ -4,15 +4,15 @@
 # Every step has its own timeout (the first python start on a fresh box can take a minute or two by itself).
 tag=${1:-chk}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -x -q -m gpu > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log; tail -3 gpurun_out/${tag}_pytest.log
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log; tail -3 gpurun_out/${tag}_pytest.log
 timeout 90 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -1 gpurun_out/${tag}_smoke.log
-timeout 200 python bench.py > gpurun_out/${tag}_bench.log 2>&1; tail -1 gpurun_out/${tag}_bench.log | cut -c1-300
-timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
-for k in spmm_vec_kernel:4 project_tc_kernel:0 score_fused_kernel:2 fused_select_kernel:2 fz_prep_kernel:2; do
+timeout 600 python bench.py > gpurun_out/${tag}_bench.log 2>&1; tail -1 gpurun_out/${tag}_bench.log | cut -c1-300
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 900 --csv --log-file gpurun_out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-other-configs > gpurun_out/${tag}_ncu_bench.log 2>&1
+for k in ${KERNELS:-}; do
     name=${k%%:*}; skip=${k##*:}
     timeout 120 ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 -o gpurun_out/${tag}_$name -f \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
+        python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-other-configs > /dev/null 2>&1
 done
 ls gpurun_out | grep "^${tag}_"
 # then, here:  python tools/summarize_ncu.py launches gpurun_out/<tag>_launches.csv profiles/rNN_launches_bench.md "<title>"
