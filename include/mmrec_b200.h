@@ -112,6 +112,24 @@ int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d,
                    const float* gate_ref, int64_t ldgate,
                    void* stream);
 
+/* The SpMMs of one propagation as ONE persistent cooperative launch (src/models/freedom.py:164-178: n_ui_layers products with
+ * A_hat, the item-item product, the layer mean and `+ h`): the steps run in order on one resident grid, with a grid-wide
+ * barrier before every step whose `sync_before` is set (= it reads what an earlier step wrote).  Every step needs its work
+ * plan; d in {32, 64, 128, 256}, 16-byte aligned operands -- otherwise MMREC_EUNSUPPORTED and the caller launches the steps
+ * one by one with mmrec_spmm_f32.  Extra epilogue term: acc_out[r,:] += post[r - post_row0,:] for r >= post_row0, applied
+ * after the division (FREEDOM's `i_g_embeddings + h`, freedom.py:178). */
+typedef struct {
+    int64_t n_rows, n_cols;
+    const int32_t* rowptr; const int32_t* colidx; const float* vals;
+    const int32_t* tasks; int64_t n_tasks, n_cta_tasks; const int32_t* split_rows; int32_t* counters; float* partial;
+    const float* X; int64_t ldx;
+    float* Y; int64_t ldy;                                   /* nullable */
+    const float* acc_in; float* acc_out; int64_t ldacc; float acc_div;   /* as mmrec_spmm_f32 */
+    const float* post; int64_t ldpost; int64_t post_row0;    /* nullable */
+    int sync_before;
+} mmrec_spmm_step;
+int mmrec_spmm_chain_f32(int d, int n_steps, const mmrec_spmm_step* steps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2  fused gather -> linear(+bias) -> optional row L2-normalise.   Replaces
  * `self.image_trs(self.image_embedding.weight)[items]` (src/models/freedom.py:205-209,

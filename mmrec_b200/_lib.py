@@ -28,6 +28,7 @@ PROTOTYPES = {
     "mmrec_spmm_set_lanes": (_i32, [_i32]),
     "mmrec_spmm_f32": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64,
                               _f32, _p, _i64, _p]),
+    "mmrec_spmm_chain_f32": (_i32, [_i32, _i32, _p, _p]),
     "mmrec_project_set_path": (_i32, [_i32]),
     "mmrec_project_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "mmrec_project_f32": (_i32, [_i64, _p, _p, _i64, _i64, _p, _p, _i32, _i32, _p, _i64, _p, _sz, _p]),
@@ -54,6 +55,15 @@ PROTOTYPES = {
     "mmrec_topk_metrics_f64": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "mmrec_peer_sum_f32": (_i32, [_i64, _i32, _p, _p, _p, _f32, _p, _p]),
 }
+
+class SpmmStep(C.Structure):
+    """`mmrec_spmm_step` of include/mmrec_b200.h."""
+    _fields_ = [("n_rows", _i64), ("n_cols", _i64), ("rowptr", _p), ("colidx", _p), ("vals", _p),
+                ("tasks", _p), ("n_tasks", _i64), ("n_cta_tasks", _i64), ("split_rows", _p), ("counters", _p), ("partial", _p),
+                ("X", _p), ("ldx", _i64), ("Y", _p), ("ldy", _i64),
+                ("acc_in", _p), ("acc_out", _p), ("ldacc", _i64), ("acc_div", _f32),
+                ("post", _p), ("ldpost", _i64), ("post_row0", _i64), ("sync_before", _i32)]
+
 
 _lib = None
 ABI_VERSION = 2

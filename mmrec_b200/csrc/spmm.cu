@@ -17,6 +17,8 @@
 //     counter) adds the partials in segment order -> the summation order never depends on scheduling, so
 //     results are bit-reproducible.
 // Grid: persistent, (SM count x resident CTAs) CTAs of 8 warps striding over the task list.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace mmrec {
@@ -29,6 +31,7 @@ struct SpmmParams {
     float* Y; int64_t ldy;
     const float* acc_in; float* acc_out; int64_t ldacc; float acc_div;
     const float* gate_ref; int64_t ldgate;
+    const float* post; int64_t post_row0; uint32_t spost;   // acc_out[r,:] += post[r - post_row0, :] for r >= post_row0 (after the division)
     int d;
     uint32_t sx, sy, sacc, sgate;      // the leading dimensions as byte strides (vector kernel: one IMAD.WIDE per row address)
 };
@@ -95,6 +98,10 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, bool on, int 
             if (p.acc_div != 1.0f) {
                 a.x = __fdiv_rn(a.x, p.acc_div); a.y = __fdiv_rn(a.y, p.acc_div);
                 a.z = __fdiv_rn(a.z, p.acc_div); a.w = __fdiv_rn(a.w, p.acc_div);
+            }
+            if (p.post && row >= p.post_row0) {
+                const float4 q = *row_f4(p.post, p.spost, row - (int)p.post_row0, v * T + l);
+                a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
             }
             *row_f4(p.acc_out, p.sacc, row, v * T + l) = a;
         }
@@ -212,10 +219,9 @@ __device__ __forceinline__ bool spmm_split_finish(const SpmmParams& p, bool spli
 // broadcast transaction).  Warps walk the sorted list boustrophedon, so whoever got the longest tasks in one sweep
 // gets the shortest in the next.
 template <int D, int T>
-__global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
+__device__ __forceinline__ void spmm_vec_body(const SpmmParams& p, float* __restrict__ red) {
     using C = VecCfg<D, T>;
     constexpr int G = 256 / T;                              // lane groups per CTA
-    __shared__ __align__(16) float red[G * D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / T, l = lane % T;
     const int64_t n_work = p.tasks ? p.n_tasks : p.n_rows;
@@ -306,6 +312,29 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
     }
 }
 
+template <int D, int T>
+__global__ void __launch_bounds__(256) spmm_vec_kernel(const SpmmParams p) {
+    __shared__ __align__(16) float red[(256 / T) * D];
+    spmm_vec_body<D, T>(p, red);
+}
+
+// A chain of SpMMs in ONE persistent cooperative launch: the steps run in order on the same resident grid, a grid-wide
+// barrier wherever a step reads what an earlier one wrote (`sync_mask`).  The propagation of one `forward` -- L layers
+// on A_hat plus the item-item layer -- is one launch instead of L + 1: at Amazon-scale graphs a layer is a handful of
+// dependent L2 round trips, and launch ramp + tail of every layer were a third of its time.
+constexpr int SPMM_CHAIN_MAX = 8;
+struct SpmmChain { SpmmParams step[SPMM_CHAIN_MAX]; int n; unsigned sync_mask; };
+
+template <int D, int T>
+__global__ void __launch_bounds__(256) spmm_chain_kernel(const SpmmChain c) {
+    __shared__ __align__(16) float red[(256 / T) * D];
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int i = 0; i < c.n; ++i) {
+        if ((c.sync_mask >> i) & 1u) { __threadfence(); grid.sync(); }
+        spmm_vec_body<D, T>(c.step[i], red);
+    }
+}
+
 // Any d: 32 columns at a time, scalar loads.  Correctness path for odd widths, not tuned.
 __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmParams p) {
     const int lane = threadIdx.x & 31;
@@ -336,6 +365,7 @@ __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmParams p) {
             if (p.acc_out) {
                 float a = acc + (p.acc_in ? p.acc_in[row * p.ldacc + k] : 0.f);
                 if (p.acc_div != 1.0f) a = __fdiv_rn(a, p.acc_div);
+                if (p.post && row >= p.post_row0) a += p.post[(row - p.post_row0) * (int64_t)(p.spost / 4) + k];
                 p.acc_out[row * p.ldacc + k] = a;
             }
         }
@@ -405,6 +435,7 @@ extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32
     p.counters = counters; p.partial = partial; p.X = X; p.ldx = ldx; p.Y = Y; p.ldy = ldy;
     p.acc_in = acc_in; p.acc_out = acc_out; p.ldacc = ldacc; p.acc_div = acc_div; p.gate_ref = gate_ref;
     p.ldgate = ldgate; p.d = d;
+    p.post = nullptr; p.post_row0 = 0; p.spost = 0;
     MMREC_CHECK_ARG(ldx < (1ll << 30) && ldy < (1ll << 30) && ldacc < (1ll << 30) && ldgate < (1ll << 30) && n_cols < (1ll << 31) &&
                     n_rows < (1ll << 31), "spmm: leading dimension / size out of range");
     p.sx = (uint32_t)(ldx * 4); p.sy = (uint32_t)(ldy * 4); p.sacc = (uint32_t)(ldacc * 4); p.sgate = (uint32_t)(ldgate * 4);
@@ -427,4 +458,68 @@ extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32
     spmm_generic_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
+}
+
+namespace mmrec {
+template <int D>
+static int launch_chain(const SpmmChain& c, int64_t max_work, cudaStream_t stream) {
+    constexpr int T = D / 4 > 32 ? 32 : D / 4;                       // one float4 per lane, as the single-step default
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        MMREC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, spmm_chain_kernel<D, T>, 256, 0));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int per_block = 8 * (32 / T);
+    int64_t grid = (max_work + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;         // every block resident: the grid barrier needs it
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    void* args[] = {(void*)&c};
+    MMREC_CUDA(cudaLaunchCooperativeKernel((const void*)spmm_chain_kernel<D, T>, dim3((unsigned)grid), dim3(256), args, 0, stream));
+    ++g_launches;
+    return MMREC_OK;
+}
+}  // namespace mmrec
+
+extern "C" int mmrec_spmm_chain_f32(int d, int n_steps, const mmrec_spmm_step* steps, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MMREC_CHECK_ARG(n_steps >= 1 && n_steps <= SPMM_CHAIN_MAX && steps, "spmm_chain: 1 <= n_steps <= %d", SPMM_CHAIN_MAX);
+    if (!(d == 32 || d == 64 || d == 128 || d == 256) || g_spmm_lanes) {
+        set_error("spmm_chain: d = %d (or a lane override) has no chained kernel; launch the steps one by one", d);
+        return MMREC_EUNSUPPORTED;
+    }
+    SpmmChain c;
+    c.n = n_steps; c.sync_mask = 0;
+    int64_t max_work = 1;
+    auto al16 = [](const void* q, int64_t ld) { return q == nullptr || ((((uintptr_t)q) & 15) == 0 && (ld & 3) == 0); };
+    for (int i = 0; i < n_steps; ++i) {
+        const mmrec_spmm_step& t = steps[i];
+        MMREC_CHECK_ARG(t.n_rows >= 0 && t.n_cols >= 0 && t.rowptr && t.X && (t.Y || t.acc_out), "spmm_chain: step %d: null pointer / bad sizes", i);
+        MMREC_CHECK_ARG(t.tasks && t.n_tasks >= 0 && t.n_cta_tasks >= 0 && t.n_cta_tasks <= t.n_tasks && t.split_rows && t.counters && t.partial,
+                        "spmm_chain: step %d: the chained kernel needs the work plan (mmrec_spmm_plan)", i);
+        MMREC_CHECK_ARG(t.ldx >= d && (!t.Y || t.ldy >= d) && (!t.acc_out || t.ldacc >= d) && (!t.post || t.ldpost >= d) && t.acc_div != 0.0f,
+                        "spmm_chain: step %d: leading dimension < d or acc_div == 0", i);
+        MMREC_CHECK_ARG(t.ldx < (1ll << 30) && t.ldy < (1ll << 30) && t.ldacc < (1ll << 30) && t.ldpost < (1ll << 30) && t.n_cols < (1ll << 31) &&
+                        t.n_rows < (1ll << 31), "spmm_chain: step %d: size out of range", i);
+        if (!(al16(t.X, t.ldx) && al16(t.Y, t.ldy) && al16(t.acc_in, t.ldacc) && al16(t.acc_out, t.ldacc) && al16(t.post, t.ldpost) && al16(t.partial, 4))) {
+            set_error("spmm_chain: step %d: operands not 16-byte aligned; launch the steps one by one", i);
+            return MMREC_EUNSUPPORTED;
+        }
+        SpmmParams& p = c.step[i];
+        p.n_rows = t.n_rows; p.n_cols = t.n_cols; p.rowptr = t.rowptr; p.colidx = t.colidx; p.vals = t.vals;
+        p.tasks = (const int4*)t.tasks; p.n_tasks = t.n_tasks; p.n_heavy = t.n_cta_tasks; p.split_rows = (const int4*)t.split_rows;
+        p.counters = t.counters; p.partial = t.partial; p.X = t.X; p.ldx = t.ldx; p.Y = t.Y; p.ldy = t.ldy;
+        p.acc_in = t.acc_in; p.acc_out = t.acc_out; p.ldacc = t.ldacc; p.acc_div = t.acc_div; p.gate_ref = nullptr; p.ldgate = 0;
+        p.post = t.post; p.post_row0 = t.post_row0; p.d = d;
+        p.sx = (uint32_t)(t.ldx * 4); p.sy = (uint32_t)(t.ldy * 4); p.sacc = (uint32_t)(t.ldacc * 4); p.sgate = 0; p.spost = (uint32_t)(t.ldpost * 4);
+        if (t.sync_before && i > 0) c.sync_mask |= 1u << i;
+        const int64_t work = t.n_tasks > t.n_cta_tasks ? t.n_tasks : t.n_cta_tasks * 8;
+        if (work > max_work) max_work = work;
+    }
+    switch (d) {
+        case 32: return launch_chain<32>(c, max_work, stream);
+        case 64: return launch_chain<64>(c, max_work, stream);
+        case 128: return launch_chain<128>(c, max_work, stream);
+        default: return launch_chain<256>(c, max_work, stream);
+    }
 }

@@ -215,6 +215,75 @@ def spmm(A: CSR, X: torch.Tensor, base: Optional[torch.Tensor] = None) -> torch.
     return _SpmmFn.apply(X, A, base)
 
 
+def _chain_step(A: CSR, X, Y=None, acc_in=None, acc_out=None, acc_div=1.0, post=None, post_row0=0, sync_before=False):
+    d = X.shape[1]
+    st = _lib.SpmmStep()
+    st.n_rows, st.n_cols = A.n_rows, A.n_cols
+    st.rowptr, st.colidx, st.vals = _ptr(A.rowptr), _ptr(A.colidx), _ptr(A.vals)
+    st.tasks, st.n_tasks, st.n_cta_tasks = _ptr(A.tasks), A.n_tasks, A.n_cta_tasks
+    st.split_rows, st.counters, st.partial = _ptr(A.split_rows), _ptr(A.counters), _ptr(A.partial(d))
+    st.X, st.ldx = _ptr(X), X.stride(0)
+    st.Y, st.ldy = _ptr(Y), d
+    st.acc_in, st.acc_out, st.ldacc, st.acc_div = _ptr(acc_in), _ptr(acc_out), d, float(acc_div)
+    st.post, st.ldpost, st.post_row0 = _ptr(post), d, int(post_row0)
+    st.sync_before = int(bool(sync_before))
+    return st
+
+
+def propagate_mean_fused(A: CSR, ego: torch.Tensor, n_layers: int, post_csr: Optional[CSR] = None, post_x: Optional[torch.Tensor] = None,
+                         post_layers: int = 1, post_row0: int = 0) -> torch.Tensor:
+    """Inference form of `propagate_mean` (+ FREEDOM / BM3's item-item term) as ONE persistent cooperative launch
+    (`mmrec_spmm_chain_f32`): `mean(E_0 .. E_L)`, and if `post_csr` is given `out[post_row0:] += post_csr^post_layers @ post_x`
+    (`src/models/freedom.py:164-178`: `h = mm_adj @ ... @ item_emb`, `i_g + h`).  No autograd.  Falls back to one launch per
+    SpMM when the chained kernel does not take the shape."""
+    import ctypes
+    _need_cuda(ego, post_x)
+    ego = _f32c(ego)
+    d = ego.shape[1]
+    if n_layers < 1 or A.n_tasks == 0 or (post_csr is not None and post_csr.n_tasks == 0):
+        return _propagate_mean_post_unfused(A, ego, n_layers, post_csr, post_x, post_layers, post_row0)
+    steps, keep = [], []
+    h = None
+    if post_csr is not None:
+        h = _f32c(post_x)
+        for i in range(post_layers):                                 # h = mm_adj @ h, the first one reads the parameters only
+            y = torch.empty(post_csr.n_rows, d, dtype=torch.float32, device=ego.device)
+            steps.append(_chain_step(post_csr, h, Y=y, sync_before=i > 0))
+            keep.append(y)
+            h = y
+    acc = torch.empty_like(ego)
+    x = ego
+    for l in range(1, n_layers + 1):
+        last = l == n_layers
+        y = None if last else torch.empty_like(ego)
+        steps.append(_chain_step(A, x, Y=y, acc_in=ego if l == 1 else acc, acc_out=acc, acc_div=float(n_layers + 1) if last else 1.0,
+                                 post=h if last else None, post_row0=post_row0,
+                                 sync_before=(l > 1) or (last and h is not None)))
+        keep.append(y)
+        x = y
+    if len(steps) > 8:
+        return _propagate_mean_post_unfused(A, ego, n_layers, post_csr, post_x, post_layers, post_row0)
+    arr = (_lib.SpmmStep * len(steps))(*steps)
+    rc = _lib.load().mmrec_spmm_chain_f32(d, len(steps), ctypes.cast(arr, ctypes.c_void_p), _stream())
+    if rc == -4:                                                     # MMREC_EUNSUPPORTED: shape without a chained kernel
+        return _propagate_mean_post_unfused(A, ego, n_layers, post_csr, post_x, post_layers, post_row0)
+    check(rc, "mmrec_spmm_chain_f32")
+    return acc
+
+
+def _propagate_mean_post_unfused(A, ego, n_layers, post_csr, post_x, post_layers, post_row0):
+    out = _PropagateMeanFn.apply(ego.detach(), A, n_layers)
+    if post_csr is not None:
+        h = _f32c(post_x).detach()
+        for _ in range(post_layers - 1):
+            y = torch.empty(post_csr.n_rows, h.shape[1], dtype=torch.float32, device=h.device)
+            spmm_raw(post_csr, h, Y=y)
+            h = y
+        tail = out[post_row0:]
+        spmm_raw(post_csr, h, acc_in=tail, acc_out=tail)
+    return out
+
+
 class _PropagateMeanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ego, A: CSR, n_layers: int):
@@ -250,6 +319,8 @@ def propagate_mean(A: CSR, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
     """mean(E_0 .. E_L), E_{l+1} = A E_l -- the LightGCN propagation every graph model repeats
     (`src/models/freedom.py:169-176`, `bm3.py:86-92`, `lightgcn.py:116-123`, `mgcn.py:159-166`), with the
     running sum and the final division fused into the SpMM epilogue (no stack, no extra passes)."""
+    if n_layers >= 1 and not (torch.is_grad_enabled() and ego.requires_grad):
+        return propagate_mean_fused(A, ego, n_layers)               # inference: all layers in one cooperative launch
     return _PropagateMeanFn.apply(ego, A, n_layers)
 
 

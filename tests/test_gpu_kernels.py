@@ -542,3 +542,45 @@ def test_device_evaluator_matches_host_metrics(dev):
     mean = (sums / n).cpu().numpy()
     for row, fn in enumerate((TE.recall_, TE.ndcg_, TE.precision_, TE.map_)):
         np.testing.assert_allclose(mean[row], fn(hit, pos_len), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("d,L,mm_layers", [(64, 3, 1), (64, 1, 1), (128, 2, 2), (32, 4, 0), (64, 2, 0)])
+def test_spmm_chain_equals_separate_launches(dev, d, L, mm_layers):
+    """mmrec_spmm_chain_f32 (all SpMMs of a propagation in one cooperative launch, grid barriers in between) runs the same
+    kernel body as mmrec_spmm_f32: bit-identical to the one-launch-per-SpMM path, also when replayed from a CUDA graph."""
+    from mmrec_b200 import ops
+    from mmrec_b200.ops import CSR
+    U, I = 900, 500
+    n = U + I
+    r, c, v = rand_coo(U, I, 7000, seed=d + L, dup_frac=0)
+    r = torch.cat([r, torch.full((1500,), 3)]); c = torch.cat([c, torch.randint(0, I, (1500,))]); v = torch.cat([v, torch.rand(1500) - 0.5])   # a row the plan splits
+    A = CSR.from_coo(torch.cat([r, c + U]).to(dev), torch.cat([c + U, r]).to(dev), torch.cat([v, v]).to(dev), n, n, symmetric=True)
+    mr, mc, mv = rand_coo(I, I, 4000, seed=77)
+    M = CSR.from_coo(mr.to(dev), mc.to(dev), mv.to(dev), I, I)
+    ego = torch.randn(n, d, generator=torch.Generator().manual_seed(2)).to(dev)
+    want = ops._propagate_mean_post_unfused(A, ego, L, M if mm_layers else None, ego[U:] if mm_layers else None, max(mm_layers, 1), U)
+    got = ops.propagate_mean_fused(A, ego, L, post_csr=M if mm_layers else None, post_x=ego[U:] if mm_layers else None,
+                                   post_layers=max(mm_layers, 1), post_row0=U)
+    assert torch.equal(got, want)
+    # oracle
+    adj = torch.sparse_coo_tensor(torch.stack([torch.cat([r, c + U]), torch.cat([c + U, r])]), torch.cat([v, v]), (n, n))
+    ref = O.propagate_mean(adj, ego.cpu(), L)
+    if mm_layers:
+        h = ego.cpu()[U:]
+        mm = torch.sparse_coo_tensor(torch.stack([mr, mc]), mv, (I, I))
+        for _ in range(mm_layers):
+            h = torch.sparse.mm(mm, h)
+        ref = torch.cat([ref[:U], ref[U:] + h])
+    assert rel(got, ref) < 1e-5
+    # replay from a CUDA graph (cooperative launches are capturable)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ops.propagate_mean_fused(A, ego, L)
+        torch.cuda.synchronize()
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph, stream=side):
+            out = ops.propagate_mean_fused(A, ego, L)
+    torch.cuda.synchronize()
+    out.zero_(); gph.replay(); torch.cuda.synchronize()
+    assert torch.equal(out, ops._propagate_mean_post_unfused(A, ego, L, None, None, 1, 0))
+    assert int(A.counters.abs().sum().item()) == 0
