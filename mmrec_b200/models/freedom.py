@@ -60,7 +60,7 @@ class FREEDOM(GeneralRecommender):
 
     def forward(self, adj):
         ego = torch.cat((self.user_embedding.weight, self.item_id_embedding.weight), dim=0)
-        if not torch.is_grad_enabled() and self.n_layers >= 1 and self.n_ui_layers >= 1:
+        if ops.CHAIN and not torch.is_grad_enabled() and self.n_layers >= 1 and self.n_ui_layers >= 1:
             # inference: the item-item product(s), the UI layers, the layer mean and `i_g + h` in one cooperative launch
             all_emb = ops.propagate_mean_fused(adj, ego, self.n_ui_layers, post_csr=self.mm_adj, post_x=self.item_id_embedding.weight,
                                                post_layers=self.n_layers, post_row0=self.n_users)

@@ -18,6 +18,10 @@ _ws_cache: dict = {}
 import os as _os
 SEG = int(_os.environ.get("MMREC_SPMM_SEG", "512"))        # non-zeros per SpMM task (rows longer than this are split)
 LIGHT_MAX = int(_os.environ.get("MMREC_SPMM_LIGHT", "32"))  # tasks longer than this are run by a whole CTA
+# All SpMMs of an inference-time propagation in one cooperative launch (mmrec_spmm_chain_f32).  Measured on B200 at the baby
+# graph (profiles/r02_notes.md): 82.5 us against 75.8 us for one launch per SpMM replayed from a CUDA graph -- a grid-wide
+# barrier costs more than the launch boundary it replaces -- so it is opt-in.
+CHAIN = _os.environ.get("MMREC_SPMM_CHAIN", "0") == "1"
 
 
 def launch_count() -> int:
@@ -319,7 +323,7 @@ def propagate_mean(A: CSR, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
     """mean(E_0 .. E_L), E_{l+1} = A E_l -- the LightGCN propagation every graph model repeats
     (`src/models/freedom.py:169-176`, `bm3.py:86-92`, `lightgcn.py:116-123`, `mgcn.py:159-166`), with the
     running sum and the final division fused into the SpMM epilogue (no stack, no extra passes)."""
-    if n_layers >= 1 and not (torch.is_grad_enabled() and ego.requires_grad):
+    if CHAIN and n_layers >= 1 and not (torch.is_grad_enabled() and ego.requires_grad):
         return propagate_mean_fused(A, ego, n_layers)               # inference: all layers in one cooperative launch
     return _PropagateMeanFn.apply(ego, A, n_layers)
 
