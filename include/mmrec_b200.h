@@ -146,6 +146,12 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
                       const float* W, const float* bias, int d, int l2_normalize,
                       float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
 
+/* measurement aid (tools/probe_stream.py): stream a [n_rows, F] fp32 table the way K2 does -- every CTA visits R rows
+ * round-robin for burst_bytes contiguous bytes each, R * burst_bytes = 64 KB in flight per CTA -- to see what the DRAM
+ * delivers for a given burst length */
+int mmrec_debug_stream_probe(const float* table, int64_t n_rows, int64_t F, int R, int burst_bytes, int ctas_per_sm, float* sink,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K3  full-catalog scoring, train-positive mask and per-user top-k.   Replaces
  * `torch.matmul(u_embeddings, restore_item_e.transpose(0, 1))` (src/models/freedom.py:219,

@@ -87,3 +87,40 @@ extern "C" int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float*
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }
+
+// ---- measurement aid: how fast can a [rows, F] fp32 table be streamed when every CTA visits `R` rows round-robin for
+// `burst` contiguous bytes each (R * burst = 64 KB in flight per CTA)?  K2 reads its table in exactly this pattern
+// (R = 128, burst = 512 B); the probe tells what longer bursts per row would buy.  Result: bytes summed (so nothing is
+// optimised away).
+namespace mmrec {
+__global__ void __launch_bounds__(256) stream_probe_kernel(const float4* __restrict__ table, int64_t n_rows, int64_t row_f4, int R, int burst_f4,
+                                                           float* __restrict__ sink) {
+    const int tiles = (int)((n_rows + R - 1) / R);
+    float acc = 0.f;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int64_t o = 0; o < row_f4; o += burst_f4) {
+            float4 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {                          // 256 threads x 16 x 16 B = 64 KB
+                const int e = i * 256 + threadIdx.x;                 // element of the (R x burst) visit, burst-major inside a row
+                const int r = e / burst_f4, c = e - r * burst_f4;
+                const int64_t row = (int64_t)tile * R + r;
+                v[i] = (r < R && row < n_rows && o + c < row_f4) ? __ldg(table + row * row_f4 + o + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+}  // namespace mmrec
+
+extern "C" int mmrec_debug_stream_probe(const float* table, int64_t n_rows, int64_t F, int R, int burst_bytes, int ctas_per_sm, float* sink,
+                                        void* stream_) {
+    MMREC_CHECK_ARG(table && sink && (F & 3) == 0 && R >= 1 && burst_bytes >= 16 && (int64_t)R * burst_bytes == 65536 && ctas_per_sm >= 1,
+                    "stream_probe: need R * burst_bytes == 65536");
+    mmrec::stream_probe_kernel<<<(unsigned)(mmrec::sm_count() * ctas_per_sm), 256, 0, (cudaStream_t)stream_>>>(
+        (const float4*)table, n_rows, F / 4, R, burst_bytes / 16, sink);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}

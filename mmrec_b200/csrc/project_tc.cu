@@ -51,6 +51,7 @@ __host__ __device__ inline PjSmem pj_smem(int N, int stages) {
 }
 // barriers: a_full[s] = 0..7 (PJ_CONV arrivals) | b_full[s] = 8..15 (tx) | empty[s] = 16..23 (1, tcgen05.commit) | acc_full = 24
 
+template <bool FAST>
 __global__ void __launch_bounds__(PJ_THREADS, 1) project_tc_kernel(const ProjParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const PjSmem L = pj_smem(p.N, p.stages);
@@ -131,7 +132,22 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) project_tc_kernel(const ProjPar
             const int64_t r = (int64_t)tile * PJ_M + (t >> 3) + 32 * i;
             rowp[i] = r < p.n_out ? p.table + (p.idx ? p.idx[r] : r) * p.F : nullptr;
         }
+        // FAST (16-byte aligned table, F a multiple of 32: every BASELINE shape): the loop is bound by the instruction stream
+        // of the 8 converter warps (measured: 236 instructions per chunk and warp at one issue per ~8.5 cycles), so the chunk
+        // rotation is a running counter instead of a modulo, and a load is one predicated 16-byte request per row.
+        int ld_c = rot;                                               // chunk (inside this split) the next load reads
+        const float* kp[4];                                           // FAST: row pointers advanced to this thread's k block
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kp[i] = rowp[i] ? rowp[i] + (int64_t)c0 * PJ_KC + kb * 4 : nullptr;
         auto load_chunk = [&](int c, float4 (&x)[4]) {
+            if (FAST) {
+                const bool on = c < n_my;                             // (warp-uniform)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    x[i] = (on && kp[i]) ? __ldg(reinterpret_cast<const float4*>(kp[i] + ld_c * PJ_KC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (on && ++ld_c == n_my) ld_c = 0;
+                return;
+            }
             const int64_t k = (int64_t)(c0 + (c + rot) % n_my) * PJ_KC + kb * 4;    // (c >= n_my: not loaded, see below)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -308,11 +324,13 @@ int project_tc(int64_t n_out, const int64_t* idx, const float* table, int64_t F,
         int dev = 0;
         MMREC_CUDA(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-            MMREC_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMREC_CUDA(cudaFuncSetAttribute(project_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            MMREC_CUDA(cudaFuncSetAttribute(project_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
     }
-    project_tc_kernel<<<(unsigned)(P.n_tiles * P.n_splits), PJ_THREADS, L.total, stream>>>(p);
+    if (p.vec_ok && (F % PJ_KC) == 0) project_tc_kernel<true><<<(unsigned)(P.n_tiles * P.n_splits), PJ_THREADS, L.total, stream>>>(p);
+    else project_tc_kernel<false><<<(unsigned)(P.n_tiles * P.n_splits), PJ_THREADS, L.total, stream>>>(p);
     MMREC_LAUNCH_CHECK();
     project_reduce_kernel<<<(unsigned)((n_out + 7) / 8), 256, 0, stream>>>(n_out, d, P.N, P.n_splits, P.rows_padded, partial, bias,
                                                                          l2_normalize, Y, ldy);
