@@ -454,7 +454,10 @@ def run_ours(args):
             raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 or args.sharded or args.workload == "xls":
+        # the item-sharded driver; at world size 1 it is the weak-scaling baseline of the same per-GPU problem (no exchange)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=dev)
         from mmrec_b200 import sharded
         return sharded.bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler)
@@ -598,7 +601,7 @@ def run_reference(args):
     # the same workload as this repo's arm at --gpus N: weak scaling = N x the items and edges
     n = max(1, args.gpus)
     wl = Workload(args.workload, n_layers=3, items_scale=n)
-    O, adj, mm, ue, ie, batch = cpu_setup(wl, 1, "features" if n == 1 else "synthetic")
+    O, adj, mm, ue, ie, batch = cpu_setup(wl, 1, "features" if (n == 1 and args.workload != "xls" and not args.sharded) else "synthetic")
     threads = pick_threads(O, wl, adj, mm, ue, ie, batch)
     edges = wl.n_layers * adj._nnz() + mm._nnz()
     ta = tc = 0.0
@@ -612,7 +615,7 @@ def run_reference(args):
     value = edges * K / ta
     sample = (f"each step: FREEDOM forward on the full graph + score/mask/top-{TOPK} of ONE batch of {EVAL_BATCH} users "
               f"(bounded sample of the {wl.U}-user pass), torch CPU fp32 with {threads} threads (fastest of 4/8/16/32/64/all {os.cpu_count()} host cores)")
-    if n == 1:
+    if n == 1 and args.workload != "xls" and not args.sharded:
         workload = wl.describe("FREEDOM", wl.n_layers, 1)
     else:
         workload = (f"FREEDOM synthetic {wl.name} x{n} items: {wl.U} users, {wl.I} items ({wl.I // n} per GPU), {len(wl.tr_u)} train edges, "
@@ -638,6 +641,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="baby", choices=list(synth.SHAPES))
     ap.add_argument("--model", default=None, help="model class (default: the one BASELINE.json pairs with the workload)")
+    ap.add_argument("--sharded", action="store_true", help="run the item-sharded driver also at --gpus 1 (weak-scaling baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the BM3/sports and MGCN/clothing lines in extra")
     args = ap.parse_args()

@@ -112,6 +112,17 @@ int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d,
                    const float* gate_ref, int64_t ldgate,
                    void* stream);
 
+/* mmrec_spmm_f32 without the gate and with an ACCUMULATING Y (y_accumulate != 0: Y[r,:] += y[r,:]; the running-sum epilogue
+ * sees this call's y only, so the division belongs to the last call).  For graphs whose dense operand X does not fit the L2:
+ * the matrix is cut into column panels whose share of X does, the panels are multiplied one after the other and add up in Y
+ * -- every row of X is fetched from HBM once per layer instead of once per non-zero (ops.PanelCSR). */
+int mmrec_spmm_acc_f32(int64_t n_rows, int64_t n_cols, int d,
+                       const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                       const int32_t* tasks, int64_t n_tasks, int64_t n_cta_tasks, const int32_t* split_rows,
+                       int32_t* counters, float* partial,
+                       const float* X, int64_t ldx, float* Y, int64_t ldy,
+                       const float* acc_in, float* acc_out, int64_t ldacc, float acc_div, int y_accumulate, void* stream);
+
 /* The SpMMs of one propagation as ONE persistent cooperative launch (src/models/freedom.py:164-178: n_ui_layers products with
  * A_hat, the item-item product, the layer mean and `+ h`): the steps run in order on one resident grid, with a grid-wide
  * barrier before every step whose `sync_before` is set (= it reads what an earlier step wrote).  Every step needs its work

@@ -28,6 +28,8 @@ PROTOTYPES = {
     "mmrec_spmm_set_lanes": (_i32, [_i32]),
     "mmrec_spmm_f32": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64,
                               _f32, _p, _i64, _p]),
+    "mmrec_spmm_acc_f32": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64,
+                                  _f32, _i32, _p]),
     "mmrec_spmm_chain_f32": (_i32, [_i32, _i32, _p, _p]),
     "mmrec_project_set_path": (_i32, [_i32]),
     "mmrec_project_workspace_bytes": (_sz, [_i64, _i64, _i32]),

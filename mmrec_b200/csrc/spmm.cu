@@ -31,6 +31,7 @@ struct SpmmParams {
     float* Y; int64_t ldy;
     const float* acc_in; float* acc_out; int64_t ldacc; float acc_div;
     const float* gate_ref; int64_t ldgate;
+    int y_acc;                         // Y[r,:] += y[r,:] instead of = (column-panelled products: the panels of one matrix add up in Y)
     const float* post; int64_t post_row0; uint32_t spost;   // acc_out[r,:] += post[r - post_row0, :] for r >= post_row0 (after the division)
     int d;
     uint32_t sx, sy, sacc, sgate;      // the leading dimensions as byte strides (vector kernel: one IMAD.WIDE per row address)
@@ -87,8 +88,14 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, bool on, int 
     if (!on) return;
     if (p.Y) {
 #pragma unroll
-        for (int v = 0; v < C::V; ++v)
-            *row_f4(p.Y, p.sy, row, v * T + l) = y[v];
+        for (int v = 0; v < C::V; ++v) {
+            float4 o = y[v];
+            if (p.y_acc) {
+                const float4 q = *row_f4(p.Y, p.sy, row, v * T + l);
+                o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            *row_f4(p.Y, p.sy, row, v * T + l) = o;
+        }
     }
     if (p.acc_out) {
 #pragma unroll
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmParams p) {
             float acc = 0.f;
             for (int j = b; j < e; ++j) acc = fmaf(p.vals[j], p.X[(int64_t)p.colidx[j] * p.ldx + k], acc);
             if (p.gate_ref) acc *= c;
-            if (p.Y) p.Y[row * p.ldy + k] = acc;
+            if (p.Y) p.Y[row * p.ldy + k] = p.y_acc ? p.Y[row * p.ldy + k] + acc : acc;
             if (p.acc_out) {
                 float a = acc + (p.acc_in ? p.acc_in[row * p.ldacc + k] : 0.f);
                 if (p.acc_div != 1.0f) a = __fdiv_rn(a, p.acc_div);
@@ -372,6 +379,7 @@ __global__ void __launch_bounds__(256) spmm_generic_kernel(const SpmmParams p) {
     }
 }
 
+static thread_local int g_spmm_y_acc = 0;   // set by mmrec_spmm_acc_f32 around its call of mmrec_spmm_f32
 int g_spmm_lanes = 0;   // 0 = default lanes per task for the width; set by mmrec_spmm_set_lanes (tuning knob)
 
 template <int D, int T>
@@ -435,7 +443,8 @@ extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32
     p.counters = counters; p.partial = partial; p.X = X; p.ldx = ldx; p.Y = Y; p.ldy = ldy;
     p.acc_in = acc_in; p.acc_out = acc_out; p.ldacc = ldacc; p.acc_div = acc_div; p.gate_ref = gate_ref;
     p.ldgate = ldgate; p.d = d;
-    p.post = nullptr; p.post_row0 = 0; p.spost = 0;
+    p.post = nullptr; p.post_row0 = 0; p.spost = 0; p.y_acc = g_spmm_y_acc;
+    MMREC_CHECK_ARG(!(p.y_acc && gate_ref), "spmm: y_accumulate does not combine with the cosine gate");
     MMREC_CHECK_ARG(ldx < (1ll << 30) && ldy < (1ll << 30) && ldacc < (1ll << 30) && ldgate < (1ll << 30) && n_cols < (1ll << 31) &&
                     n_rows < (1ll << 31), "spmm: leading dimension / size out of range");
     p.sx = (uint32_t)(ldx * 4); p.sy = (uint32_t)(ldy * 4); p.sacc = (uint32_t)(ldacc * 4); p.sgate = (uint32_t)(ldgate * 4);
@@ -458,6 +467,20 @@ extern "C" int mmrec_spmm_f32(int64_t n_rows, int64_t n_cols, int d, const int32
     spmm_generic_kernel<<<(unsigned)grid, 256, 0, stream>>>(p);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
+}
+
+// mmrec_spmm_f32 whose Y output ACCUMULATES (Y += A X): the column panels of one matrix are multiplied one after the other
+// so that the gathered rows of X stay L2-resident (graphs whose dense operand does not fit the L2).
+extern "C" int mmrec_spmm_acc_f32(int64_t n_rows, int64_t n_cols, int d, const int32_t* rowptr, const int32_t* colidx,
+                                  const float* vals, const int32_t* tasks, int64_t n_tasks, int64_t n_cta_tasks,
+                                  const int32_t* split_rows, int32_t* counters, float* partial, const float* X, int64_t ldx, float* Y,
+                                  int64_t ldy, const float* acc_in, float* acc_out, int64_t ldacc, float acc_div, int y_accumulate,
+                                  void* stream_) {
+    g_spmm_y_acc = y_accumulate ? 1 : 0;
+    const int rc = mmrec_spmm_f32(n_rows, n_cols, d, rowptr, colidx, vals, tasks, n_tasks, n_cta_tasks, split_rows, counters, partial, X, ldx,
+                                  Y, ldy, acc_in, acc_out, ldacc, acc_div, nullptr, 0, stream_);
+    g_spmm_y_acc = 0;
+    return rc;
 }
 
 namespace mmrec {
@@ -510,7 +533,7 @@ extern "C" int mmrec_spmm_chain_f32(int d, int n_steps, const mmrec_spmm_step* s
         p.tasks = (const int4*)t.tasks; p.n_tasks = t.n_tasks; p.n_heavy = t.n_cta_tasks; p.split_rows = (const int4*)t.split_rows;
         p.counters = t.counters; p.partial = t.partial; p.X = t.X; p.ldx = t.ldx; p.Y = t.Y; p.ldy = t.ldy;
         p.acc_in = t.acc_in; p.acc_out = t.acc_out; p.ldacc = t.ldacc; p.acc_div = t.acc_div; p.gate_ref = nullptr; p.ldgate = 0;
-        p.post = t.post; p.post_row0 = t.post_row0; p.d = d;
+        p.post = t.post; p.post_row0 = t.post_row0; p.d = d; p.y_acc = 0;
         p.sx = (uint32_t)(t.ldx * 4); p.sy = (uint32_t)(t.ldy * 4); p.sacc = (uint32_t)(t.ldacc * 4); p.sgate = 0; p.spost = (uint32_t)(t.ldpost * 4);
         if (t.sync_before && i > 0) c.sync_mask |= 1u << i;
         const int64_t work = t.n_tasks > t.n_cta_tasks ? t.n_tasks : t.n_cta_tasks * 8;

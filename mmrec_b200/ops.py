@@ -168,11 +168,61 @@ class CSR:
 # ------------------------------------------------------------------------------------------------
 # K1: SpMM
 # ------------------------------------------------------------------------------------------------
-def spmm_raw(A: CSR, X: torch.Tensor, Y: Optional[torch.Tensor] = None, acc_in: Optional[torch.Tensor] = None,
+class PanelCSR:
+    """A sparse matrix cut into column panels (each an ordinary `CSR` over all rows and the panel's columns only) for graphs
+    whose dense operand does not fit the L2 (BASELINE config 5: 2M x 128 fp32 user table = 1 GB).  `spmm_raw` multiplies
+    the panels one after the other, accumulating in Y, so that the rows of X a panel gathers -- `panel_bytes` of them -- are
+    L2-resident: every row of X comes from HBM once per product instead of once per non-zero.  Same interface as `CSR` as far
+    as the propagation needs it (`n_rows`, `n_cols`, `nnz`, `t()`, `algorithmic_bytes`)."""
+
+    def __init__(self, n_rows, n_cols, panels, bounds, symmetric=False):
+        self.n_rows, self.n_cols, self.panels, self.bounds, self.symmetric = n_rows, n_cols, panels, bounds, symmetric
+        self.nnz = sum(p.nnz for p in panels)
+        self.n_tasks = min(p.n_tasks for p in panels) if panels else 0
+        self._t = None
+
+    @staticmethod
+    def from_coo(row, col, val, n_rows, n_cols, d, panel_bytes=48 << 20, sum_duplicates=True, symmetric=False) -> "PanelCSR":
+        cols_per_panel = max(1024, panel_bytes // (4 * d))
+        n_panels = max(1, -(-n_cols // cols_per_panel))
+        cols_per_panel = -(-n_cols // n_panels)
+        panels, bounds = [], []
+        for p in range(n_panels):
+            lo, hi = p * cols_per_panel, min(n_cols, (p + 1) * cols_per_panel)
+            m = (col >= lo) & (col < hi)
+            panels.append(CSR.from_coo(row[m], col[m], None if val is None else val[m], n_rows, n_cols, sum_duplicates, False))
+            bounds.append((lo, hi))
+        out = PanelCSR(n_rows, n_cols, panels, bounds, symmetric)
+        out._coo = (row, col, val, d, panel_bytes, sum_duplicates)
+        return out
+
+    def t(self):
+        if self.symmetric:
+            return self
+        if self._t is None:
+            row, col, val, d, pb, sd = self._coo
+            self._t = PanelCSR.from_coo(col, row, val, self.n_cols, self.n_rows, d, pb, sd, False)
+            self._t._t = self
+        return self._t
+
+    def algorithmic_bytes(self, d: int) -> int:
+        return 4 * (self.n_rows + 1) + 8 * self.nnz + 4 * self.n_cols * d + 4 * self.n_rows * d
+
+
+def spmm_raw(A, X: torch.Tensor, Y: Optional[torch.Tensor] = None, acc_in: Optional[torch.Tensor] = None,
              acc_out: Optional[torch.Tensor] = None, acc_div: float = 1.0, gate_ref: Optional[torch.Tensor] = None,
-             use_plan: bool = True):
+             use_plan: bool = True, y_accumulate: bool = False):
     """y = A X with the fused epilogue of include/mmrec_b200.h (no autograd).  Replaces `torch.sparse.mm`
     (`src/models/freedom.py:167,172`) plus the stack/mean (`:175-176`) and `+ h` (`:178`) that follow."""
+    if isinstance(A, PanelCSR):
+        if gate_ref is not None:
+            raise MMRecError("spmm: the cosine gate needs the whole row sum: not available on a PanelCSR")
+        last = len(A.panels) - 1
+        for i, P in enumerate(A.panels):                              # Y accumulates over the panels; the running sum takes every
+            run_in = None if acc_out is None else (acc_in if i == 0 else acc_out)   # panel's share, the division comes with the last one
+            spmm_raw(P, X, Y=Y, acc_in=run_in, acc_out=acc_out, acc_div=acc_div if i == last else 1.0, use_plan=use_plan,
+                     y_accumulate=Y is not None and (i > 0 or y_accumulate))
+        return
     _need_cuda(X, Y, acc_in, acc_out, gate_ref)
     lib = _lib.load()
     if X.dim() != 2 or X.shape[0] != A.n_cols:
@@ -185,6 +235,16 @@ def spmm_raw(A: CSR, X: torch.Tensor, Y: Optional[torch.Tensor] = None, acc_in: 
     if Y is None and acc_out is None:
         raise MMRecError("spmm: nothing to write")
     plan = use_plan and A.n_tasks > 0
+    if y_accumulate:
+        if gate_ref is not None or Y is None:
+            raise MMRecError("spmm: y_accumulate needs Y and no gate")
+        check(lib.mmrec_spmm_acc_f32(A.n_rows, A.n_cols, d, _ptr(A.rowptr), _ptr(A.colidx), _ptr(A.vals),
+                                     _ptr(A.tasks) if plan else None, A.n_tasks if plan else 0, A.n_cta_tasks if plan else 0,
+                                     _ptr(A.split_rows) if plan else None, _ptr(A.counters) if plan else None,
+                                     _ptr(A.partial(d)) if plan else None,
+                                     _ptr(X), X.stride(0), _ptr(Y), d, _ptr(acc_in), _ptr(acc_out), d, float(acc_div), 1, _stream()),
+              "mmrec_spmm_acc_f32")
+        return
     check(lib.mmrec_spmm_f32(A.n_rows, A.n_cols, d, _ptr(A.rowptr), _ptr(A.colidx), _ptr(A.vals),
                              _ptr(A.tasks) if plan else None, A.n_tasks if plan else 0, A.n_cta_tasks if plan else 0,
                              _ptr(A.split_rows) if plan else None, _ptr(A.counters) if plan else None,
@@ -323,7 +383,7 @@ def propagate_mean(A: CSR, ego: torch.Tensor, n_layers: int) -> torch.Tensor:
     """mean(E_0 .. E_L), E_{l+1} = A E_l -- the LightGCN propagation every graph model repeats
     (`src/models/freedom.py:169-176`, `bm3.py:86-92`, `lightgcn.py:116-123`, `mgcn.py:159-166`), with the
     running sum and the final division fused into the SpMM epilogue (no stack, no extra passes)."""
-    if CHAIN and n_layers >= 1 and not (torch.is_grad_enabled() and ego.requires_grad):
+    if CHAIN and n_layers >= 1 and isinstance(A, CSR) and not (torch.is_grad_enabled() and ego.requires_grad):
         return propagate_mean_fused(A, ego, n_layers)               # inference: all layers in one cooperative launch
     return _PropagateMeanFn.apply(ego, A, n_layers)
 

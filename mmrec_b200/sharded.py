@@ -52,7 +52,7 @@ class ItemShard:
     def to_global(self, local_idx):
         return local_idx * self.world + self.rank
 
-    def mm_csr(self, row, col, val, device):
+    def mm_csr(self, row, col, val, device, d=64, l2_bytes=96 << 20):
         """This rank's rows of an item-item matrix (global COO, e.g. FREEDOM's mm_adj) as a CSR over LOCAL rows and
         RANK-MAJOR columns: global item j sits at (j % world) * n_local + j // world, the layout `mmrec_peer_gather_f32`
         produces.  Needs equally sized shards."""
@@ -63,19 +63,27 @@ class ItemShard:
         mine = (row % self.world) == self.rank
         r = row[mine] // self.world
         c = (col[mine] % self.world) * self.n_local + col[mine] // self.world
-        return CSR.from_coo(torch.from_numpy(r).to(device), torch.from_numpy(c).to(device),
-                            torch.from_numpy(np.asarray(val, dtype=np.float32)[mine]).to(device), self.n_local,
-                            self.world * self.n_local, sum_duplicates=True)
+        rt, ct = torch.from_numpy(r).to(device), torch.from_numpy(c).to(device)
+        vt = torch.from_numpy(np.asarray(val, dtype=np.float32)[mine]).to(device)
+        n_cols = self.world * self.n_local
+        if n_cols * d * 4 > l2_bytes:
+            from .ops import PanelCSR
+            return PanelCSR.from_coo(rt, ct, vt, self.n_local, n_cols, d, sum_duplicates=True)
+        return CSR.from_coo(rt, ct, vt, self.n_local, n_cols, sum_duplicates=True)
 
-    def csrs(self, device):
-        """(users x local items, local items x users) as device CSRs."""
-        from .ops import CSR
+    def csrs(self, device, d=64, l2_bytes=96 << 20):
+        """(users x local items, local items x users) as device CSRs; a matrix whose dense operand ([n_cols, d] fp32) is
+        larger than `l2_bytes` comes as a column-panelled `ops.PanelCSR` (every panel's share of the operand stays L2-resident)."""
+        from .ops import CSR, PanelCSR
         u = torch.from_numpy(self.u).to(device)
         i = torch.from_numpy(self.i_local).to(device)
         v = torch.from_numpy(self.val).to(device)
-        a_ui = CSR.from_coo(u, i, v, self.n_users, self.n_local, sum_duplicates=False)
-        a_iu = CSR.from_coo(i, u, v, self.n_local, self.n_users, sum_duplicates=False)
-        return a_ui, a_iu
+
+        def build(r, c, n_rows, n_cols):
+            if n_cols * d * 4 > l2_bytes:
+                return PanelCSR.from_coo(r, c, v, n_rows, n_cols, d, sum_duplicates=False)
+            return CSR.from_coo(r, c, v, n_rows, n_cols, sum_duplicates=False)
+        return build(u, i, self.n_users, self.n_local), build(i, u, self.n_local, self.n_users)
 
 
 def _cuda_spmm(A, X, acc_in=None, acc_div=1.0, want_y=True):
@@ -387,14 +395,15 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     wl = Workload(args.workload, n_layers=3, items_scale=world)
     U, I, d = wl.U, wl.I, wl.d
     shard = ItemShard(wl.tr_u, wl.tr_i, U, I, rank, world)
-    a_ui, a_iu = shard.csrs(dev)
+    a_ui, a_iu = shard.csrs(dev, d)
     kr, kc, kv = wl.knn_coo()
-    mm_local = shard.mm_csr(kr, kc, kv, dev)                        # FREEDOM's item-item layer: this rank's rows, rank-major columns
+    mm_local = shard.mm_csr(kr, kc, kv, dev, d)                     # FREEDOM's item-item layer: this rank's rows, rank-major columns
     ue = torch.from_numpy(wl.user_emb).to(dev)
     ie = torch.from_numpy(wl.item_emb[shard.local_items]).to(dev)
+    U_eval = min(U, 8 * EVAL_BATCH) if U * I > (1 << 36) else U     # (very large jobs: a bounded sample of the user batches per step)
     batches = []
-    for lo in range(0, U, EVAL_BATCH):
-        hi = min(U, lo + EVAL_BATCH)
+    for lo in range(0, U_eval, EVAL_BATCH):
+        hi = min(U_eval, lo + EVAL_BATCH)
         m = torch.from_numpy(wl.eval_mask(lo, hi)).to(dev)
         batches.append((torch.arange(lo, hi, device=dev), m, local_mask(shard, m)))
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
@@ -404,7 +413,7 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     state = {}
 
-    px = None if os.environ.get("MMREC_EXCHANGE", "p2p") == "nccl" else PeerExchange.create(U, d, wl.n_layers, shard.n_local, dev, k=TOPK)
+    px = None if (world == 1 or os.environ.get("MMREC_EXCHANGE", "p2p") == "nccl") else PeerExchange.create(U, d, wl.n_layers, shard.n_local, dev, k=TOPK)
     have = torch.tensor([1.0 if px is not None else 0.0], device=dev)
     dist.all_reduce(have, op=dist.ReduceOp.MIN)
     if have.item() == 0.0:
@@ -538,19 +547,19 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
         algo_bytes = (wl.n_layers * (a_ui.algorithmic_bytes(d) + a_iu.algorithmic_bytes(d)) + mm_local.algorithmic_bytes(d)) * world
         nvl_bytes = wl.n_layers * 2 * (world - 1) / world * U * d * 4 + (world - 1) * shard.n_local * d * 4   # per rank: slices read + pushed, item rows gathered
         print(json.dumps({
-            "metric": "graph-prop edges/sec (+ full-catalog scored-items/sec in extra) @ d=64",
+            "metric": f"graph-prop edges/sec (+ full-catalog scored-items/sec in extra) @ d={d}",
             "value": edges / (msA * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": msA + msC, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"FREEDOM synthetic {wl.name} x{world} items: {U} users, {I} items ({I // world} per GPU), "
-                                   f"{len(wl.tr_u)} train edges, d={d}, {wl.n_layers} UI layers + 1 mm layer, top-{TOPK} over all users, "
-                                   f"eval batch {EVAL_BATCH}",
+                                   f"{len(wl.tr_u)} train edges, d={d}, {wl.n_layers} UI layers + 1 mm layer, top-{TOPK} over "
+                                   f"{'all' if U_eval == U else U_eval} users, eval batch {EVAL_BATCH}",
                        "l2": "flushed (512 MiB write) before every step",
                        "parallelism": f"item-sharded x{world}: per layer reduce-scatter + all-gather of the user table, item rows gathered once "
                                       f"for the item-item layer, per-user top-k merge on 1/{world} of the rows per rank",
                        "launch": mode, "user_exchange": exchange},
             "parity": parity,
-            "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U * I / (msC * 1e-3),
+            "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U_eval * I / (msC * 1e-3), "eval_users_per_step": U_eval,
                       "nvlink_bytes_per_rank_per_step_prop": nvl_bytes,
                       "limiting_collective": "per-layer user-table exchange (2 device barriers + (N-1)/N of [U, d] read and written per rank)"},
             "roofline": {"kernel": "spmm_vec_kernel<64> (per rank: 2 per UI layer + 1 item-item layer)", "bound": "hbm",
@@ -560,7 +569,7 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             "gpu_launches": int(e_all[1].item()), "clocks": clocks,
             "e2e": {"value": edges / (t[2].item() / K * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": int(e_all[2].item()),
                     "d2h_bytes_per_step": int(e_all[3].item()), "prop_ms": t[2].item() / K, "score_topk_ms": t[3].item() / K,
-                    "scored_items_per_sec": U * I / (t[3].item() / K * 1e-3)},
+                    "scored_items_per_sec": U_eval * I / (t[3].item() / K * 1e-3)},
         }))
     # Shut down in order: the captured graphs hold the barrier / collective work, drop them before the process group.  The
     # daemon timer only fires if the teardown of this torch/NCCL build blocks (rank 0 has printed its line by then).

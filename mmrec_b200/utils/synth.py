@@ -23,6 +23,10 @@ SHAPES = {
     "sports": (36000, 18000, 300000, 64, 4096),     # configs[2]
     "clothing": (40000, 23000, 280000, 64, 4096),   # configs[3]
     "xl": (2000000, 1000000, 50000000, 128, 4096),  # configs[4] (never with dense features)
+    # one GPU's share of a configs[4]-shaped job for the weak-scaling run (x N items and edges at N GPUs: 1M items at N = 8),
+    # d = 128, user table and item shard beyond the L2; fewer users / edges than configs[4] so that the synthetic graph is
+    # drawn in under a minute per rank
+    "xls": (250000, 125000, 2000000, 128, 4096),
 }
 
 

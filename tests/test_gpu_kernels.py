@@ -584,3 +584,32 @@ def test_spmm_chain_equals_separate_launches(dev, d, L, mm_layers):
     out.zero_(); gph.replay(); torch.cuda.synchronize()
     assert torch.equal(out, ops._propagate_mean_post_unfused(A, ego, L, None, None, 1, 0))
     assert int(A.counters.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_panel_csr_equals_plain_csr(dev, d):
+    """ops.PanelCSR (column panels multiplied one after the other, Y accumulating: the form for graphs whose dense operand
+    does not fit the L2) against the unpanelled CSR and the oracle, forward and backward of propagate_mean."""
+    from mmrec_b200 import ops
+    from mmrec_b200.ops import CSR, PanelCSR
+    n = 3000
+    r, c, v = rand_coo(n, n, 40000, seed=d)
+    rr, cc, vv = torch.cat([r, c]).to(dev), torch.cat([c, r]).to(dev), torch.cat([v, v]).to(dev)       # symmetric
+    A = CSR.from_coo(rr, cc, vv, n, n, symmetric=True)
+    P = PanelCSR.from_coo(rr, cc, vv, n, n, d, panel_bytes=700 * 4 * d, symmetric=True)               # ~5 panels
+    assert len(P.panels) >= 4 and P.nnz == A.nnz
+    X = torch.randn(n, d, generator=torch.Generator().manual_seed(1)).to(dev)
+    base = torch.randn(n, d, generator=torch.Generator().manual_seed(2)).to(dev)
+    Y1, Y2 = torch.empty(n, d, device=dev), torch.empty(n, d, device=dev)
+    a1, a2 = base.clone(), base.clone()
+    ops.spmm_raw(A, X, Y=Y1, acc_in=a1, acc_out=a1, acc_div=3.0)
+    ops.spmm_raw(P, X, Y=Y2, acc_in=a2, acc_out=a2, acc_div=3.0)
+    assert rel(Y2, Y1) < 1e-6 and rel(a2, a1) < 1e-6
+    e1 = X.clone().requires_grad_(True); e2 = X.clone().requires_grad_(True)
+    o1 = ops.propagate_mean(A, e1, 3); o2 = ops.propagate_mean(P, e2, 3)
+    assert rel(o2, o1) < 1e-6
+    w = torch.randn_like(o1)
+    (o1 * w).sum().backward(); (o2 * w).sum().backward()
+    assert rel(e2.grad, e1.grad) < 1e-6
+    ref = O.propagate_mean(torch.sparse_coo_tensor(torch.stack([rr.cpu(), cc.cpu()]), vv.cpu(), (n, n)), X.cpu(), 3)
+    assert rel(o2, ref) < 1e-5
