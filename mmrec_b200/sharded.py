@@ -52,7 +52,7 @@ class ItemShard:
     def to_global(self, local_idx):
         return local_idx * self.world + self.rank
 
-    def mm_csr(self, row, col, val, device, d=64, l2_bytes=96 << 20):
+    def mm_csr(self, row, col, val, device, d=64, l2_bytes=1 << 62):
         """This rank's rows of an item-item matrix (global COO, e.g. FREEDOM's mm_adj) as a CSR over LOCAL rows and
         RANK-MAJOR columns: global item j sits at (j % world) * n_local + j // world, the layout `mmrec_peer_gather_f32`
         produces.  Needs equally sized shards."""
@@ -71,9 +71,11 @@ class ItemShard:
             return PanelCSR.from_coo(rt, ct, vt, self.n_local, n_cols, d, sum_duplicates=True)
         return CSR.from_coo(rt, ct, vt, self.n_local, n_cols, sum_duplicates=True)
 
-    def csrs(self, device, d=64, l2_bytes=96 << 20):
+    def csrs(self, device, d=64, l2_bytes=1 << 62):
         """(users x local items, local items x users) as device CSRs; a matrix whose dense operand ([n_cols, d] fp32) is
-        larger than `l2_bytes` comes as a column-panelled `ops.PanelCSR` (every panel's share of the operand stays L2-resident)."""
+        larger than `l2_bytes` comes as a column-panelled `ops.PanelCSR`.  (Off by default: measured on B200 the panels LOSE --
+        1.27 ms -> 2.19 ms per layer at 32M non-zeros, d = 64; 0.35 -> 0.67 ms at the xls shape -- because every panel
+        re-reads and re-writes the whole output for a handful of non-zeros per row; profiles/r02_notes.md.)"""
         from .ops import CSR, PanelCSR
         u = torch.from_numpy(self.u).to(device)
         i = torch.from_numpy(self.i_local).to(device)
@@ -400,7 +402,7 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
     mm_local = shard.mm_csr(kr, kc, kv, dev, d)                     # FREEDOM's item-item layer: this rank's rows, rank-major columns
     ue = torch.from_numpy(wl.user_emb).to(dev)
     ie = torch.from_numpy(wl.item_emb[shard.local_items]).to(dev)
-    U_eval = min(U, 8 * EVAL_BATCH) if U * I > (1 << 36) else U     # (very large jobs: a bounded sample of the user batches per step)
+    U_eval = min(U, 8 * EVAL_BATCH) if U > 16 * EVAL_BATCH else U    # (very large jobs: a bounded sample of the user batches per step)
     batches = []
     for lo in range(0, U_eval, EVAL_BATCH):
         hi = min(U_eval, lo + EVAL_BATCH)
