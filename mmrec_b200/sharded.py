@@ -232,9 +232,19 @@ def propagate_mean_sharded_p2p(a_ui, a_iu, user_emb, item_emb_local, n_layers, p
     acc_i = item_emb_local.clone()
     main = torch.cuda.current_stream()
     side = _side_stream(dev)
-    ei_all = None
-    if mm_local is not None:                                         # publish the layer-0 item rows for the peers' gathers
+    hh = None
+    _mark("start")
+    if mm_local is not None:
+        # The item-item term needs layer-0 rows only, so it runs on the second stream from the start, underneath the UI
+        # layers: publish my item rows, barrier, gather the peers' rows straight from their memory, hh = mm_adj @ E_I.
         px.items.copy_(item_emb_local)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            px.barrier()
+            ei_all = torch.empty(px.world * px.n_local, d, dtype=torch.float32, device=dev)
+            ops.peer_gather(px.item_ptrs, px.n_local * d, ei_all)
+            hh = torch.empty(px.n_local, d, dtype=torch.float32, device=dev)
+            ops.spmm_raw(mm_local, ei_all, Y=hh)
     ue_flat = user_emb.reshape(-1)
     for l in range(1, n_layers + 1):
         last = l == n_layers
@@ -245,6 +255,7 @@ def propagate_mean_sharded_p2p(a_ui, a_iu, user_emb, item_emb_local, n_layers, p
         with torch.cuda.stream(side):
             ei_next, acc_i = _cuda_spmm(a_iu, eu, acc_in=acc_i, acc_div=div, want_y=not last)
         ops.spmm_raw(a_ui, ei, Y=px.parts[l - 1])                    # R_g E_Ig -> peer-visible partial of layer l
+        _mark(f"L{l} user-side spmm")
         acc_in = ue_flat[px.lo:px.hi] if l == 1 else px.acc
         if px.sync_in_kernel:
             # one launch: wait for every rank's partial, reduce my slice, store it to every rank, wait for every rank's stores
@@ -252,28 +263,50 @@ def propagate_mean_sharded_p2p(a_ui, a_iu, user_emb, item_emb_local, n_layers, p
                               acc_out=px.acc, acc_div=div, final_layer=last)
         else:
             px.barrier()                                             # every rank's partial of layer l is complete
+            _mark(f"L{l} barrier A")
             ops.peer_reduce_push(px.part_ptrs[l - 1], px.gath_ptrs[l - 1], U * d, px.rank, acc_in=acc_in, acc_out=px.acc, acc_div=div,
                                  final_layer=last)
+            _mark(f"L{l} reduce+push")
             px.barrier()                                             # every slice of the reduced table has landed
-        if l == 1 and mm_local is not None:                          # (the peers published their item rows before that exchange)
-            ei_all = torch.empty(px.world * px.n_local, d, dtype=torch.float32, device=dev)
-            ops.peer_gather(px.item_ptrs, px.n_local * d, ei_all)
+        _mark(f"L{l} barrier B")
         main.wait_stream(side)
+        _mark(f"L{l} join item-side stream")
         eu, ei = px.gath[l - 1], ei_next
     u_g = px.gath[n_layers - 1] if n_layers > 0 else user_emb
     if mm_local is not None:
-        if ei_all is None:                                           # n_layers == 0
-            if px.sync_in_kernel:
-                ops.peer_barrier(px.flag_ptrs, px.state, px.rank)
-            else:
-                px.barrier()
-            ei_all = torch.empty(px.world * px.n_local, d, dtype=torch.float32, device=dev)
-            ops.peer_gather(px.item_ptrs, px.n_local * d, ei_all)
-        ops.spmm_raw(mm_local, ei_all, acc_in=acc_i, acc_out=acc_i)  # i_g + mm_adj @ E_I  (freedom.py:178)
+        main.wait_stream(side)
+        acc_i = acc_i + hh                                           # i_g + mm_adj @ E_I  (freedom.py:178)
+    _mark("end")
     return u_g, acc_i
 
 
 _side = {}
+_timing = None                                                      # tuning aid: list of (label, event) while MMREC_SHARDED_TIMING is set
+
+
+def _mark(label):
+    if _timing is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        _timing.append((label, e))
+
+
+def timed_phases(fn, reps=3):
+    """Run `fn` eagerly `reps` times with CUDA events between the phases of `propagate_mean_sharded_p2p`; returns
+    [(label, mean microseconds since the previous mark)]."""
+    global _timing
+    acc = {}
+    order = []
+    for _ in range(reps):
+        _timing = []
+        fn()
+        torch.cuda.synchronize()
+        for (l0, e0), (l1, e1) in zip(_timing[:-1], _timing[1:]):
+            if l1 not in acc:
+                acc[l1] = 0.0; order.append(l1)
+            acc[l1] += e0.elapsed_time(e1) * 1e3 / reps
+    _timing = None
+    return [(l, acc[l]) for l in order]
 
 
 def _side_stream(device):
@@ -505,6 +538,11 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
                 tA += e[0].elapsed_time(e[1]); tC += e[2].elapsed_time(e[3])
                 launches += (n_launch["a"] + n_launch["c"]) if graphs else ops.launch_count() - l0
     dist.barrier()
+    phases = None
+    if os.environ.get("MMREC_SHARDED_TIMING") and px is not None:
+        with torch.no_grad():
+            phases = timed_phases(lambda: prop(ue, ie))
+        dist.barrier()
     # ---- e2e: the same calls with pinned HOST buffers, copies inside the timed region
     ue_h = torch.from_numpy(wl.user_emb).pin_memory()
     ie_h = torch.from_numpy(wl.item_emb[shard.local_items]).pin_memory()
@@ -563,7 +601,8 @@ def bench_sharded(args, rank, world, dev, Workload, peaks, ClockSampler):
             "parity": parity,
             "extra": {"prop_ms": msA, "score_topk_ms": msC, "scored_items_per_sec": U_eval * I / (msC * 1e-3), "eval_users_per_step": U_eval,
                       "nvlink_bytes_per_rank_per_step_prop": nvl_bytes,
-                      "limiting_collective": "per-layer user-table exchange (2 device barriers + (N-1)/N of [U, d] read and written per rank)"},
+                      "limiting_collective": "per-layer user-table exchange (2 device barriers + (N-1)/N of [U, d] read and written per rank)",
+                      "phases_us_rank0_eager": phases},
             "roofline": {"kernel": "spmm_vec_kernel<64> (per rank: 2 per UI layer + 1 item-item layer)", "bound": "hbm",
                          "achieved": algo_bytes / (msA * 1e-3) / 1e9 / world, "peak": pk["hbm_gbs"], "unit": "GB/s per GPU",
                          "frac": algo_bytes / (msA * 1e-3) / 1e9 / world / pk["hbm_gbs"], "traffic": None, "peak_src": pk["src"],
