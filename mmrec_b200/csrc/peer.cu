@@ -40,19 +40,53 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(int64_t n4, int world, co
 // slice only; a non-final layer does acc += sum and pushes the sum (the next layer's E_U), the final layer pushes
 // (acc + sum) / div (the propagated user table).  The caller synchronises the ranks before (partials complete) and
 // after (pushes visible) the call.
-__global__ void __launch_bounds__(256) peer_reduce_push_kernel(int64_t lo4, int64_t hi4, int world, const PeerParts parts, const PeerParts dst,
+template <int W, int U>
+__global__ void __launch_bounds__(256) peer_reduce_push_kernel(int64_t lo4, int64_t hi4, const PeerParts parts, const PeerParts dst,
                                                                const float4* __restrict__ acc_in, float4* __restrict__ acc_out, float div,
                                                                int final_layer) {
+    // W ranks, U elements per thread and trip: W * U sixteen-byte loads are in flight per thread before the first add (a peer
+    // load is a ~2-3 us round trip over NVLink; with one element per thread the kernel ran at ~150 GB/s per direction)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < hi4; i0 += stride * U) {
+        float4 v[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+#pragma unroll
+            for (int r = 0; r < W; ++r) v[u][r] = i < hi4 ? parts.p[r][i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= hi4) continue;
+            float4 s = v[u][0];
+#pragma unroll
+            for (int r = 1; r < W; ++r) { s.x += v[u][r].x; s.y += v[u][r].y; s.z += v[u][r].z; s.w += v[u][r].w; }   // rank order
+            float4 out = s;
+            if (acc_in) {
+                float4 a = acc_in[i - lo4];
+                a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+                if (final_layer) {
+                    if (div != 1.0f) { a.x = __fdiv_rn(a.x, div); a.y = __fdiv_rn(a.y, div); a.z = __fdiv_rn(a.z, div); a.w = __fdiv_rn(a.w, div); }
+                    out = a;
+                } else if (acc_out) {
+                    acc_out[i - lo4] = a;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < W; ++r) const_cast<float4*>(dst.p[r])[i] = out;
+        }
+    }
+}
+
+// any world size up to PEER_MAX (the common ones have their own instantiation above)
+__global__ void __launch_bounds__(256) peer_reduce_push_any_kernel(int64_t lo4, int64_t hi4, int world, const PeerParts parts, const PeerParts dst,
+                                                                   const float4* __restrict__ acc_in, float4* __restrict__ acc_out, float div,
+                                                                   int final_layer) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = lo4 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi4; i += stride) {
-        float4 v[PEER_MAX];
-#pragma unroll
-        for (int r = 0; r < PEER_MAX; ++r)
-            if (r < world) v[r] = parts.p[r][i];                     // all peer loads in flight before the first add
-        float4 s = v[0];
-#pragma unroll
-        for (int r = 1; r < PEER_MAX; ++r)
-            if (r < world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        float4 s = parts.p[0][i];
+        for (int r = 1; r < world; ++r) { const float4 v = parts.p[r][i]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
         float4 out = s;
         if (acc_in) {
             float4 a = acc_in[i - lo4];
@@ -64,9 +98,7 @@ __global__ void __launch_bounds__(256) peer_reduce_push_kernel(int64_t lo4, int6
                 acc_out[i - lo4] = a;
             }
         }
-#pragma unroll
-        for (int r = 0; r < PEER_MAX; ++r)
-            if (r < world) const_cast<float4*>(dst.p[r])[i] = out;
+        for (int r = 0; r < world; ++r) const_cast<float4*>(dst.p[r])[i] = out;
     }
 }
 
@@ -115,9 +147,18 @@ __global__ void peer_barrier_kernel(int world, int rank, const PeerFlags flags, 
 __global__ void __launch_bounds__(256) peer_gather_kernel(int64_t n4, int world, const PeerParts src, float4* __restrict__ dst) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t total = n4 * world;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int p = (int)(i / n4);
-        dst[i] = src.p[p][i - (int64_t)p * n4];
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {   // 4 peer loads in flight per thread
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < total) { const int p = (int)(i / n4); v[u] = src.p[p][i - (int64_t)p * n4]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < total) dst[i] = v[u];
+        }
     }
 }
 
@@ -169,11 +210,18 @@ extern "C" int mmrec_peer_reduce_push_f32(int64_t n, int world, int rank, const 
     const int64_t per = (n4 + world - 1) / world;                     // slice of this rank (the accumulator holds `per` float4)
     const int64_t lo4 = per * rank < n4 ? per * rank : n4, hi4 = lo4 + per < n4 ? lo4 + per : n4;
     if (hi4 <= lo4) return MMREC_OK;
-    int64_t grid = (hi4 - lo4 + 255) / 256;
+    const int U = world == 2 ? 4 : (world == 4 ? 2 : 1);
+    int64_t grid = (hi4 - lo4 + 256 * U - 1) / (256 * U);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
-    peer_reduce_push_kernel<<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, world, P, D, (const float4*)acc_in, (float4*)acc_out, acc_div,
-                                                                 final_layer);
+    const float4 *ai = (const float4*)acc_in;
+    float4* ao = (float4*)acc_out;
+    switch (world) {
+        case 2: peer_reduce_push_kernel<2, 4><<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, P, D, ai, ao, acc_div, final_layer); break;
+        case 4: peer_reduce_push_kernel<4, 2><<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, P, D, ai, ao, acc_div, final_layer); break;
+        case 8: peer_reduce_push_kernel<8, 1><<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, P, D, ai, ao, acc_div, final_layer); break;
+        default: peer_reduce_push_any_kernel<<<(unsigned)grid, 256, 0, stream>>>(lo4, hi4, world, P, D, ai, ao, acc_div, final_layer); break;
+    }
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }
@@ -190,7 +238,7 @@ extern "C" int mmrec_peer_gather_f32(int64_t n_each, int world, const void* cons
         S.p[r] = (const float4*)src[r];
     }
     const int64_t n4 = n_each / 4;
-    int64_t grid = (n4 * world + 255) / 256;
+    int64_t grid = (n4 * world + 1023) / 1024;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (grid > cap) grid = cap;
     peer_gather_kernel<<<(unsigned)grid, 256, 0, stream>>>(n4, world, S, (float4*)dst);
