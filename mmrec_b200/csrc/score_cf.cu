@@ -90,6 +90,25 @@ __device__ __forceinline__ void cf_tmem_wait16(uint32_t (&v)[16]) {
                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
                  :: "memory");
 }
+__device__ __forceinline__ void cf_tmem_ld32(uint32_t taddr, uint32_t (&a)[16], uint32_t (&b)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+          "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+          "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+          "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void cf_tmem_wait32(uint32_t (&a)[16], uint32_t (&b)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                   "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+                 :: "memory");
+}
 __device__ __forceinline__ float cf_max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -215,11 +234,17 @@ __device__ __forceinline__ void cf_epilogue(const CfParams& p, const CfSmem& L, 
             uint32_t va[16], vb[16];
             float gm[8];
             uint32_t w[4];
-            cf_tmem_ld16(t0, va);
 #pragma unroll
             for (int c = 0; c < 8; c += 2) {
-                cf_tmem_wait16(va);
-                cf_tmem_ld16(t0 + (c + 1) * 16, vb);
+                // 32 columns per tcgen05.ld (MMREC_CF_DEBUG bit 2: 16 per load, the next one requested before this one is used)
+                if (p.dbg & 4) {
+                    if (c == 0) cf_tmem_ld16(t0, va);
+                    cf_tmem_wait16(va);
+                    cf_tmem_ld16(t0 + (c + 1) * 16, vb);
+                } else {
+                    cf_tmem_ld32(t0 + c * 16, va, vb);
+                    cf_tmem_wait32(va, vb);
+                }
                 if (n_valid < CF_TILE) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
@@ -227,8 +252,10 @@ __device__ __forceinline__ void cf_epilogue(const CfParams& p, const CfSmem& L, 
                 }
                 if (PASS == 1) gm[c] = cf_max16(va);
                 const uint32_t lt0 = PASS == 2 ? cf_lt16(va, thr) : 0u;
-                cf_tmem_wait16(vb);
-                if (c + 2 < 8) cf_tmem_ld16(t0 + (c + 2) * 16, va);
+                if (p.dbg & 4) {
+                    cf_tmem_wait16(vb);
+                    if (c + 2 < 8) cf_tmem_ld16(t0 + (c + 2) * 16, va);
+                }
                 if (n_valid < CF_TILE) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)

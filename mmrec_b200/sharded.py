@@ -52,40 +52,26 @@ class ItemShard:
     def to_global(self, local_idx):
         return local_idx * self.world + self.rank
 
-    def mm_csr(self, row, col, val, device, d=64, l2_bytes=1 << 62):
-        """This rank's rows of an item-item matrix (global COO, e.g. FREEDOM's mm_adj) as a CSR over LOCAL rows and
-        RANK-MAJOR columns: global item j sits at (j % world) * n_local + j // world, the layout `mmrec_peer_gather_f32`
-        produces.  Needs equally sized shards."""
-        from .ops import CSR
+    def mm_coo(self, row, col, val):
+        """This rank's rows of an item-item matrix (global COO, e.g. FREEDOM's mm_adj) with LOCAL row ids and RANK-MAJOR
+        column ids: global item j sits at (j % world) * n_local + j // world, the layout `mmrec_peer_gather_f32` (or an
+        all-gather of the shards) produces.  Needs equally sized shards.  Host only (numpy)."""
         if self.n_items % self.world:
-            raise ValueError("mm_csr: n_items must be a multiple of the world size (equal shards)")
+            raise ValueError("mm_coo: n_items must be a multiple of the world size (equal shards)")
         row, col = np.asarray(row, dtype=np.int64), np.asarray(col, dtype=np.int64)
         mine = (row % self.world) == self.rank
-        r = row[mine] // self.world
-        c = (col[mine] % self.world) * self.n_local + col[mine] // self.world
-        rt, ct = torch.from_numpy(r).to(device), torch.from_numpy(c).to(device)
-        vt = torch.from_numpy(np.asarray(val, dtype=np.float32)[mine]).to(device)
+        return row[mine] // self.world, (col[mine] % self.world) * self.n_local + col[mine] // self.world, np.asarray(val, dtype=np.float32)[mine]
+
+    def mm_csr(self, row, col, val, device, d=64, l2_bytes=1 << 62):
+        """`mm_coo` as a device CSR (duplicates summed, as `coalesce()` does for FREEDOM's mm_adj, freedom.py:74)."""
+        from .ops import CSR
+        r, c, v = self.mm_coo(row, col, val)
+        rt, ct, vt = torch.from_numpy(r).to(device), torch.from_numpy(c).to(device), torch.from_numpy(v).to(device)
         n_cols = self.world * self.n_local
         if n_cols * d * 4 > l2_bytes:
             from .ops import PanelCSR
             return PanelCSR.from_coo(rt, ct, vt, self.n_local, n_cols, d, sum_duplicates=True)
         return CSR.from_coo(rt, ct, vt, self.n_local, n_cols, sum_duplicates=True)
-
-    def csrs(self, device, d=64, l2_bytes=1 << 62):
-        """(users x local items, local items x users) as device CSRs; a matrix whose dense operand ([n_cols, d] fp32) is
-        larger than `l2_bytes` comes as a column-panelled `ops.PanelCSR`.  (Off by default: measured on B200 the panels LOSE --
-        1.27 ms -> 2.19 ms per layer at 32M non-zeros, d = 64; 0.35 -> 0.67 ms at the xls shape -- because every panel
-        re-reads and re-writes the whole output for a handful of non-zeros per row; profiles/r02_notes.md.)"""
-        from .ops import CSR, PanelCSR
-        u = torch.from_numpy(self.u).to(device)
-        i = torch.from_numpy(self.i_local).to(device)
-        v = torch.from_numpy(self.val).to(device)
-
-        def build(r, c, n_rows, n_cols):
-            if n_cols * d * 4 > l2_bytes:
-                return PanelCSR.from_coo(r, c, v, n_rows, n_cols, d, sum_duplicates=False)
-            return CSR.from_coo(r, c, v, n_rows, n_cols, sum_duplicates=False)
-        return build(u, i, self.n_users, self.n_local), build(i, u, self.n_local, self.n_users)
 
 
 def _cuda_spmm(A, X, acc_in=None, acc_div=1.0, want_y=True):

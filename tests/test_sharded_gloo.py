@@ -66,6 +66,16 @@ def worker(rank, world, port, tmp):
         ref = O.propagate_mean(O.norm_adj_coo(g["inter_row"], g["inter_col"], U, I), torch.cat([ue, ie]), L)
         assert ((u_g - ref[:U]).norm() / ref[:U].norm()).item() < 1e-5
         assert ((i_loc - ref[U:][sh.local_items]).norm() / ref[U:][sh.local_items].norm()).item() < 1e-5
+        # the item-item layer of the sharded FREEDOM (freedom.py:166-167,178): all-gather of the layer-0 item rows (rank-major),
+        # local SpMM with this rank's rows of mm_adj -> i_g + mm_adj @ E_I
+        if I % world == 0:
+            mm_idx, mm_val = g["mm_adj_idx"], g["mm_adj_val"]
+            r, c, v = sh.mm_coo(mm_idx[0], mm_idx[1], mm_val)
+            mm_local = CpuMat(r, c, v, sh.n_local, world * sh.n_local)
+            i_full = sharded.mm_layer_sharded(sh, mm_local, ie[sh.local_items].clone(), i_loc.clone(), spmm=cpu_spmm)
+            mm = torch.sparse_coo_tensor(torch.from_numpy(mm_idx), torch.from_numpy(mm_val), (I, I))
+            ref_i = ref[U:] + torch.sparse.mm(mm, ie)
+            assert ((i_full - ref_i[sh.local_items]).norm() / ref_i[sh.local_items].norm()).item() < 1e-5
         # every shard's edge count adds up to the graph
         n = torch.tensor([sh.nnz]); dist.all_reduce(n)
         assert int(n.item()) == len(np.unique(g["inter_row"] * I + g["inter_col"]))
