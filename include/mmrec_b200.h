@@ -157,6 +157,10 @@ int mmrec_project_f32(int64_t n_out, const int64_t* idx, const float* table, int
                       const float* W, const float* bias, int d, int l2_normalize,
                       float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
 
+/* measurement aid (tools/probe_mma.py): cycles of `iters` back-to-back tcgen05.mma (cta_group::1, operands in shared memory,
+ * K-major no swizzle, M = 128, K = 32 bytes) per CTA, one CTA per SM; kind 0 = tf32, 1 = bf16 */
+int mmrec_debug_mma_rate(int kind, int N, int iters, int distinct, long long* cycles_per_cta, void* stream);
+
 /* measurement aid (tools/probe_stream.py): stream a [n_rows, F] fp32 table the way K2 does -- every CTA visits R rows
  * round-robin for burst_bytes contiguous bytes each, R * burst_bytes = 64 KB in flight per CTA -- to see what the DRAM
  * delivers for a given burst length */

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "mmrec_project_set_path": (_i32, [_i32]),
     "mmrec_project_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "mmrec_project_f32": (_i32, [_i64, _p, _p, _i64, _i64, _p, _p, _i32, _i32, _p, _i64, _p, _sz, _p]),
+    "mmrec_debug_mma_rate": (_i32, [_i32, _i32, _i32, _i32, _p, _p]),
     "mmrec_debug_stream_probe": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p]),
     "mmrec_score_set_path": (_i32, [_i32]),
     "mmrec_score_workspace_bytes": (_sz, [_i64, _i64, _i32]),

@@ -100,24 +100,29 @@ __global__ void __launch_bounds__(PJ_THREADS, 1) project_tc_kernel(const ProjPar
             uint32_t acc = 0;
             int s = 0;
             uint32_t par = 0;
+            // one thread's instruction stream feeds the tensor pipe: the four descriptors are built once and only their
+            // address field (16-byte units, low word) moves -- rebuilding them per instruction costs ~200 cycles per MMA
+            // against ~90 for the MMA itself (tools/probe_mma.py)
+            const uint64_t a_hi0 = smem_desc(sbase + L.a0, PJ_LBO_A, 128), a_lo0 = smem_desc(sbase + L.a0 + PJ_A_BYTES, PJ_LBO_A, 128);
+            const uint64_t b_hi0 = smem_desc(sbase + L.b0, LBO_B, 128), b_lo0 = smem_desc(sbase + L.b0 + L.b_bytes, LBO_B, 128);
+            const uint64_t ka = (2 * PJ_LBO_A) >> 4, kb = (2 * LBO_B) >> 4, st_step = L.stage_bytes >> 4;
+            uint64_t st = 0;
             for (int c = 0; c < n_my; ++c) {
                 mbar_wait(bar + s * 8, par);
                 mbar_wait(bar + (8 + s) * 8, par);
                 fence_after_sync();
-                const uint32_t st = sbase + s * L.stage_bytes;
+                uint64_t a_hi = a_hi0 + st, a_lo = a_lo0 + st, b_hi = b_hi0 + st, b_lo = b_lo0 + st;
 #pragma unroll
                 for (int j = 0; j < PJ_KC / 8; ++j) {
-                    const uint64_t a_hi = smem_desc(st + L.a0 + j * 2 * PJ_LBO_A, PJ_LBO_A, 128);
-                    const uint64_t a_lo = smem_desc(st + L.a0 + PJ_A_BYTES + j * 2 * PJ_LBO_A, PJ_LBO_A, 128);
-                    const uint64_t b_hi = smem_desc(st + L.b0 + j * 2 * LBO_B, LBO_B, 128);
-                    const uint64_t b_lo = smem_desc(st + L.b0 + L.b_bytes + j * 2 * LBO_B, LBO_B, 128);
                     mma_tf32(tmem_base, a_hi, b_hi, idesc, acc);
                     acc = 1;
                     mma_tf32(tmem_base, a_lo, b_hi, idesc, 1);
                     mma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+                    a_hi += ka; a_lo += ka; b_hi += kb; b_lo += kb;
                 }
                 mma_commit(bar + (16 + s) * 8);
-                if (++s == p.stages) { s = 0; par ^= 1; }
+                st += st_step;
+                if (++s == p.stages) { s = 0; par ^= 1; st = 0; }
             }
             mma_commit(bar + 24 * 8);
         }

@@ -38,25 +38,30 @@ namespace mmrec {
 using namespace tc;
 
 constexpr int CF_TILE = 128;                    // rows of one MMA operand tile (users: TMEM lanes; items: TMEM columns)
-constexpr int CF_KC = 32;                       // k per item slab
-constexpr int CF_SLAB = CF_TILE * CF_KC * 4;    // 16 KB
+// k per item slab: the whole K of a unit when it fits 32 KB (d <= 64: one bulk copy and one barrier round trip per unit),
+// else 32.  What bounds the passes at large batches is the slab ring, not the tensor pipe (profiles/r02_notes.md): the
+// bytes in flight per SM (ring size) over the round trip "copy lands -> MMAs -> commit -> producer refills".
+__host__ __device__ inline int cf_kc(int KP) { return KP <= 64 ? KP : 32; }
 constexpr int CF_EPI_WARPS = 16;                // (buffer parity, user half, TMEM lane quarter)
 constexpr int CF_THREADS = 64 + 32 * CF_EPI_WARPS;
-constexpr int CF_MAX_STAGES = 8;
+constexpr int CF_MAX_STAGES = 10;
 constexpr int CF_CAP = 512;                     // candidates one warp ranks per row
 constexpr int CF_EX_SLOTS = 128;                // CTAs (and key buffers) of the exact kernel
 constexpr float CF_EPS = 1.125f / 1024.f;       // |s~ - s| <= CF_EPS |u| |i|: two RN roundings to tf32 (2^-11 each) + accumulation slack
 
 struct CfSmem {
-    uint32_t a, slab0, bars, tmem_ptr, total;
+    uint32_t a, slab0, slab, bars, tmem_ptr, total;
     int stages;
 };
 __host__ __device__ inline CfSmem cf_smem(int KP) {
     CfSmem L;
     L.a = 0;
     L.slab0 = 2 * CF_TILE * KP * 4;             // the 256-user operand: two tiles of 128
-    L.stages = KP >= 128 ? 5 : CF_MAX_STAGES;
-    L.bars = L.slab0 + L.stages * CF_SLAB;
+    const uint32_t slab = CF_TILE * cf_kc(KP) * 4;
+    L.slab = slab;
+    L.stages = (int)((226u * 1024u - L.slab0 - 300u) / slab);        // as many slabs in flight as shared memory holds
+    if (L.stages > CF_MAX_STAGES) L.stages = CF_MAX_STAGES;
+    L.bars = L.slab0 + L.stages * slab;
     L.tmem_ptr = L.bars + 32 * 8;
     L.total = L.tmem_ptr + 16;
     return L;
@@ -137,27 +142,38 @@ __device__ __forceinline__ uint32_t cf_lt16(const uint32_t (&v)[16], float thr) 
 __device__ __forceinline__ void cf_producer(const CfParams& p, const CfSmem& L, uint32_t sbase, int64_t u0, int64_t u1) {
     const uint32_t bar = sbase + L.bars;
     const uint32_t a_bytes = 2 * CF_TILE * p.KP * 4;
-    const int kchunks = p.KP / CF_KC;
-    int64_t cur_pair = -1;
-    uint32_t a_cnt = 0, s = 0;
+    const int KC = cf_kc(p.KP);
+    const int kchunks = p.KP / KC;
+    // (pair, it) and the ring position advance by counting: a 64-bit division per unit is several hundred cycles of a
+    // single thread's dependent instructions, and this loop is what the slab ring's refill rate hangs on
+    int64_t pair = u0 / p.n_it;
+    int it = (int)(u0 - pair * p.n_it);
+    bool new_pair = true;
+    uint32_t a_cnt = 0, slot = 0, ph = 1;                            // ph: parity to wait for on the slot's "empty" barrier
     for (int64_t u = u0; u < u1; ++u) {
-        const int64_t pair = u / p.n_it;
-        const int it = (int)(u % p.n_it);
-        if (pair != cur_pair) {
+        if (new_pair) {
             if (a_cnt > 0) mbar_wait(bar + CB_AFREE * 8, (a_cnt - 1) & 1);   // every MMA that reads the old operand is done
             mbar_expect_tx(bar + CB_AFULL * 8, a_bytes);
             const char* src = (const char*)(p.Upk + pair * (int64_t)(2 * CF_TILE) * p.KP);
             for (uint32_t o = 0; o < a_bytes; o += 16384) bulk_g2s(sbase + L.a + o, src + o, 16384, bar + CB_AFULL * 8);
             ++a_cnt;
-            cur_pair = pair;
+            new_pair = false;
         }
-        for (int kc = 0; kc < kchunks; ++kc, ++s) {
-            const uint32_t slot = s % L.stages, use = s / L.stages;
-            mbar_wait(bar + (CB_EMPTY + slot) * 8, (use & 1) ^ 1);
-            mbar_expect_tx(bar + (CB_FULL + slot) * 8, CF_SLAB);
-            const float* src = p.Ipk + ((int64_t)it * (p.KP / 4) + kc * (CF_KC / 4)) * (CF_TILE / 8) * 32;
-            bulk_g2s(sbase + L.slab0 + slot * CF_SLAB, src, CF_SLAB, bar + (CB_FULL + slot) * 8);
+        const char* src = (const char*)(p.Ipk + (int64_t)it * p.KP * CF_TILE);
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const uint32_t fb = bar + (CB_FULL + slot) * 8;
+            mbar_wait(bar + (CB_EMPTY + slot) * 8, ph);
+            if (p.dbg & 16) {                                         // (tuning aid: no item traffic)
+                mbar_arrive(fb);
+            } else {
+                mbar_expect_tx(fb, L.slab);
+                const uint32_t dst = sbase + L.slab0 + slot * L.slab;
+                for (uint32_t o = 0; o < L.slab; o += 16384) bulk_g2s(dst + o, src + o, 16384, fb);
+            }
+            src += L.slab;
+            if (++slot == (uint32_t)L.stages) { slot = 0; ph ^= 1; }
         }
+        if (++it == p.n_it) { it = 0; ++pair; new_pair = true; }
     }
 }
 
@@ -166,41 +182,64 @@ __device__ __forceinline__ void cf_mma(const CfParams& p, const CfSmem& L, uint3
     const uint32_t bar = sbase + L.bars;
     constexpr uint32_t LBO = (CF_TILE / 8) * 128, SBO = 128;         // both operands: tiles of 128 rows
     const uint32_t idesc = idesc_tf32(CF_TILE, CF_TILE);
-    const int kchunks = p.KP / CF_KC;
+    const int KC = cf_kc(p.KP);
+    const int kchunks = p.KP / KC;
     const uint32_t half_bytes = CF_TILE * p.KP * 4;
-    int64_t cur_pair = -1;
-    uint32_t a_cnt = 0, s = 0;
+    uint32_t a_cnt = 0;
     int halves = 2;
-    for (int64_t u = u0, t = 0; u < u1; ++u, ++t) {
-        const int64_t pair = u / p.n_it;
-        const uint32_t buf = (uint32_t)t & 1;
-        mbar_wait(bar + (CB_TEMPTY + buf) * 8, (((uint32_t)t >> 1) & 1) ^ 1);     // accumulators drained by the epilogue
-        if (pair != cur_pair) {
+    // The issuing thread is a single instruction stream: measured (tools/probe_mma.py) ~200 cycles per tcgen05.mma when
+    // the descriptors are rebuilt around every instruction -- three times the 64 cycles the tensor pipe needs for M128
+    // N128 K8.  So the descriptors are built once and only their address field (low word, 16-byte units) moves.
+    const uint64_t a_desc0 = smem_desc(sbase + L.a, LBO, SBO), a_desc1 = smem_desc(sbase + L.a + half_bytes, LBO, SBO);
+    const uint64_t b_desc0 = smem_desc(sbase + L.slab0, LBO, SBO);
+    const uint64_t kstep = (2 * LBO) >> 4;                           // one K step of 8 = two 16-byte k blocks
+    int64_t pair = u0 / p.n_it;
+    int it = (int)(u0 - pair * p.n_it);
+    bool new_pair = true;
+    uint32_t slot = 0, ph = 0, buf = 0, tph = 1;                      // ring position / parity; accumulator buffer / its "empty" parity
+    uint64_t bd_slot = b_desc0;
+    const uint64_t slab_step = L.slab >> 4;
+    for (int64_t u = u0; u < u1; ++u) {
+        mbar_wait(bar + (CB_TEMPTY + buf) * 8, tph);                  // accumulators drained by the epilogue
+        if (new_pair) {
             mbar_wait(bar + CB_AFULL * 8, a_cnt & 1);
             ++a_cnt;
-            cur_pair = pair;
             halves = (pair * 2 * CF_TILE + CF_TILE < p.B) ? 2 : 1;
+            new_pair = false;
         }
         fence_after_sync();
-        for (int kc = 0; kc < kchunks; ++kc, ++s) {
-            const uint32_t slot = s % L.stages, use = s / L.stages;
-            mbar_wait(bar + (CB_FULL + slot) * 8, use & 1);
+        const uint32_t d0 = tmem_base + (buf * 2 + 0) * CF_TILE, d1 = d0 + CF_TILE;
+        uint64_t ad0 = a_desc0, ad1 = a_desc1;
+        for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(bar + (CB_FULL + slot) * 8, ph);
             fence_after_sync();
-            const uint32_t b_base = sbase + L.slab0 + slot * CF_SLAB;
-#pragma unroll
-            for (int j = 0; j < CF_KC / 8; ++j) {
-                const uint64_t bd = smem_desc(b_base + j * 2 * LBO, LBO, SBO);
-                const uint32_t a_off = (kc * (CF_KC / 4) + 2 * j) * LBO;
-                const uint32_t acc = (kc | j) ? 1u : 0u;
-                if (p.dbg & 2) continue;
-                mma_tf32(tmem_base + (buf * 2 + 0) * CF_TILE, smem_desc(sbase + L.a + a_off, LBO, SBO), bd, idesc, acc);
-                if (halves == 2)
-                    mma_tf32(tmem_base + (buf * 2 + 1) * CF_TILE, smem_desc(sbase + L.a + half_bytes + a_off, LBO, SBO), bd, idesc, acc);
+            uint64_t bd = bd_slot;
+            if (!(p.dbg & 2)) {
+                if (halves == 2) {
+#pragma unroll 8
+                    for (int j = 0; j < KC / 8; ++j) {
+                        const uint32_t acc = (kc | j) ? 1u : 0u;
+                        mma_tf32(d0, ad0, bd, idesc, acc);
+                        mma_tf32(d1, ad1, bd, idesc, acc);
+                        ad0 += kstep; ad1 += kstep; bd += kstep;
+                    }
+                } else {
+#pragma unroll 8
+                    for (int j = 0; j < KC / 8; ++j) {
+                        mma_tf32(d0, ad0, bd, idesc, (kc | j) ? 1u : 0u);
+                        ad0 += kstep; bd += kstep;
+                    }
+                }
             }
             mma_commit(bar + (CB_EMPTY + slot) * 8);                  // slab consumed -> slot back to the producer
+            bd_slot += slab_step;
+            if (++slot == (uint32_t)L.stages) { slot = 0; ph ^= 1; bd_slot = b_desc0; }
         }
         mma_commit(bar + (CB_TFULL + buf) * 8);                       // accumulators complete -> epilogue
-        if (u + 1 == u1 || (u + 1) / p.n_it != pair) mma_commit(bar + CB_AFREE * 8);
+        if (++it == p.n_it) { it = 0; ++pair; new_pair = true; }
+        if (new_pair || u + 1 == u1) mma_commit(bar + CB_AFREE * 8);
+        buf ^= 1;
+        if (buf == 0) tph ^= 1;
     }
 }
 
@@ -216,16 +255,17 @@ __device__ __forceinline__ void cf_epilogue(const CfParams& p, const CfSmem& L, 
     int64_t row = 0;
     bool live = false;
     float thr = INFINITY;
-    for (int u = u0 + par, t = par; u < u1; u += 2, t += 2) {
-        const int pair = u / p.n_it;
-        const int it = u - pair * p.n_it;
+    int pair = (u0 + par) / p.n_it;
+    int it = (u0 + par) - pair * p.n_it;
+    uint32_t fph = 0;
+    for (int u = u0 + par; u < u1; u += 2, fph ^= 1) {
         if (pair != cur_pair) {
             cur_pair = pair;
             row = (int64_t)pair * (2 * CF_TILE) + h * CF_TILE + q * 32 + lane;
             live = row < p.B;
             if (PASS == 2) thr = live ? __ldg(p.thr + row) : INFINITY;
         }
-        mbar_wait(bar + (CB_TFULL + par) * 8, ((uint32_t)t >> 1) & 1);
+        mbar_wait(bar + (CB_TFULL + par) * 8, fph);
         fence_after_sync();
         // (a whole half beyond the batch: nothing to read, but the buffer still has to be released)
         if ((int64_t)pair * (2 * CF_TILE) + h * CF_TILE < p.B && !(p.dbg & 1)) {
@@ -289,6 +329,8 @@ __device__ __forceinline__ void cf_epilogue(const CfParams& p, const CfSmem& L, 
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar + (CB_TEMPTY + par) * 8);
+        it += 2;
+        while (it >= p.n_it) { it -= p.n_it; ++pair; }
     }
 }
 

@@ -72,29 +72,36 @@ __device__ __forceinline__ void tc_mma_issuer(const ScoreTcParams& p, const TcSm
     const int kchunks = p.KP / TC_KC;
     mbar_wait(bar + 0 * 8, 0);
     fence_after_sync();
-    uint32_t s = 0;
+    // descriptors are built once; per instruction only the address field moves (see tools/probe_mma.py: rebuilding them
+    // around every MMA makes the issuing thread, not the tensor pipe, the limit)
+    const uint64_t a_hi0 = smem_desc(sbase + L.u_hi, LBO_A, SBO), a_lo0 = smem_desc(sbase + L.u_lo, LBO_A, SBO);
+    const uint64_t b0 = smem_desc(sbase + L.slab0, LBO_B, SBO);
+    const uint64_t ka = (2 * LBO_A) >> 4, kb = (2 * LBO_B) >> 4, slab_step = TC_SLAB_BYTES >> 4;
+    uint32_t slot = 0, ph = 0;
+    uint64_t bd_slot = b0;
     for (int it = it0, t = 0; it < it1; ++it, ++t) {
         const uint32_t buf = t & 1;
         mbar_wait(bar + (11 + buf) * 8, ((t >> 1) & 1) ^ 1);     // accumulator drained by the epilogue
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * TC_N;
         uint32_t acc = 0;
-        for (int c = 0; c < 2 * kchunks; ++c, ++s) {
-            const uint32_t slot = s % L.stages, use = s / L.stages;
-            mbar_wait(bar + (1 + slot) * 8, use & 1);
+        uint64_t a_hi = a_hi0, a_lo = a_lo0;
+        for (int c = 0; c < 2 * kchunks; ++c) {
+            mbar_wait(bar + (1 + slot) * 8, ph);
             fence_after_sync();
             const bool item_lo = c >= kchunks;
-            const int kc = c % kchunks;
-            const uint32_t b_base = sbase + L.slab0 + slot * TC_SLAB_BYTES;
+            if (c == kchunks) { a_hi = a_hi0; a_lo = a_lo0; }     // second sweep over K: the items' lo parts
+            uint64_t bd = bd_slot;
 #pragma unroll
             for (int j = 0; j < TC_KC / 8; ++j) {
-                const uint64_t bd = smem_desc(b_base + j * 2 * LBO_B, LBO_B, SBO);
-                const uint32_t a_off = (kc * (TC_KC / 4) + 2 * j) * LBO_A;
-                mma_tf32(d_tmem, smem_desc(sbase + L.u_hi + a_off, LBO_A, SBO), bd, idesc, acc);
+                mma_tf32(d_tmem, a_hi, bd, idesc, acc);
                 acc = 1;
-                if (!item_lo) mma_tf32(d_tmem, smem_desc(sbase + L.u_lo + a_off, LBO_A, SBO), bd, idesc, 1);
+                if (!item_lo) mma_tf32(d_tmem, a_lo, bd, idesc, 1);
+                a_hi += ka; a_lo += ka; bd += kb;
             }
             mma_commit(bar + (5 + slot) * 8);                     // slab consumed -> slot back to the producer
+            bd_slot += slab_step;
+            if (++slot == (uint32_t)L.stages) { slot = 0; ph ^= 1; bd_slot = b0; }
         }
         mma_commit(bar + (9 + buf) * 8);                          // accumulator complete -> epilogue
     }
@@ -215,3 +222,75 @@ int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
 }
 
 }  // namespace mmrec
+
+// ---- measurement aid: how many cycles does one tcgen05.mma (cta_group::1, both operands in shared memory, K-major, no swizzle
+// -- the form every tensor-core kernel of this library issues) take when nothing else runs?  One CTA per SM, one thread
+// issues `iters` MMAs of M = 128, the given N and K = 32 bytes (8 tf32 / 16 bf16) into one accumulator, commits and waits.
+namespace mmrec {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int iters, int distinct, long long* __restrict__ cycles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_ptr_sm;
+    __shared__ __align__(8) unsigned long long bar_sm;
+    const uint32_t sbase = tc::smem_u32(smem);
+    const uint32_t bar = tc::smem_u32(&bar_sm);
+    for (int i = threadIdx.x; i < 48 * 1024; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;   // 192 KB of zeros
+    if (threadIdx.x == 0) { tc::mbar_init(bar, 1); tc::mbar_fence_init(); }
+    if (threadIdx.x < 32) { tc::tmem_alloc(tc::smem_u32(&tmem_ptr_sm), 512); tc::tmem_relinquish(); }
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_ptr_sm;
+    if (threadIdx.x == 0) {
+        const uint32_t LBO_A = (128 / 8) * 128, LBO_B = (uint32_t)(N / 8) * 128;
+        // instruction descriptors: tf32 (a/b format 2) or bf16 (format 1), fp32 accumulate, K-major both
+        const uint32_t idesc = kind == 0 ? tc::idesc_tf32(128, N)
+                                         : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
+        const long long t0 = clock64();
+        if (distinct == 0) {
+            // lean issue loop: descriptors built once, only the address field moves (8 K steps, unrolled)
+            const uint64_t a0 = tc::smem_desc(sbase, LBO_A, 128), b0 = tc::smem_desc(sbase + 65536, LBO_B, 128);
+            const uint64_t ka = (2 * LBO_A) >> 4, kb = (2 * LBO_B) >> 4;
+            for (int i = 0; i < iters; i += 8) {
+                uint64_t ad = a0, bd = b0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (kind == 0) tc::mma_tf32(tmem, ad, bd, idesc, (i | j) ? 1u : 0u);
+                    else mma_f16(tmem, ad, bd, idesc, (i | j) ? 1u : 0u);
+                    ad += ka; bd += kb;
+                }
+            }
+        } else
+        for (int i = 0; i < iters; ++i) {
+            const uint32_t off = (uint32_t)(i % distinct) * 2 * LBO_A;            // walk over `distinct` K steps of the operands
+            const uint64_t ad = tc::smem_desc(sbase + off, LBO_A, 128);
+            const uint64_t bd = tc::smem_desc(sbase + 65536 + (uint32_t)(i % distinct) * 2 * LBO_B, LBO_B, 128);
+            if (kind == 0) tc::mma_tf32(tmem, ad, bd, idesc, i > 0);
+            else mma_f16(tmem, ad, bd, idesc, i > 0);
+        }
+        tc::mma_commit(bar);
+        tc::mbar_wait(bar, 0);
+        const long long t1 = clock64();
+        cycles[blockIdx.x] = t1 - t0;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace mmrec
+
+extern "C" int mmrec_debug_mma_rate(int kind, int N, int iters, int distinct, long long* cycles_per_cta, void* stream_) {
+    MMREC_CHECK_ARG((kind == 0 || kind == 1) && (N == 64 || N == 128 || N == 256) && iters >= 1 && distinct >= 0 && distinct <= 8 && cycles_per_cta,
+                    "mma_rate: kind 0 (tf32) | 1 (bf16), N in {64,128,256}, 1 <= distinct <= 8");
+    MMREC_CUDA(cudaFuncSetAttribute(mmrec::mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    mmrec::mma_rate_kernel<<<mmrec::sm_count(), 128, 192 * 1024, (cudaStream_t)stream_>>>(kind, N, iters, distinct, cycles_per_cta);
+    MMREC_LAUNCH_CHECK();
+    return MMREC_OK;
+}

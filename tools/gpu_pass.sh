@@ -5,6 +5,6 @@ for dbg in $1; do
   python - <<PY
 import csv
 rows=[r for r in csv.reader(open("gpurun_out/pass_dbg$dbg.csv")) if len(r)>10 and r[0].isdigit()]
-print("dbg=$dbg", [(r[4].split('::')[1].split('(')[0][:18], r[-1]) for r in rows[-7:]])
+print("dbg=$dbg", [(r[4].split("(")[0][-24:], r[-1]) for r in rows[-8:]])
 PY
 done
