@@ -661,36 +661,90 @@ __global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int G_va
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// exact fp32 score of one (user, item) pair.  THE arithmetic of this file's results: four fmaf chains (element c goes to
-// chain c % 4, ascending c), then (s0 + s1) + (s2 + s3).  One thread per pair, 16-byte loads when the rows allow it.
+// exact fp32 score of one (user, item) pair.  THE arithmetic of this file's results, chosen so that a group of lanes can
+// compute it from one coalesced read of the item row:
+//     L = 8 / 16 / 32 blocks of four elements (d <= 32 / 64 / 128; elements beyond d count as 0),
+//     p_l = fmaf(u[4l+3], v[4l+3], fmaf(u[4l+2], v[4l+2], fmaf(u[4l+1], v[4l+1], fmaf(u[4l], v[4l], 0)))),
+//     then the butterfly tree  p_a += p_(a + w)  for a < w,  w = L/2, L/4, ..., 1;  the score is p_0.
+// cf_dot_thread is one thread doing all of it (exact kernel: every item of a flagged row); cf_dot_round is a warp doing
+// 32 candidates, L lanes per item row, the tree run as a transposed butterfly so that each lane ends up with the
+// complete score of one candidate.  Float addition commutes, so both give the same bits.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, const float* __restrict__ v, int d, bool vec_ok) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+__host__ __device__ constexpr int cf_lpr(int d) { return d <= 32 ? 8 : (d <= 64 ? 16 : 32); }
+
+__device__ __forceinline__ float4 cf_load4(const float* __restrict__ row, int l, int d, bool vec_ok) {
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (vec_ok) {                                                    // d % 4 == 0, rows 16-byte aligned
-        const int n4 = d >> 2;
-        for (int i0 = 0; i0 < n4; i0 += 8) {                         // 8 x 16 bytes of the item row in flight
-            float4 x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = i0 + i < n4 ? ldg4(v + 4 * (i0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (i0 + i < n4) {
-                    const float4 uu = *reinterpret_cast<const float4*>(u_sm + 4 * (i0 + i));
-                    s0 = fmaf(uu.x, x[i].x, s0); s1 = fmaf(uu.y, x[i].y, s1); s2 = fmaf(uu.z, x[i].z, s2); s3 = fmaf(uu.w, x[i].w, s3);
-                }
-            }
-        }
+        if (4 * l < d) x = ldg4(row + 4 * l);
     } else {
-        int c = 0;
-        for (; c + 3 < d; c += 4) {
-            s0 = fmaf(u_sm[c], __ldg(v + c), s0); s1 = fmaf(u_sm[c + 1], __ldg(v + c + 1), s1);
-            s2 = fmaf(u_sm[c + 2], __ldg(v + c + 2), s2); s3 = fmaf(u_sm[c + 3], __ldg(v + c + 3), s3);
-        }
-        if (c < d) s0 = fmaf(u_sm[c], __ldg(v + c), s0);
-        if (c + 1 < d) s1 = fmaf(u_sm[c + 1], __ldg(v + c + 1), s1);
-        if (c + 2 < d) s2 = fmaf(u_sm[c + 2], __ldg(v + c + 2), s2);
+        if (4 * l < d) x.x = __ldg(row + 4 * l);
+        if (4 * l + 1 < d) x.y = __ldg(row + 4 * l + 1);
+        if (4 * l + 2 < d) x.z = __ldg(row + 4 * l + 2);
+        if (4 * l + 3 < d) x.w = __ldg(row + 4 * l + 3);
     }
-    return (s0 + s1) + (s2 + s3);
+    return x;
+}
+__device__ __forceinline__ float cf_chain4(const float4 u, const float4 x) {
+    return fmaf(u.w, x.w, fmaf(u.z, x.z, fmaf(u.y, x.y, fmaf(u.x, x.x, 0.f))));
+}
+
+template <int LPR>
+__device__ __forceinline__ float cf_dot_thread_t(const float* __restrict__ u_sm /* zero-padded to 128 */, const float* __restrict__ v, int d, bool vec_ok) {
+    float p[LPR];
+#pragma unroll
+    for (int l0 = 0; l0 < LPR; l0 += 8) {                            // 8 x 16 bytes of the item row in flight
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = cf_load4(v, l0 + i, d, vec_ok);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[l0 + i] = cf_chain4(*reinterpret_cast<const float4*>(u_sm + 4 * (l0 + i)), x[i]);
+    }
+#pragma unroll
+    for (int w = LPR / 2; w >= 1; w >>= 1)
+#pragma unroll
+        for (int a = 0; a < w; ++a) p[a] = p[a] + p[a + w];
+    return p[0];
+}
+__device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, const float* __restrict__ v, int d, bool vec_ok) {
+    return d <= 32 ? cf_dot_thread_t<8>(u_sm, v, d, vec_ok) : (d <= 64 ? cf_dot_thread_t<16>(u_sm, v, d, vec_ok) : cf_dot_thread_t<32>(u_sm, v, d, vec_ok));
+}
+
+// 32 candidates cand[t0 .. t0 + 31] (negative = dropped, beyond n = absent): returns, in lane (sub, l) = (lane / LPR, lane % LPR),
+// the score of candidate t0 + l * (32 / LPR) + sub.  `uu` = this lane's four elements 4l .. 4l + 3 of the user row.
+// One load instruction covers 32 / LPR whole item rows (contiguous 16-byte pieces: every 128-byte line is touched once
+// -- a lane per candidate touches 32 lines per instruction and the L1 tag stage becomes the limit).
+template <int LPR>
+__device__ __forceinline__ float cf_dot_round(const float4 uu, const float* __restrict__ Ie, int64_t ldi, int d, bool vec_ok,
+                                              const int32_t* cand, int t0, int n, int lane) {
+    constexpr int RPI = 32 / LPR, NI = LPR;
+    const int l = lane & (LPR - 1), sub = lane / LPR;
+    float p[NI];
+#pragma unroll
+    for (int h = 0; h < NI; h += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = t0 + (h + i) * RPI + sub;
+            const int item = t < n ? cand[t] : -1;
+            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (item >= 0) x[i] = cf_load4(Ie + (int64_t)item * ldi, l, d, vec_ok);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[h + i] = cf_chain4(uu, x[i]);
+    }
+    // transposed butterfly: at width w the lanes with bit w set keep the upper half of their values, the others the lower
+    // half, and each adds what its partner sends of the same candidates; value count and lane-group size halve together
+#pragma unroll
+    for (int w = LPR / 2; w >= 1; w >>= 1) {
+        const bool up = (l & w) != 0;
+#pragma unroll
+        for (int a = 0; a < w; ++a) {
+            const float keep = up ? p[a + w] : p[a];
+            const float send = up ? p[a] : p[a + w];
+            p[a] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return p[0];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -699,7 +753,7 @@ __device__ __forceinline__ float cf_dot_thread(const float* __restrict__ u_sm, c
 //   * the set bits come out in ascending item order (lane = bitmap word, positions by a warp prefix sum);
 //   * the mask is applied from the mask's side: lane q looks its masked item up in the sorted candidate list (binary
 //     search), O(m log n) instead of n x m comparisons;
-//   * one exact dot product per lane and round (cf_dot_thread);
+//   * exact scores 32 candidates at a time, 8 / 16 / 32 lanes per item row (cf_dot_round: coalesced reads);
 //   * ranking counts, per element, the larger 32-bit value keys (one LDS broadcast feeds up to four elements of the
 //     lane); equal values are ordered by item index = list position in a second pass that runs only when the rank sum
 //     shows that two candidates share a value.
@@ -754,7 +808,8 @@ __device__ __forceinline__ void cf_rank_sweeps(const int32_t* cand, const uint32
 }
 
 constexpr int CF_FIN_WARPS = 4;
-__global__ void __launch_bounds__(32 * CF_FIN_WARPS) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
+template <int LPR>
+__global__ void __launch_bounds__(32 * CF_FIN_WARPS, LPR <= 16 ? 8 : 6) cf_final_kernel(int64_t nb, int n_it, int64_t n_items, int d, int k, int64_t item_offset,
                                                                      const uint4* __restrict__ bitmap, const int64_t* __restrict__ users,
                                                                      const float* __restrict__ Ue, int64_t ldu, const float* __restrict__ Ie, int64_t ldi,
                                                                      const int32_t* __restrict__ mask_ptr, const int32_t* __restrict__ mask_items,
@@ -763,7 +818,6 @@ __global__ void __launch_bounds__(32 * CF_FIN_WARPS) cf_final_kernel(int64_t nb,
                                                                      float* __restrict__ out_val) {
     __shared__ int32_t cand_all[CF_FIN_WARPS][CF_CAP];
     __shared__ uint32_t key_all[CF_FIN_WARPS][CF_CAP];
-    __shared__ __align__(16) float u_all[CF_FIN_WARPS][128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * CF_FIN_WARPS + warp;
     if (row >= nb) return;
@@ -783,12 +837,6 @@ __global__ void __launch_bounds__(32 * CF_FIN_WARPS) cf_final_kernel(int64_t nb,
     if (flagged) { condemn(0); return; }
     int32_t* cand = cand_all[warp];
     uint32_t* keys = key_all[warp];
-    float* u_sm = u_all[warp];
-    {
-        const float* u = Ue + urow * ldu;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) u_sm[c * 32 + lane] = c * 32 + lane < d ? __ldg(u + c * 32 + lane) : 0.f;
-    }
     // 1. set bits -> candidate list in ascending item order; keys[] = 1 marks a live candidate
     int n = 0;
     for (int w0 = 0; w0 < n_it; w0 += 32) {
@@ -834,15 +882,20 @@ __global__ void __launch_bounds__(32 * CF_FIN_WARPS) cf_final_kernel(int64_t nb,
         }
     }
     __syncwarp();
-    // 3. exact fp32 scores (float_key of a real score is never 0; -NaN would be: such a candidate is dropped)
+    // 3. exact fp32 scores (float_key of a real score is never 0; -NaN would be: such a candidate is dropped).  Dropped
+    //    candidates are marked in cand[] first (sign bit) so that a round reads one word per candidate.
+    for (int t = lane; t < n; t += 32)
+        if (keys[t] == 0u || cand[t] >= n_items) cand[t] |= (int32_t)0x80000000;
+    __syncwarp();
     const bool vec_ok = (ldi & 3) == 0 && (d & 3) == 0 && ((((uintptr_t)Ie) & 15) == 0);
+    const bool vec_u = (ldu & 3) == 0 && (d & 3) == 0 && ((((uintptr_t)Ue) & 15) == 0);
+    const float4 uu = cf_load4(Ue + urow * ldu, lane & (LPR - 1), d, vec_u);
     int kept = 0;
     for (int t0 = 0; t0 < n; t0 += 32) {
-        const int t = t0 + lane;
-        if (t < n && keys[t] != 0u) {
-            const int item = cand[t];
-            uint32_t key = 0u;
-            if (item < n_items) key = float_key(cf_dot_thread(u_sm, Ie + (int64_t)item * ldi, d, vec_ok));
+        const float sc = cf_dot_round<LPR>(uu, Ie, ldi, d, vec_ok, cand, t0, n, lane);
+        const int t = t0 + (lane & (LPR - 1)) * (32 / LPR) + lane / LPR;
+        if (t < n) {
+            const uint32_t key = cand[t] >= 0 ? float_key(sc) : 0u;
             kept += key != 0u;
             keys[t] = key;
         }
@@ -1181,8 +1234,13 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
         cf_pass_kernel<2, 8><<<grid, CF_THREADS, L.total, stream>>>(p);
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
-        cf_final_kernel<<<(unsigned)((nb + CF_FIN_WARPS - 1) / CF_FIN_WARPS), 32 * CF_FIN_WARPS, 0, stream>>>(nb, (int)P.n_it, n_items, d, k, item_offset, bitmap, ub, ue, ldu, Ie, ldi, mp,
-                                                                      mitems, flags, counter, row_of_slot, out_idx + r0 * k, out_val + r0 * k);
+        {
+            const unsigned fg = (unsigned)((nb + CF_FIN_WARPS - 1) / CF_FIN_WARPS);
+#define CF_FINAL(LPR) cf_final_kernel<LPR><<<fg, 32 * CF_FIN_WARPS, 0, stream>>>(nb, (int)P.n_it, n_items, d, k, item_offset, bitmap, ub, ue, ldu, Ie, ldi, mp, \
+                                                                            mitems, flags, counter, row_of_slot, out_idx + r0 * k, out_val + r0 * k)
+            if (cf_lpr(d) == 8) CF_FINAL(8); else if (cf_lpr(d) == 16) CF_FINAL(16); else CF_FINAL(32);
+#undef CF_FINAL
+        }
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
         cf_exact_kernel<<<CF_EX_SLOTS, 256, 0, stream>>>(ub, ue, ldu, n_items, Ie, ldi, d, k, item_offset, mp, mitems, counter, row_of_slot, keys,
