@@ -1,15 +1,20 @@
 // K3: full-catalog scoring fused with mask + top-k as a CERTIFIED FILTER on the tensor cores.
 //
 // The score matrix (115 MB per 4096 users at 7k items, 16 GB at 1M) is never written and no threshold depends on
-// timing.  The tensor cores (tcgen05, kind::tf32, ONE pass over operands rounded to tf32) compute APPROXIMATE scores
-// s~ with a proven bound |s~ - s| <= eps * |u| * max|i|; they are only used to decide which (user, item) pairs can
+// timing.  The tensor cores (tcgen05, kind::f16, ONE pass over operands rounded to fp16 after a power-of-two scaling:
+// the same 11-bit significand as tf32 at twice the MMA rate and half the operand bytes) compute APPROXIMATE scores
+// s~ with a proven bound |s~ - s| <= eps * |u| * max|i| (+ a subnormal term that only matters for degenerate
+// tables, see cf_thr_kernel); they are only used to decide which (user, item) pairs can
 // be in the top-k.  Every pair that can is then scored again in full fp32 (fmaf chain, the arithmetic of the exact
 // kernel below), and the final order is taken on those fp32 values -- so the result is the fp32 top-k, tie -> lower
 // item index, exactly the contract of topk.cu.
 //
-//   cf_pack_kernel      operands -> tf32 (round to nearest) in the UMMA canonical K-major no-swizzle layout, tiles of
-//                       128 rows; row norms (users) / maximum row norm (catalogue).  The catalogue side is packed once
-//                       per embedding table (mmrec_catalog_pack_f32), not once per batch.
+//   cf_pack_kernel      operands -> fp16 (round to nearest) in the UMMA canonical K-major no-swizzle layout, tiles of
+//                       128 rows, scaled by a power of two (per user row; one for the whole catalogue) so that the
+//                       largest element lands in [2^14, 2^15): no overflow, and fp16 subnormals only for elements
+//                       2^-28 below the largest.  Scores, norms and thresholds of a row all live in that scaled domain
+//                       (the exact re-scoring reads the original tables).  Row norms (users) / maximum row norm
+//                       (catalogue).  The catalogue side is packed once per embedding table (mmrec_catalog_pack_f32).
 //   cf_pass_kernel<1>   s~ for every (user, item); epilogue = maximum of every group of w = 16 gw consecutive items
 //                       (tcgen05.ld -> FMNMX3 tree), written as gmax[row][group].  No branches, no atomics.
 //   cf_thr_kernel       per row: t = the need-th largest group maximum, need = k + (masked items of the row).  At
@@ -38,16 +43,14 @@ namespace mmrec {
 using namespace tc;
 
 constexpr int CF_TILE = 128;                    // rows of one MMA operand tile (users: TMEM lanes; items: TMEM columns)
-// k per item slab: the whole K of a unit when it fits 32 KB (d <= 64: one bulk copy and one barrier round trip per unit),
-// else 32.  What bounds the passes at large batches is the slab ring, not the tensor pipe (profiles/r02_notes.md): the
-// bytes in flight per SM (ring size) over the round trip "copy lands -> MMAs -> commit -> producer refills".
-__host__ __device__ inline int cf_kc(int KP) { return KP <= 64 ? KP : 32; }
+// An item slab is the whole K of a 128-item tile (8 / 16 / 32 KB at KP = 32 / 64 / 128): one barrier round trip per unit.
 constexpr int CF_EPI_WARPS = 16;                // (buffer parity, user half, TMEM lane quarter)
 constexpr int CF_THREADS = 64 + 32 * CF_EPI_WARPS;
 constexpr int CF_MAX_STAGES = 10;
 constexpr int CF_CAP = 512;                     // candidates one warp ranks per row
 constexpr int CF_EX_SLOTS = 128;                // CTAs (and key buffers) of the exact kernel
-constexpr float CF_EPS = 1.125f / 1024.f;       // |s~ - s| <= CF_EPS |u| |i|: two RN roundings to tf32 (2^-11 each) + accumulation slack
+constexpr float CF_EPS = 1.125f / 1024.f;       // |s~ - s| <= CF_EPS |u| |i|: two RN roundings to 11 significand bits (2^-11 each) + accumulation slack
+constexpr float CF_EPS_SUB = 1.0f / 16777216.f; // fp16 subnormal spacing 2^-24 (scaled domain): |dx| <= 2^-11 |x| + 2^-25 per element
 
 struct CfSmem {
     uint32_t a, slab0, slab, bars, tmem_ptr, total;
@@ -56,8 +59,8 @@ struct CfSmem {
 __host__ __device__ inline CfSmem cf_smem(int KP) {
     CfSmem L;
     L.a = 0;
-    L.slab0 = 2 * CF_TILE * KP * 4;             // the 256-user operand: two tiles of 128
-    const uint32_t slab = CF_TILE * cf_kc(KP) * 4;
+    L.slab0 = 2 * CF_TILE * KP * 2;             // the 256-user operand: two tiles of 128 rows, fp16
+    const uint32_t slab = CF_TILE * KP * 2;
     L.slab = slab;
     L.stages = (int)((226u * 1024u - L.slab0 - 300u) / slab);        // as many slabs in flight as shared memory holds
     if (L.stages > CF_MAX_STAGES) L.stages = CF_MAX_STAGES;
@@ -70,8 +73,8 @@ __host__ __device__ inline CfSmem cf_smem(int KP) {
 enum { CB_AFULL = 0, CB_AFREE = 1, CB_FULL = 2, CB_EMPTY = 2 + CF_MAX_STAGES, CB_TFULL = 2 + 2 * CF_MAX_STAGES, CB_TEMPTY = 4 + 2 * CF_MAX_STAGES };
 
 struct CfParams {
-    const float* Upk;                           // [pairs][2][KP/4][16][8][4]
-    const float* Ipk;                           // [item tiles][KP/4][16][8][4]
+    const char* Upk;                            // fp16 [pairs][2][KP/8][16][8][8]
+    const char* Ipk;                            // fp16 [item tiles][KP/8][16][8][8]
     int KP, n_it;
     int64_t B, n_items, n_units;
     float* gmax; int G, gw;                     // pass 1: [B][G], G = n_it * (8 / gw)
@@ -141,9 +144,8 @@ __device__ __forceinline__ uint32_t cf_lt16(const uint32_t (&v)[16], float thr) 
 // ---- producer: the 256-user operand of the current pair, then its run of item slabs ----------------------------
 __device__ __forceinline__ void cf_producer(const CfParams& p, const CfSmem& L, uint32_t sbase, int64_t u0, int64_t u1) {
     const uint32_t bar = sbase + L.bars;
-    const uint32_t a_bytes = 2 * CF_TILE * p.KP * 4;
-    const int KC = cf_kc(p.KP);
-    const int kchunks = p.KP / KC;
+    const uint32_t a_bytes = 2 * CF_TILE * p.KP * 2;
+    const uint32_t piece = L.slab < 16384u ? L.slab : 16384u;        // bulk copies of at most 16 KB
     // (pair, it) and the ring position advance by counting: a 64-bit division per unit is several hundred cycles of a
     // single thread's dependent instructions, and this loop is what the slab ring's refill rate hangs on
     int64_t pair = u0 / p.n_it;
@@ -154,45 +156,41 @@ __device__ __forceinline__ void cf_producer(const CfParams& p, const CfSmem& L, 
         if (new_pair) {
             if (a_cnt > 0) mbar_wait(bar + CB_AFREE * 8, (a_cnt - 1) & 1);   // every MMA that reads the old operand is done
             mbar_expect_tx(bar + CB_AFULL * 8, a_bytes);
-            const char* src = (const char*)(p.Upk + pair * (int64_t)(2 * CF_TILE) * p.KP);
+            const char* src = p.Upk + pair * (int64_t)a_bytes;
             for (uint32_t o = 0; o < a_bytes; o += 16384) bulk_g2s(sbase + L.a + o, src + o, 16384, bar + CB_AFULL * 8);
             ++a_cnt;
             new_pair = false;
         }
-        const char* src = (const char*)(p.Ipk + (int64_t)it * p.KP * CF_TILE);
-        for (int kc = 0; kc < kchunks; ++kc) {
-            const uint32_t fb = bar + (CB_FULL + slot) * 8;
-            mbar_wait(bar + (CB_EMPTY + slot) * 8, ph);
-            if (p.dbg & 16) {                                         // (tuning aid: no item traffic)
-                mbar_arrive(fb);
-            } else {
-                mbar_expect_tx(fb, L.slab);
-                const uint32_t dst = sbase + L.slab0 + slot * L.slab;
-                for (uint32_t o = 0; o < L.slab; o += 16384) bulk_g2s(dst + o, src + o, 16384, fb);
-            }
-            src += L.slab;
-            if (++slot == (uint32_t)L.stages) { slot = 0; ph ^= 1; }
+        const char* src = p.Ipk + (int64_t)it * L.slab;
+        const uint32_t fb = bar + (CB_FULL + slot) * 8;
+        mbar_wait(bar + (CB_EMPTY + slot) * 8, ph);
+        if (p.dbg & 16) {                                             // (tuning aid: no item traffic)
+            mbar_arrive(fb);
+        } else {
+            mbar_expect_tx(fb, L.slab);
+            const uint32_t dst = sbase + L.slab0 + slot * L.slab;
+            for (uint32_t o = 0; o < L.slab; o += piece) bulk_g2s(dst + o, src + o, piece, fb);
         }
+        if (++slot == (uint32_t)L.stages) { slot = 0; ph ^= 1; }
         if (++it == p.n_it) { it = 0; ++pair; new_pair = true; }
     }
 }
 
-// ---- MMA issuer: one thread, M128 N128 K8, two user halves per item slab ------------------------------------------
+// ---- MMA issuer: one thread, M128 N128 K16 (kind::f16), two user halves per item slab ------------------------------
 __device__ __forceinline__ void cf_mma(const CfParams& p, const CfSmem& L, uint32_t sbase, uint32_t tmem_base, int64_t u0, int64_t u1) {
     const uint32_t bar = sbase + L.bars;
     constexpr uint32_t LBO = (CF_TILE / 8) * 128, SBO = 128;         // both operands: tiles of 128 rows
-    const uint32_t idesc = idesc_tf32(CF_TILE, CF_TILE);
-    const int KC = cf_kc(p.KP);
-    const int kchunks = p.KP / KC;
-    const uint32_t half_bytes = CF_TILE * p.KP * 4;
+    const uint32_t idesc = idesc_f16(CF_TILE, CF_TILE);
+    const int ksteps = p.KP / 16;
+    const uint32_t half_bytes = CF_TILE * p.KP * 2;
     uint32_t a_cnt = 0;
     int halves = 2;
     // The issuing thread is a single instruction stream: measured (tools/probe_mma.py) ~200 cycles per tcgen05.mma when
-    // the descriptors are rebuilt around every instruction -- three times the 64 cycles the tensor pipe needs for M128
-    // N128 K8.  So the descriptors are built once and only their address field (low word, 16-byte units) moves.
+    // the descriptors are rebuilt around every instruction -- twice what the tensor pipe needs for M128 N128.  So the
+    // descriptors are built once and only their address field (low word, 16-byte units) moves.
     const uint64_t a_desc0 = smem_desc(sbase + L.a, LBO, SBO), a_desc1 = smem_desc(sbase + L.a + half_bytes, LBO, SBO);
     const uint64_t b_desc0 = smem_desc(sbase + L.slab0, LBO, SBO);
-    const uint64_t kstep = (2 * LBO) >> 4;                           // one K step of 8 = two 16-byte k blocks
+    const uint64_t kstep = (2 * LBO) >> 4;                           // one K step of 16 = two 16-byte k blocks
     int64_t pair = u0 / p.n_it;
     int it = (int)(u0 - pair * p.n_it);
     bool new_pair = true;
@@ -207,35 +205,35 @@ __device__ __forceinline__ void cf_mma(const CfParams& p, const CfSmem& L, uint3
             halves = (pair * 2 * CF_TILE + CF_TILE < p.B) ? 2 : 1;
             new_pair = false;
         }
-        fence_after_sync();
+        mbar_wait(bar + (CB_FULL + slot) * 8, ph);
+        if (!(p.dbg & 64)) fence_after_sync();
         const uint32_t d0 = tmem_base + (buf * 2 + 0) * CF_TILE, d1 = d0 + CF_TILE;
-        uint64_t ad0 = a_desc0, ad1 = a_desc1;
-        for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(bar + (CB_FULL + slot) * 8, ph);
-            fence_after_sync();
-            uint64_t bd = bd_slot;
-            if (!(p.dbg & 2)) {
-                if (halves == 2) {
-#pragma unroll 8
-                    for (int j = 0; j < KC / 8; ++j) {
-                        const uint32_t acc = (kc | j) ? 1u : 0u;
-                        mma_tf32(d0, ad0, bd, idesc, acc);
-                        mma_tf32(d1, ad1, bd, idesc, acc);
-                        ad0 += kstep; ad1 += kstep; bd += kstep;
-                    }
-                } else {
-#pragma unroll 8
-                    for (int j = 0; j < KC / 8; ++j) {
-                        mma_tf32(d0, ad0, bd, idesc, (kc | j) ? 1u : 0u);
-                        ad0 += kstep; bd += kstep;
-                    }
+        uint64_t ad0 = a_desc0, ad1 = a_desc1, bd = bd_slot;
+        if (!(p.dbg & 2)) {
+            if (halves == 2) {
+#pragma unroll 4
+                for (int j = 0; j < ksteps; ++j) {
+                    mma_f16(d0, ad0, bd, idesc, j ? 1u : 0u);
+                    mma_f16(d1, ad1, bd, idesc, j ? 1u : 0u);
+                    ad0 += kstep; ad1 += kstep; bd += kstep;
+                }
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < ksteps; ++j) {
+                    mma_f16(d0, ad0, bd, idesc, j ? 1u : 0u);
+                    ad0 += kstep; bd += kstep;
                 }
             }
-            mma_commit(bar + (CB_EMPTY + slot) * 8);                  // slab consumed -> slot back to the producer
-            bd_slot += slab_step;
-            if (++slot == (uint32_t)L.stages) { slot = 0; ph ^= 1; bd_slot = b_desc0; }
         }
-        mma_commit(bar + (CB_TFULL + buf) * 8);                       // accumulators complete -> epilogue
+        if (p.dbg & 32) {                                             // (tuning aid, only meaningful without MMAs: plain arrives)
+            mbar_arrive(bar + (CB_EMPTY + slot) * 8);
+            mbar_arrive(bar + (CB_TFULL + buf) * 8);
+        } else {
+            mma_commit(bar + (CB_EMPTY + slot) * 8);                  // slab consumed -> slot back to the producer
+            mma_commit(bar + (CB_TFULL + buf) * 8);                   // accumulators complete -> epilogue
+        }
+        bd_slot += slab_step;
+        if (++slot == (uint32_t)L.stages) { slot = 0; ph ^= 1; bd_slot = b_desc0; }
         if (++it == p.n_it) { it = 0; ++pair; new_pair = true; }
         if (new_pair || u + 1 == u1) mma_commit(bar + CB_AFREE * 8);
         buf ^= 1;
@@ -369,43 +367,80 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cf_pass_kernel(const CfParams p
 // ------------------------------------------------------------------------------------------------------------------
 // operand packing
 // ------------------------------------------------------------------------------------------------------------------
-// One thread per (padded row, k block of 4): round to tf32, store into the tile layout; the KP/4 threads of a row are
-// consecutive lanes and reduce the row's squared norm with shuffles.
+// Power of two that brings a largest magnitude m into [2^14, 2^15) (m = 0, inf, NaN, or below 2^-113: 1 -- the
+// non-finite cases flag their rows in cf_thr_kernel; the tiny ones are what CF_EPS_SUB in the margin is for).
+__device__ __forceinline__ float cf_scale_for(uint32_t m_bits) {
+    const uint32_t e = (m_bits >> 23) & 0xffu;                       // biased exponent
+    if (e == 0u || e == 255u || e < 14u) return 1.0f;
+    return __uint_as_float((268u - e) << 23);                        // 2^(14 - (e - 127))
+}
+
+// One thread per (padded row, k block of 8): scale, round to fp16, store 16 bytes into the tile layout; the KP/8 threads
+// of a row are consecutive lanes and reduce the row's squared norm (and, for user rows, its largest magnitude) with
+// shuffles.  `scale_src` = the catalogue-wide largest magnitude (items), or NULL: per-row scale (users).
 __device__ __forceinline__ void cf_pack_one(int64_t t, int64_t n_rows, const int64_t* __restrict__ idx, const float* __restrict__ E, int64_t ld,
-                                            int d, int KP, float* __restrict__ out, float* __restrict__ row_norm, uint32_t* __restrict__ max_norm) {
-    const int kblks = KP / 4;
+                                            int d, int KP, const uint32_t* __restrict__ scale_src, uint4* __restrict__ out,
+                                            float* __restrict__ row_norm, uint32_t* __restrict__ max_norm) {
+    const int kblks = KP / 8;
     const int64_t row = t / kblks;
     const int kb = (int)(t % kblks);
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
     if (row < n_rows) {
         const float* src = E + (idx ? idx[row] : row) * ld;
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (kb * 4 + e < d) x[e] = __ldg(src + kb * 4 + e);
+        for (int e = 0; e < 8; ++e)
+            if (kb * 8 + e < d) x[e] = __ldg(src + kb * 8 + e);
     }
-    float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
-    for (int o = kblks / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    uint32_t r[4];
+    float ss = 0.f;
+    uint32_t am = 0u;                                                 // largest |x| as a bit pattern (orders like the value; NaN above inf)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[e]) : "f"(x[e]));
+    for (int e = 0; e < 8; ++e) { ss = fmaf(x[e], x[e], ss); const uint32_t b = __float_as_uint(x[e]) & 0x7fffffffu; am = b > am ? b : am; }
+    for (int o = kblks / 2; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const uint32_t a2 = __shfl_xor_sync(0xffffffffu, am, o);
+        am = a2 > am ? a2 : am;
+    }
+    const float sc = cf_scale_for(scale_src ? __ldg(scale_src) : am);
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 h = __floats2half2_rn(x[2 * e] * sc, x[2 * e + 1] * sc);
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
     const int64_t tile = row / CF_TILE;
     const int rr = (int)(row % CF_TILE);
-    const int64_t off = ((tile * kblks + kb) * (CF_TILE / 8) + rr / 8) * 32 + (rr % 8) * 4;
-    *reinterpret_cast<uint4*>(out + off) = make_uint4(r[0], r[1], r[2], r[3]);
+    out[((tile * kblks + kb) * (CF_TILE / 8) + rr / 8) * 8 + (rr % 8)] = make_uint4(w[0], w[1], w[2], w[3]);
     if (kb == 0 && row < n_rows) {
-        const float nrm = sqrtf(ss) * (1.0f + 1e-6f);                 // (rounded up: the bound must hold)
+        const float nrm = sqrtf(ss) * sc * (1.0f + 1e-6f);            // norm of the scaled row (rounded up: the bound must hold)
         if (row_norm) row_norm[row] = nrm;
         if (max_norm) atomicMax(max_norm, __float_as_uint(nrm));      // non-negative floats order like their bit patterns
     }
 }
 
-// header word 0 (the running maximum norm) is zeroed by a memset node before the launch; thread 0 fills in the rest
+// header: word 0 = running maximum (scaled) norm, word 4 = largest magnitude of the table, both zeroed by a memset node
+// before the launches; thread 0 of the pack kernel fills in the rest
+__global__ void __launch_bounds__(256) cf_item_absmax_kernel(int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int d,
+                                                             uint32_t* __restrict__ header) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * 8;
+    uint32_t m = 0;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n_items; r += warps)        // warp per row
+        for (int c = lane; c < d; c += 32) {
+            const uint32_t b = __float_as_uint(__ldg(Ie + r * ldi + c)) & 0x7fffffffu;             // |x|; NaN patterns sort above inf
+            m = b > m ? b : m;
+        }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0 && m) atomicMax(header + 4, m);
+}
+
 __global__ void __launch_bounds__(256) cf_pack_items_kernel(int64_t n_items, const float* __restrict__ Ie, int64_t ldi, int d, int KP,
-                                                            float* __restrict__ Ipk, uint32_t* __restrict__ header, int64_t n_threads) {
+                                                            uint4* __restrict__ Ipk, uint32_t* __restrict__ header, int64_t n_threads) {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n_threads) return;                                       // (n_threads is a multiple of 32: whole warps leave together)
     if (t == 0) { header[1] = (uint32_t)n_items; header[2] = (uint32_t)d; header[3] = (uint32_t)KP; }
-    cf_pack_one(t, n_items, nullptr, Ie, ldi, d, KP, Ipk, nullptr, header);
+    cf_pack_one(t, n_items, nullptr, Ie, ldi, d, KP, header + 4, Ipk, nullptr, header);
 }
 
 // ---- mask CSR over batch rows -------------------------------------------------------------------------------------
@@ -538,14 +573,14 @@ __global__ void __launch_bounds__(256) cf_prep_kernel(int64_t mask_blocks, int64
                                                       const int64_t* __restrict__ mask_cols, int B_all, int64_t item_offset,
                                                       int32_t* __restrict__ mptr, int32_t* __restrict__ mitems, int32_t* __restrict__ unsorted,
                                                       int64_t nb, const int64_t* __restrict__ users, const float* __restrict__ Ue, int64_t ldu,
-                                                      int d, int KP, float* __restrict__ Upk, float* __restrict__ unorm, int64_t pack_threads,
+                                                      int d, int KP, uint4* __restrict__ Upk, float* __restrict__ unorm, int64_t pack_threads,
                                                       uint32_t* __restrict__ zero, int64_t zero_words) {
     if ((int64_t)blockIdx.x < mask_blocks) {
         cf_mask_sorted_block(blockIdx.x, mask_nnz, mask_rows, mask_cols, B_all, item_offset, mptr, mitems, unsorted);
         return;
     }
     int64_t t = (blockIdx.x - mask_blocks) * (int64_t)blockDim.x + threadIdx.x;
-    if (t < pack_threads) { cf_pack_one(t, nb, users, Ue, ldu, d, KP, Upk, unorm, nullptr); return; }   // (multiple of 256: whole blocks)
+    if (t < pack_threads) { cf_pack_one(t, nb, users, Ue, ldu, d, KP, nullptr, Upk, unorm, nullptr); return; }   // (multiple of 256: whole blocks)
     t -= pack_threads;
     if (t < zero_words) zero[t] = 0;
 }
@@ -634,7 +669,7 @@ __device__ __forceinline__ uint32_t cf_warp_kth_coarse(const float* __restrict__
     return prefix;                                                   // <= the need-th largest key, same top bits
 }
 
-__global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int G_valid, int k, const float* __restrict__ gmax, const float* __restrict__ unorm,
+__global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int G_valid, int k, int d, const float* __restrict__ gmax, const float* __restrict__ unorm,
                                                      const uint32_t* __restrict__ max_norm, const int32_t* __restrict__ mask_ptr,
                                                      float* __restrict__ thr, int32_t* __restrict__ flags) {
     __shared__ uint32_t hist_all[8][256];
@@ -653,7 +688,11 @@ __global__ void __launch_bounds__(256) cf_thr_kernel(int64_t nb, int G, int G_va
     else kth = cf_warp_kth([&](int t) { return float_key(__ldg(g + t)); }, G, need, hist_all[warp], lane);
     if (lane == 0) {
         const float t = key_float(kth);
-        const float margin = 2.0f * CF_EPS * unorm[row] * __uint_as_float(*max_norm);
+        // scaled domain.  Per element |dx| <= 2^-11 |x| + 2^-25 (fp16 subnormals), so
+        //   |s~ - s| <= 2^-10 |u| |i| (1 + 2^-12) + 2^-25 sqrt(d) (|u| + |i|) + (2^-25)^2 d + accumulation  <=  eps' below;
+        // with the largest elements scaled into [2^14, 2^15) the second term is ~2^-38 of the first
+        const float un = unorm[row], mn = __uint_as_float(*max_norm);
+        const float margin = 2.0f * (CF_EPS * un * mn + CF_EPS_SUB * sqrtf((float)d) * (un + mn + 1.0f));
         const float out = t - margin;
         if (!(fabsf(t) < INFINITY) || !(margin < INFINITY)) { thr[row] = INFINITY; flags[row] = 2; }   // NaN / inf scores
         else thr[row] = out;
@@ -1042,12 +1081,12 @@ __global__ void __launch_bounds__(256) cf_exact_kernel(const int64_t* __restrict
 static inline int cf_kp(int d) { return d <= 32 ? 32 : (d <= 64 ? 64 : 128); }
 static inline int cf_gw(int64_t n_items) { return n_items <= 16384 ? 1 : (n_items <= 32768 ? 2 : (n_items <= 65536 ? 4 : 8)); }
 
-constexpr size_t CF_CAT_HEADER = 1024;          // {max item norm (fp32 bits), n_items, d, KP} + padding
+constexpr size_t CF_CAT_HEADER = 1024;          // {max scaled item norm (fp32 bits), n_items, d, KP, largest |element| (fp32 bits)} + padding
 
 size_t cf_catalog_bytes(int64_t n_items, int d) {
     if (n_items <= 0 || d < 1 || d > 128) return 0;
     const int64_t n_it = (n_items + CF_TILE - 1) / CF_TILE;
-    return CF_CAT_HEADER + (size_t)n_it * CF_TILE * cf_kp(d) * 4;
+    return CF_CAT_HEADER + (size_t)n_it * CF_TILE * cf_kp(d) * 2;
 }
 
 int cf_catalog_pack(int64_t n_items, const float* Ie, int64_t ldi, int d, void* cat, size_t cat_bytes, cudaStream_t stream) {
@@ -1056,8 +1095,13 @@ int cf_catalog_pack(int64_t n_items, const float* Ie, int64_t ldi, int d, void* 
     const int KP = cf_kp(d);
     const int64_t n_it = (n_items + CF_TILE - 1) / CF_TILE;
     MMREC_CUDA(cudaMemsetAsync(cat, 0, CF_CAT_HEADER, stream));
-    const int64_t threads = n_it * CF_TILE * (KP / 4);
-    cf_pack_items_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n_items, Ie, ldi, d, KP, (float*)((char*)cat + CF_CAT_HEADER),
+    {
+        const int64_t blocks = (n_items + 7) / 8;
+        cf_item_absmax_kernel<<<(unsigned)(blocks < 2368 ? blocks : 2368), 256, 0, stream>>>(n_items, Ie, ldi, d, (uint32_t*)cat);
+        MMREC_LAUNCH_CHECK();
+    }
+    const int64_t threads = n_it * CF_TILE * (KP / 8);
+    cf_pack_items_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n_items, Ie, ldi, d, KP, (uint4*)((char*)cat + CF_CAT_HEADER),
                                                                                   (uint32_t*)cat, threads);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
@@ -1086,7 +1130,7 @@ static CfPlan cf_plan(int64_t B, int64_t n_items, int d, int64_t mask_nnz, bool 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
     P.off_cat = take(with_cat ? cf_catalog_bytes(n_items, d) : 0);
-    P.off_upk = take((size_t)P.rows_pad * P.KP * 4);
+    P.off_upk = take((size_t)P.rows_pad * P.KP * 2);
     P.off_unorm = take((size_t)P.rows_pad * 4);
     P.off_gmax = take((size_t)P.rows_blk * P.G * 4);
     P.off_thr = take((size_t)P.rows_pad * 4);
@@ -1171,8 +1215,9 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
     }
     cf_mark(stream);
     const uint32_t* max_norm = (const uint32_t*)cat;
-    const float* Ipk = (const float*)((const char*)cat + CF_CAT_HEADER);
-    float *Upk = (float*)(base + P.off_upk), *unorm = (float*)(base + P.off_unorm), *gmax = (float*)(base + P.off_gmax), *thr = (float*)(base + P.off_thr);
+    const char* Ipk = (const char*)cat + CF_CAT_HEADER;
+    uint4* Upk = (uint4*)(base + P.off_upk);
+    float *unorm = (float*)(base + P.off_unorm), *gmax = (float*)(base + P.off_gmax), *thr = (float*)(base + P.off_thr);
     uint4* bitmap = (uint4*)(base + P.off_bitmap);
     int32_t* flags = (int32_t*)(base + P.off_flags);
     int32_t* counter = flags + P.rows_blk;
@@ -1203,7 +1248,7 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
         const int32_t* mp = has_mask ? mptr + r0 : nullptr;
         // prep: [mask CSR of the whole batch (first block, sorted case)] + user operand + zeroed flags / counter
         const int64_t mask_blocks = (small_mask && r0 == 0) ? (mask_nnz + 1 + T - 1) / T : 0;      // <= 1025 words of mcur hold the order flags
-        const int64_t pack_threads = nb_pad * (P.KP / 4);
+        const int64_t pack_threads = nb_pad * (P.KP / 8);
         const int64_t zero_words = P.rows_blk + 1;
         cf_prep_kernel<<<(unsigned)(mask_blocks + (pack_threads + zero_words + T - 1) / T), T, 0, stream>>>(
             mask_blocks, mask_nnz, mask_rows, mask_cols, (int)B, item_offset, mptr, mitems, mcur, nb, ub, ue, ldu, d, P.KP, Upk, unorm,
@@ -1216,7 +1261,7 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
         }
         cf_mark(stream);
         CfParams p;
-        p.Upk = Upk; p.Ipk = Ipk; p.KP = P.KP; p.n_it = (int)P.n_it; p.B = nb; p.n_items = n_items; p.n_units = n_pairs * P.n_it;
+        p.Upk = (const char*)Upk; p.Ipk = Ipk; p.KP = P.KP; p.n_it = (int)P.n_it; p.B = nb; p.n_items = n_items; p.n_units = n_pairs * P.n_it;
         p.gmax = gmax; p.G = P.G; p.gw = P.gw; p.thr = thr; p.bitmap = bitmap;
         { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MMREC_CF_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
         const unsigned grid = (unsigned)(p.n_units < sms ? p.n_units : sms);
@@ -1228,7 +1273,7 @@ int score_cf(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
         }
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
-        cf_thr_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, stream>>>(nb, P.G, (int)((n_items + 16 * P.gw - 1) / (16 * P.gw)), k, gmax, unorm, max_norm, mp, thr, flags);
+        cf_thr_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, stream>>>(nb, P.G, (int)((n_items + 16 * P.gw - 1) / (16 * P.gw)), k, d, gmax, unorm, max_norm, mp, thr, flags);
         MMREC_LAUNCH_CHECK();
         cf_mark(stream);
         cf_pass_kernel<2, 8><<<grid, CF_THREADS, L.total, stream>>>(p);

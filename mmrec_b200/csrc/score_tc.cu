@@ -227,13 +227,6 @@ int score_tc(int64_t B, const int64_t* users, const float* Ue, int64_t ldu, int6
 // -- the form every tensor-core kernel of this library issues) take when nothing else runs?  One CTA per SM, one thread
 // issues `iters` MMAs of M = 128, the given N and K = 32 bytes (8 tf32 / 16 bf16) into one accumulator, commits and waits.
 namespace mmrec {
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int iters, int distinct, long long* __restrict__ cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_ptr_sm;
@@ -252,7 +245,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int i
         const uint32_t LBO_A = (128 / 8) * 128, LBO_B = (uint32_t)(N / 8) * 128;
         // instruction descriptors: tf32 (a/b format 2) or bf16 (format 1), fp32 accumulate, K-major both
         const uint32_t idesc = kind == 0 ? tc::idesc_tf32(128, N)
-                                         : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
+                                         : tc::idesc_bf16(128, N);
         const long long t0 = clock64();
         if (distinct == 0) {
             // lean issue loop: descriptors built once, only the address field moves (8 K steps, unrolled)
@@ -263,7 +256,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int i
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (kind == 0) tc::mma_tf32(tmem, ad, bd, idesc, (i | j) ? 1u : 0u);
-                    else mma_f16(tmem, ad, bd, idesc, (i | j) ? 1u : 0u);
+                    else tc::mma_f16(tmem, ad, bd, idesc, (i | j) ? 1u : 0u);
                     ad += ka; bd += kb;
                 }
             }
@@ -273,7 +266,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int kind, int N, int i
             const uint64_t ad = tc::smem_desc(sbase + off, LBO_A, 128);
             const uint64_t bd = tc::smem_desc(sbase + 65536 + (uint32_t)(i % distinct) * 2 * LBO_B, LBO_B, 128);
             if (kind == 0) tc::mma_tf32(tmem, ad, bd, idesc, i > 0);
-            else mma_f16(tmem, ad, bd, idesc, i > 0);
+            else tc::mma_f16(tmem, ad, bd, idesc, i > 0);
         }
         tc::mma_commit(bar);
         tc::mbar_wait(bar, 0);

@@ -3,6 +3,8 @@
 // the CUTLASS 4.x headers (cute/arch/mma_sm100_desc.hpp, mma_sm100_umma.hpp, copy_sm100.hpp) -- the kernels
 // themselves are hand-written.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mmrec {
@@ -77,6 +79,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same with kind::f16 (fp16 or bf16 operands as the instruction descriptor says), K = 16 per instruction
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive on an mbarrier once every previously issued MMA of this thread has completed
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -112,6 +122,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_b
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// instruction descriptor, kind::f16 with fp16 operands (format 0; bf16 would be 1), fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) { return idesc_f16(M, N) | (1u << 7) | (1u << 10); }
 
 // 3xTF32 split: hi = x rounded to tf32 (RN, ties away), lo = (x - hi) rounded to tf32; x = hi + lo to ~2^-22 |x|
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {

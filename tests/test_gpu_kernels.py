@@ -282,6 +282,37 @@ def _check_near_tie(idx, ref, ri, scale):
         assert gap < 4e-6 * scale, f"row {b}: non-tie mismatch, gap {gap}"
 
 
+def test_fused_topk_operand_scaling(dev):
+    """The filter's fp16 operands are scaled by powers of two (per user row, per catalogue): tiny, huge and mixed
+    magnitudes must neither overflow nor lose the certificate (every row served by the filter, result = fp32 top-k)."""
+    from mmrec_b200 import ops
+    ops.set_score_path("fused")
+    try:
+        g = torch.Generator().manual_seed(5)
+        B, U, I, d, k = 300, 300, 5000, 64, 50
+        for su, si, mix in [(1e-6, 1e-7, False), (3e4, 2e3, False), (1.0, 1.0, True), (1e-20, 1e-15, False)]:
+            ue = torch.randn(U, d, generator=g) * su; ie = torch.randn(I, d, generator=g) * si
+            if mix:     # rows and columns spanning 12 orders of magnitude
+                ue *= 10.0 ** torch.randint(-6, 6, (U, 1), generator=g).float()
+                ie *= 10.0 ** torch.randint(-3, 3, (1, d), generator=g).float()
+            users = torch.arange(B)
+            mask = torch.stack([torch.randint(0, B, (B * 8,), generator=g), torch.randint(0, I, (B * 8,), generator=g)])
+            val, idx = ops.score_topk(ue.to(dev), ie.to(dev), users.to(dev), mask.to(dev), k)
+            assert ops.fused_fallback_rows() == 0
+            ref = ue.double() @ ie.double().T
+            ref[mask[0], mask[1]] = -float("inf")
+            ri = torch.from_numpy(O.topk_tie_low_index(ref.numpy(), k)[1])
+            got = idx.cpu()
+            for b in torch.nonzero((got != ri).any(dim=1)).flatten().tolist():
+                cols = torch.nonzero(got[b] != ri[b]).flatten()
+                gap = (ref[b, got[b, cols]] - ref[b, ri[b, cols]]).abs().max().item()
+                assert gap < 4e-6 * ref[b][torch.isfinite(ref[b])].abs().max().item(), f"row {b}: non-tie mismatch"
+            chk = (ue[users][:, None, :].double() * ie[got].double()).sum(-1)
+            assert ((chk - val.cpu().double()).abs() <= 2e-6 * chk.abs().max(dim=1, keepdim=True).values + 1e-300).all()
+    finally:
+        ops.set_score_path("auto")
+
+
 def test_fused_topk_edge_cases(dev):
     """The fused tcgen05 path (forced): heavy users (more masked items than there are item groups -> exact kernel),
     unsorted mask, degenerate (all-equal) scores, ragged sizes, d = 32 / 128."""
