@@ -56,7 +56,7 @@ def test_argument_errors_without_a_gpu():
     assert lib.mmrec_peer_reduce_push_f32(8, 2, 2, ctypes.cast(two, ctypes.c_void_p), ctypes.cast(two, ctypes.c_void_p), None, None, 1.0, 0,
                                           None) == -1                                  # rank outside the world
     assert lib.mmrec_peer_gather_f32(6, 2, ctypes.cast(two, ctypes.c_void_p), None, None) == -1
-    assert lib.mmrec_catalog_bytes(7000, 64) > 7000 * 64 * 4 and lib.mmrec_catalog_bytes(7000, 300) == 0
+    assert lib.mmrec_catalog_bytes(7000, 64) >= 7000 * 64 * 2 and lib.mmrec_catalog_bytes(7000, 300) == 0
     assert lib.mmrec_launch_count() >= 0
 
 
