@@ -33,7 +33,7 @@ extern "C" {
 #define MMREC_ECUDA (-3)       /* a CUDA runtime call failed; see mmrec_last_error() */
 #define MMREC_EUNSUPPORTED (-4)/* device is not sm_100 (the library carries sm_100a code only) */
 
-#define MMREC_ABI_VERSION 2
+#define MMREC_ABI_VERSION 3
 
 int mmrec_abi_version(void);
 const char* mmrec_last_error(void);
@@ -290,6 +290,46 @@ int mmrec_peer_barrier(int world, int rank, void* const* flags, int32_t* state, 
  * ------------------------------------------------------------------------------------------- */
 int mmrec_topk_metrics_f64(int64_t n_users, int K, const int64_t* topk_idx, const int64_t* pos_ptr, const int64_t* pos_items,
                            const double* disc, const double* idcg_all, double* sums, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * f1  feature-table gradient path and optimiser step.   Replaces, per training batch and modality, the backward of
+ * `self.image_trs(self.image_embedding.weight)` (src/models/freedom.py:58-62,205-209; bm3.py:102-104; mgcn.py:148-150:
+ * the tables are `nn.Embedding.from_pretrained(.., freeze=False)`, i.e. trainable [n_items, F] parameters) -- cuBLAS
+ * GEMMs dW = g^T X, dX = g W plus a dense [n_items, F] gradient -- and `torch.optim.Adam.step` over it
+ * (src/common/trainer.py:117-118,185-189).  IEEE fp32 on CUDA cores, operation order of torch's `_multi_tensor_adam`.
+ *
+ * mmrec_index_sum_rows_f32     G[i,:] = sum over j ascending with idx[j] == i of g[j,:]    G [n_rows, ldG], g [n_idx, ldg],
+ *                              1 <= d <= 256; rows nobody points at become zero; indices outside [0, n_rows) are ignored.
+ *                              The gradient of a gathered projection `Linear(table)[idx]` w.r.t. the table is G W.
+ * mmrec_linear_wgrad_f32       dW[k,f] = sum_j g[j,k] table[idx ? idx[j] : j, f]   dW [d, F];   db[k] = sum_j g[j,k]  (db nullable)
+ *                              F a multiple of 4, table and dW 16-byte aligned; ws from mmrec_linear_wgrad_workspace_bytes
+ *                              (per-CTA partials, reduced in a fixed order: bit-reproducible).
+ * mmrec_linear_dgrad_f32       dX = G W   dX [n_rows, F] (leading dimension F), G [n_rows, ldG], W [d, F], d <= 128.
+ * mmrec_linear_dgrad_adam_f32  one Adam step of `param` [n_rows, F] whose gradient is G W, WITHOUT materialising it:
+ *                                grad = G W (+ weight_decay * param);  exp_avg += (1 - beta1)(grad - exp_avg);
+ *                                exp_avg_sq = beta2 exp_avg_sq + (1 - beta2) grad^2;
+ *                                param += step_size * exp_avg / (sqrt(exp_avg_sq) / bc2_sqrt + eps)
+ *                              with step_size = -lr / (1 - beta1^t) and bc2_sqrt = sqrt(1 - beta2^t) computed by the caller in
+ *                              double, as torch/optim/adam.py does.  W must still hold the values the forward used.
+ * mmrec_adam_f32               the same update for `n_tensors` ordinary (param, grad) pairs, one launch per 24 tensors;
+ *                              `tensors` is a HOST array.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+    int64_t n;
+    double step_size, bc2_sqrt;
+} mmrec_adam_tensor;
+int mmrec_index_sum_rows_f32(int64_t n_idx, const int64_t* idx, const float* g, int64_t ldg, int d, int64_t n_rows, float* G,
+                             int64_t ldG, void* stream);
+size_t mmrec_linear_wgrad_workspace_bytes(int64_t n, int64_t F, int d);
+int mmrec_linear_wgrad_f32(int64_t n, const int64_t* idx, const float* g, int64_t ldg, int d, const float* table, int64_t n_table,
+                           int64_t F, float* dW, float* db, void* ws, size_t ws_bytes, void* stream);
+int mmrec_linear_dgrad_f32(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, float* dX, void* stream);
+int mmrec_linear_dgrad_adam_f32(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, float* param,
+                                float* exp_avg, float* exp_avg_sq, double beta1, double beta2, double eps, double weight_decay,
+                                double step_size, double bc2_sqrt, void* stream);
+int mmrec_adam_f32(int n_tensors, const mmrec_adam_tensor* tensors, double beta1, double beta2, double eps, double weight_decay,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libmmrec_b200.so")
 
-_i64, _i32, _f32, _sz, _p = C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_void_p
+_i64, _i32, _f32, _f64, _sz, _p = C.c_int64, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_void_p
 
 # name -> (restype, argtypes); pointers are passed as raw addresses (tensor.data_ptr())
 PROTOTYPES = {
@@ -58,6 +58,12 @@ PROTOTYPES = {
     "mmrec_peer_gather_f32": (_i32, [_i64, _i32, _p, _p, _p]),
     "mmrec_topk_metrics_f64": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "mmrec_peer_sum_f32": (_i32, [_i64, _i32, _p, _p, _p, _f32, _p, _p]),
+    "mmrec_index_sum_rows_f32": (_i32, [_i64, _p, _p, _i64, _i32, _i64, _p, _i64, _p]),
+    "mmrec_linear_wgrad_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "mmrec_linear_wgrad_f32": (_i32, [_i64, _p, _p, _i64, _i32, _p, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "mmrec_linear_dgrad_f32": (_i32, [_i64, _p, _i64, _i32, _p, _i64, _p, _p]),
+    "mmrec_linear_dgrad_adam_f32": (_i32, [_i64, _p, _i64, _i32, _p, _i64, _p, _p, _p, _f64, _f64, _f64, _f64, _f64, _f64, _p]),
+    "mmrec_adam_f32": (_i32, [_i32, _p, _f64, _f64, _f64, _f64, _p]),
 }
 
 class SpmmStep(C.Structure):
@@ -69,8 +75,13 @@ class SpmmStep(C.Structure):
                 ("post", _p), ("ldpost", _i64), ("post_row0", _i64), ("sync_before", _i32)]
 
 
+class AdamTensor(C.Structure):
+    """`mmrec_adam_tensor` of include/mmrec_b200.h."""
+    _fields_ = [("param", _p), ("grad", _p), ("exp_avg", _p), ("exp_avg_sq", _p), ("n", _i64), ("step_size", _f64), ("bc2_sqrt", _f64)]
+
+
 _lib = None
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class MMRecError(RuntimeError):

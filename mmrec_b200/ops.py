@@ -430,25 +430,106 @@ def set_project_path(tensor_core: bool):
     _lib.load().mmrec_project_set_path(int(bool(tensor_core)))
 
 
+# -- f1: backward of the projection and the optimiser step (csrc/train.cu) -------------------------------------------
+def index_sum_rows(g: torch.Tensor, idx: torch.Tensor, n_rows: int) -> torch.Tensor:
+    """G[i] = sum_{j: idx[j] = i} g[j] in ascending j (`mmrec_index_sum_rows_f32`): `zeros.index_add_(0, idx, g)` made
+    bit-reproducible.  The table gradient of a gathered projection is `G @ W` (linearity), so the scatter is d wide."""
+    _need_cuda(g, idx)
+    g = _f32c(g)
+    idx = idx.to(torch.int64).contiguous()
+    G = torch.empty(n_rows, g.shape[1], dtype=torch.float32, device=g.device)
+    check(_lib.load().mmrec_index_sum_rows_f32(idx.numel(), _ptr(idx), _ptr(g), g.stride(0), g.shape[1], n_rows, _ptr(G), G.stride(0),
+                                               _stream()), "mmrec_index_sum_rows_f32")
+    return G
+
+
+def linear_wgrad(g: torch.Tensor, table: torch.Tensor, idx: Optional[torch.Tensor] = None, want_bias: bool = True):
+    """(dW [d, F], db [d] | None) of `y = table[idx] @ W^T + b` for the upstream gradient g [n, d]: `g.t().mm(x)`, `g.sum(0)`
+    (autograd of `nn.Linear`, src/models/freedom.py:205-209) through `mmrec_linear_wgrad_f32`."""
+    _need_cuda(g, table, idx)
+    lib = _lib.load()
+    g, table = _f32c(g), _f32c(table)
+    if idx is not None:
+        idx = idx.to(torch.int64).contiguous()
+    n, d = g.shape
+    F = table.shape[1]
+    dW = torch.empty(d, F, dtype=torch.float32, device=g.device)
+    db = torch.empty(d, dtype=torch.float32, device=g.device) if want_bias else None
+    ws = _ws("wgrad", lib.mmrec_linear_wgrad_workspace_bytes(n, F, d), g.device)
+    check(lib.mmrec_linear_wgrad_f32(n, _ptr(idx), _ptr(g), g.stride(0), d, _ptr(table), table.shape[0], F, _ptr(dW), _ptr(db),
+                                     _ptr(ws), ws.numel(), _stream()), "mmrec_linear_wgrad_f32")
+    return dW, db
+
+
+def linear_dgrad(G: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """`G @ W` as a fresh [n_rows, F] tensor (`mmrec_linear_dgrad_f32`): the dense table gradient autograd expects."""
+    _need_cuda(G, weight)
+    G, weight = _f32c(G), _f32c(weight)
+    out = torch.empty(G.shape[0], weight.shape[1], dtype=torch.float32, device=G.device)
+    check(_lib.load().mmrec_linear_dgrad_f32(G.shape[0], _ptr(G), G.stride(0), G.shape[1], _ptr(weight), weight.shape[1], _ptr(out),
+                                             _stream()), "mmrec_linear_dgrad_f32")
+    return out
+
+
+def linear_dgrad_adam(G, weight, param, exp_avg, exp_avg_sq, beta1, beta2, eps, weight_decay, step_size, bc2_sqrt):
+    """One Adam step of `param` [n_rows, F] with the gradient `G @ W` computed inside the kernel, never stored
+    (`mmrec_linear_dgrad_adam_f32`; torch.optim.Adam.step of src/common/trainer.py:189 fused with the projection backward)."""
+    _need_cuda(G, weight, param, exp_avg, exp_avg_sq)
+    G, weight = _f32c(G), _f32c(weight)
+    for t in (param, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.shape != (G.shape[0], weight.shape[1]):
+            raise MMRecError("linear_dgrad_adam: param / exp_avg / exp_avg_sq must be contiguous float32 [n_rows, F]")
+    check(_lib.load().mmrec_linear_dgrad_adam_f32(G.shape[0], _ptr(G), G.stride(0), G.shape[1], _ptr(weight), weight.shape[1], _ptr(param),
+                                                  _ptr(exp_avg), _ptr(exp_avg_sq), float(beta1), float(beta2), float(eps),
+                                                  float(weight_decay), float(step_size), float(bc2_sqrt), _stream()),
+          "mmrec_linear_dgrad_adam_f32")
+
+
+def adam_step(entries, beta1, beta2, eps, weight_decay):
+    """`entries`: (param, grad, exp_avg, exp_avg_sq, step_size, bc2_sqrt) per tensor; all updated by `mmrec_adam_f32`."""
+    import ctypes
+    if not entries:
+        return
+    arr = (_lib.AdamTensor * len(entries))()
+    for a, (p, g, m, v, step_size, bc2_sqrt) in zip(arr, entries):
+        _need_cuda(p, g, m, v)
+        for t in (p, g, m, v):
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+                raise MMRecError("adam_step: contiguous float32 tensors of one size per entry")
+        a.param, a.grad, a.exp_avg, a.exp_avg_sq, a.n = _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel()
+        a.step_size, a.bc2_sqrt = float(step_size), float(bc2_sqrt)
+    check(_lib.load().mmrec_adam_f32(len(entries), ctypes.cast(arr, ctypes.c_void_p), float(beta1), float(beta2), float(eps),
+                                     float(weight_decay), _stream()), "mmrec_adam_f32")
+
+
 class _ProjectFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table, weight, bias, idx):
         ctx.save_for_backward(table, weight, idx)
         ctx.has_bias = bias is not None
+        ctx.table_param = table if isinstance(table, torch.nn.Parameter) else None
         return project_raw(table, weight, bias, idx, False)
 
     @staticmethod
     def backward(ctx, g):
-        # Backward of nn.Linear over the (gathered) table: dense GEMMs, left to cuBLAS through torch for now
-        # (the feature-table gradient path is a "next" row, not part of K2's forward).
+        # Backward of nn.Linear over the (gathered) table (SURVEY.md 8f f1) on the kernels of csrc/train.cu.
         table, weight, idx = ctx.saved_tensors
-        x = table if idx is None else table[idx]
-        gw = g.t().mm(x) if ctx.needs_input_grad[1] else None
-        gb = g.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        gt = None
+        g = _f32c(g)
+        gw = gb = gt = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = linear_wgrad(g, table, idx, want_bias=ctx.has_bias and ctx.needs_input_grad[2])
+            if not ctx.needs_input_grad[1]:
+                gw = None
         if ctx.needs_input_grad[0]:
-            gx = g.mm(weight)
-            gt = gx if idx is None else torch.zeros_like(table).index_add_(0, idx, gx)
+            G = g if idx is None else index_sum_rows(g, idx, table.shape[0])     # d-wide scatter; the table gradient is G @ W
+            p = ctx.table_param
+            if p is not None and getattr(p, "_mmrec_defer", False) and getattr(p, "_mmrec_pending", None) is None \
+                    and weight.shape[0] <= 128 and weight.shape[1] % 4 == 0:
+                # The optimiser (optim.FusedAdam) asked for the gradient in factored form: it updates the table with G @ W
+                # computed inside its kernel, so the [n_items, F] gradient never exists.  `.grad` stays None for this table.
+                p._mmrec_pending = (G, weight, weight._version)
+            else:
+                gt = linear_dgrad(G, weight)
         return gt, gw, gb, None
 
 
