@@ -331,6 +331,20 @@ int mmrec_linear_dgrad_adam_f32(int64_t n_rows, const float* G, int64_t ldG, int
 int mmrec_adam_f32(int n_tensors, const mmrec_adam_tensor* tensors, double beta1, double beta2, double eps, double weight_decay,
                    void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * a5b  MGCN's row-wise fusion (src/models/mgcn.py:153-154 purifier gates, :187-201 two-view attention, preference gates,
+ * side + content), inference form.  d in {32, 64, 128}; all matrices row-major with leading dimension d; W are
+ * `nn.Linear` weights [d, d] (y = x W^T + b), biases nullable.
+ * mmrec_gate_rows_f32   out[n,:] = mul[n,:] * sigmoid(X[n,:] W^T + b)                  (mul nullable: the gate alone)
+ * mmrec_mgcn_fuse_f32   a_v = wq2 . tanh(Wq img + bq), a_t likewise on txt; (w0, w1) = softmax(a_v, a_t);
+ *                       common = w0 img + w1 txt; sep_v = sigmoid(Wgi content + bgi) (img - common), sep_t likewise;
+ *                       side = (sep_v + sep_t + common) / 3 (stored if side != NULL); out = content + side
+ * ------------------------------------------------------------------------------------------- */
+int mmrec_gate_rows_f32(int64_t n, int d, const float* X, const float* W, const float* b, const float* mul, float* out, void* stream);
+int mmrec_mgcn_fuse_f32(int64_t n, int d, const float* img, const float* txt, const float* content, const float* Wq, const float* bq,
+                        const float* wq2, const float* Wgi, const float* bgi, const float* Wgt, const float* bgt, float* out,
+                        float* side, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,8 @@ PROTOTYPES = {
     "mmrec_linear_dgrad_f32": (_i32, [_i64, _p, _i64, _i32, _p, _i64, _p, _p]),
     "mmrec_linear_dgrad_adam_f32": (_i32, [_i64, _p, _i64, _i32, _p, _i64, _p, _p, _p, _f64, _f64, _f64, _f64, _f64, _f64, _p]),
     "mmrec_adam_f32": (_i32, [_i32, _p, _f64, _f64, _f64, _f64, _p]),
+    "mmrec_gate_rows_f32": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p]),
+    "mmrec_mgcn_fuse_f32": (_i32, [_i64, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 class SpmmStep(C.Structure):

@@ -52,6 +52,11 @@ class Trainer(object):
         params, lr, wd = self.model.parameters(), self.learning_rate, self.weight_decay
         name = self.learner.lower()
         if name == "adam":
+            # f1: the same optimiser on the kernels of csrc/train.cu (Adam step fused with the projection backward of the
+            # trainable modality tables); `config["fused_adam"] = False` keeps torch's.
+            if self.config["fused_adam"] is not False and next(self.model.parameters()).is_cuda:
+                from ..optim import FusedAdam
+                return FusedAdam(params, lr=lr, weight_decay=wd)
             return optim.Adam(params, lr=lr, weight_decay=wd)
         if name == "sgd":
             return optim.SGD(params, lr=lr, weight_decay=wd)
@@ -95,6 +100,8 @@ class Trainer(object):
             else:
                 loss.backward()
             if self.clip_grad_norm:
+                if hasattr(self.optimizer, "materialize_pending"):
+                    self.optimizer.materialize_pending()        # the norm needs every gradient as a tensor
                 clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
             self.optimizer.step()
             loss_batches.append(loss.detach())

@@ -439,14 +439,11 @@ static void wgrad_shape(int64_t n, int64_t F, int d, int64_t* strips, int* ktile
 }
 
 extern "C" size_t mmrec_linear_wgrad_workspace_bytes(int64_t n, int64_t F, int d) {
-    if (n < 0 || F < 1 || d < 1) return 256;
+    if (n <= 0 || F < 1 || d < 1) return 256;
     int64_t strips, chunks, rpc; int kt;
-    // the chunk count depends on the SM count of the current device; size for the largest it can be (one chunk per SM)
-    (void)strips; (void)rpc;
-    wgrad_shape(n > 0 ? n : 1, F, d, &strips, &kt, &chunks, &rpc);
-    const int64_t max_chunks = chunks > 256 ? chunks : 256;
+    wgrad_shape(n, F, d, &strips, &kt, &chunks, &rpc);        // depends on the SM count of the current device, like the launch
     const size_t d_pad = (size_t)kt * WG_KT;
-    return align_up((size_t)max_chunks * d_pad * (size_t)F * sizeof(float), 256) + align_up((size_t)max_chunks * d_pad * sizeof(float), 256) + 256;
+    return align_up((size_t)chunks * d_pad * (size_t)F * sizeof(float), 256) + align_up((size_t)chunks * d_pad * sizeof(float), 256);
 }
 
 extern "C" int mmrec_linear_wgrad_f32(int64_t n, const int64_t* idx, const float* g, int64_t ldg, int d, const float* table, int64_t n_table,

@@ -7,7 +7,7 @@ Reference code replaced (paths relative to /root/reference):
   * `MGCN.get_adj_mat`  -- src/models/mgcn.py:109-144 (lil-matrix slicing, 128 s at clothing scale);
   * `pre_epoch_processing` / `_normalize_adj_m` / `get_edge_info` -- src/models/freedom.py:128-162;
   * `get_knn_adj_mat` -- src/models/freedom.py:79-100 and `build_knn_normalized_graph` -- src/utils/utils.py:165-183
-    (init-time item-item graphs; SURVEY.md 8f f4 "next" row: built with torch device ops for now).
+    (init-time item-item graphs; SURVEY.md 8f f4: contraction and selection on the scoring kernels, `_knn`).
 """
 from __future__ import annotations
 
@@ -112,13 +112,17 @@ class EdgePruner:
 # item-item kNN graphs (init time)
 # ------------------------------------------------------------------------------------------------
 def _knn(feat: torch.Tensor, k: int):
-    cn = feat.div(torch.norm(feat, p=2, dim=-1, keepdim=True))
+    """Cosine kNN of the item features (`sim = cn @ cn.T; torch.topk(sim, k)`, src/models/freedom.py:79-84,
+    src/utils/utils.py:165-172) on the scoring kernels: the contraction is `ops.score` -- the same
+    `U I^T` as full_sort_predict with the normalised features on both sides (exact fp32 fmaf chains for F > 128) -- in row
+    blocks bounded to 256 MiB of similarities, the selection is `ops.mask_topk` (radix select, ties -> lower index)."""
+    cn = feat.div(torch.norm(feat, p=2, dim=-1, keepdim=True)).contiguous()
     n = cn.shape[0]
     vals, inds = [], []
-    step = max(1, (256 << 20) // (4 * n))          # bound the dense similarity block to 256 MiB
+    step = max(128, (256 << 20) // (4 * n))
     for s in range(0, n, step):
-        sim = torch.mm(cn[s:s + step], cn.t())
-        v, i = torch.topk(sim, k, dim=-1)
+        sim = ops.score(cn[s:s + step], cn)
+        v, i = ops.mask_topk(sim, None, k)
         vals.append(v); inds.append(i)
     return torch.cat(vals), torch.cat(inds)
 

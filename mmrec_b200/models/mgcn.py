@@ -1,7 +1,7 @@
 """MGCN on the B200 hot path; mirrors `/root/reference/src/models/mgcn.py` (class name, config keys, parameter
 names and order).  Six SpMMs per forward (`:157-185`) -> ops.propagate_mean / ops.spmm on CSR; projections
-`:148-150` -> ops.project; the row-wise fusion (`:153-201`: purifier gates, 2-way attention, preference gates)
-stays in torch (bandwidth-trivial)."""
+`:148-150` -> ops.project; the row-wise fusion (`:153-201`: purifier gates, 2-way attention, preference gates) is two
+kernels at inference (`ops.gate_rows`, `ops.mgcn_fuse`) and torch expressions under autograd."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -50,7 +50,33 @@ class MGCN(GeneralRecommender):
     def pre_epoch_processing(self):
         pass
 
+    def _forward_inference(self, adj):
+        """`forward` without autograd (evaluation): a5b -- the purifier gates as one kernel per modality, the modality SpMMs
+        writing straight into the [users; items] tables, attention + preference gates + `content + side` as one kernel."""
+        d, U = self.embedding_dim, self.n_users
+        item_w = self.item_id_embedding.weight
+        image_feats = ops.project(self.image_embedding.weight, self.image_trs.weight, self.image_trs.bias)
+        text_feats = ops.project(self.text_embedding.weight, self.text_trs.weight, self.text_trs.bias)
+        content = ops.propagate_mean(adj, torch.cat([self.user_embedding.weight, item_w], dim=0), self.n_ui_layers)
+        views = []
+        for feats, gate, knn in ((image_feats, self.gate_v, self.image_original_adj), (text_feats, self.gate_t, self.text_original_adj)):
+            emb = torch.empty(U + self.n_items, d, dtype=torch.float32, device=item_w.device)
+            x = ops.gate_rows(feats, gate[0].weight, gate[0].bias, mul=item_w, out=emb[U:] if self.n_layers == 0 else None)
+            for l in range(self.n_layers):                           # mgcn.py:169-172 / :177-180
+                y = emb[U:] if l == self.n_layers - 1 else torch.empty_like(x)
+                ops.spmm_raw(knn, x, Y=y)
+                x = y
+            ops.spmm_raw(self.R, emb[U:], Y=emb[:U])                 # user rows = R @ item rows (mgcn.py:173,181)
+            views.append(emb)
+        q = self.query_common
+        all_embeds = ops.mgcn_fuse(views[0], views[1], content, q[0].weight, q[0].bias, q[2].weight, self.gate_image_prefer[0].weight,
+                                   self.gate_image_prefer[0].bias, self.gate_text_prefer[0].weight, self.gate_text_prefer[0].bias)
+        return all_embeds[:U], all_embeds[U:]
+
     def forward(self, adj, train=False):
+        if not train and not torch.is_grad_enabled() and self.embedding_dim in (32, 64, 128) and self.v_feat is not None \
+                and self.t_feat is not None:
+            return self._forward_inference(adj)
         image_feats = ops.project(self.image_embedding.weight, self.image_trs.weight, self.image_trs.bias)
         text_feats = ops.project(self.text_embedding.weight, self.text_trs.weight, self.text_trs.bias)
         item_w = self.item_id_embedding.weight

@@ -543,6 +543,38 @@ def project(table, weight, bias=None, idx=None, l2_normalize=False) -> torch.Ten
     return torch.nn.functional.normalize(y) if l2_normalize else y
 
 
+# -- a5b: MGCN's row-wise fusion (csrc/fuse.cu), inference form ---------------------------------------------------------
+def gate_rows(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mul: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`mul * sigmoid(x @ weight.T + bias)` in one kernel (`mmrec_gate_rows_f32`): MGCN's behaviour-guided purifier
+    `item_id_embedding.weight * gate_v(image_feats)` (src/models/mgcn.py:153-154).  No autograd."""
+    _need_cuda(x, weight, bias, mul, out)
+    x, weight = _f32c(x), _f32c(weight)
+    n, d = x.shape
+    if weight.shape != (d, d):
+        raise MMRecError(f"gate_rows: weight must be [{d}, {d}]")
+    out = torch.empty(n, d, dtype=torch.float32, device=x.device) if out is None else out
+    check(_lib.load().mmrec_gate_rows_f32(n, d, _ptr(x), _ptr(weight), _ptr(None if bias is None else _f32c(bias)),
+                                          _ptr(None if mul is None else _f32c(mul)), _ptr(out), _stream()), "mmrec_gate_rows_f32")
+    return out
+
+
+def mgcn_fuse(img, txt, content, q_w, q_b, q_w2, gi_w, gi_b, gt_w, gt_b, want_side: bool = False):
+    """MGCN's attention over the two modality views, preference gates and `content + side` (src/models/mgcn.py:187-201)
+    for all rows in one kernel (`mmrec_mgcn_fuse_f32`).  Returns `all_embeds` (and `side` if asked).  No autograd."""
+    _need_cuda(img, txt, content, q_w, q_b, q_w2, gi_w, gi_b, gt_w, gt_b)
+    img, txt, content = _f32c(img), _f32c(txt), _f32c(content)
+    n, d = img.shape
+    if txt.shape != (n, d) or content.shape != (n, d):
+        raise MMRecError("mgcn_fuse: img, txt and content must share one shape")
+    out = torch.empty(n, d, dtype=torch.float32, device=img.device)
+    side = torch.empty_like(out) if want_side else None
+    check(_lib.load().mmrec_mgcn_fuse_f32(n, d, _ptr(img), _ptr(txt), _ptr(content), _ptr(_f32c(q_w)), _ptr(_f32c(q_b)),
+                                          _ptr(_f32c(q_w2).reshape(-1)), _ptr(_f32c(gi_w)), _ptr(_f32c(gi_b)), _ptr(_f32c(gt_w)),
+                                          _ptr(_f32c(gt_b)), _ptr(out), _ptr(side), _stream()), "mmrec_mgcn_fuse_f32")
+    return (out, side) if want_side else out
+
+
 # ------------------------------------------------------------------------------------------------
 # K3: scoring, mask, top-k
 # ------------------------------------------------------------------------------------------------

@@ -54,6 +54,11 @@ def install_cpu_ops():
     ops.project = lambda table, weight, bias=None, idx=None, l2_normalize=False: O.project(table, weight, bias, idx=idx, l2_normalize=l2_normalize)
     ops.score = lambda u, i, users=None: O.full_sort_scores(u, i, users if users is not None else torch.arange(u.shape[0]))
 
+    def mask_topk(scores, mask, k, item_offset=0):                    # graph._knn: selection of the kNN build
+        assert mask is None
+        return torch.topk(scores, k, dim=-1)
+    ops.mask_topk = mask_topk
+
     def bipartite_norm(users, items, n_users, n_items, eps=1e-7):
         return O.normalize_adj_m(torch.stack([users, items]), n_users, n_items)
     ops.bipartite_norm = bipartite_norm

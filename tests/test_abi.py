@@ -28,7 +28,7 @@ def test_library_built_and_exports_every_header_symbol():
 def test_loader_binds_and_reports_version():
     from mmrec_b200 import _lib
     lib = _lib.load()
-    assert lib.mmrec_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.mmrec_abi_version() == _lib.ABI_VERSION == 3
     assert lib.mmrec_last_error() is not None
 
 
@@ -58,6 +58,17 @@ def test_argument_errors_without_a_gpu():
     assert lib.mmrec_peer_gather_f32(6, 2, ctypes.cast(two, ctypes.c_void_p), None, None) == -1
     assert lib.mmrec_catalog_bytes(7000, 64) >= 7000 * 64 * 2 and lib.mmrec_catalog_bytes(7000, 300) == 0
     assert lib.mmrec_launch_count() >= 0
+    # f1: projection backward / Adam
+    assert lib.mmrec_index_sum_rows_f32(4, None, None, 64, 300, 10, None, 300, None) == -1          # d > 256
+    assert lib.mmrec_linear_wgrad_f32(8, None, None, 64, 64, None, 8, 4098, None, None, None, 0, None) == -1   # F not a multiple of 4
+    assert b"linear_wgrad" in lib.mmrec_last_error()
+    assert lib.mmrec_linear_dgrad_f32(8, None, 200, 200, None, 4096, None, None) == -4             # d > 128: no kernel
+    assert lib.mmrec_linear_dgrad_adam_f32(0, None, 64, 64, None, 4096, None, None, None, 0.9, 0.999, 1e-8, 0.0, -1e-3, 1.0, None) == 0
+    assert lib.mmrec_adam_f32(0, None, 0.9, 0.999, 1e-8, 0.0, None) == 0
+    bad = (_lib.AdamTensor * 1)()
+    bad[0].n, bad[0].bc2_sqrt = 16, 1.0                                                             # null pointers
+    assert lib.mmrec_adam_f32(1, ctypes.cast(bad, ctypes.c_void_p), 0.9, 0.999, 1e-8, 0.0, None) == -1
+    assert lib.mmrec_linear_wgrad_workspace_bytes(7000, 4096, 64) >= 64 * 4096 * 4
 
 
 def test_product_path_refuses_cpu_tensors():
@@ -72,13 +83,25 @@ def test_product_path_refuses_cpu_tensors():
         ops.CSR.from_coo(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64), None, 4, 4)
 
 
+def test_fused_adam_refuses_cpu_parameters():
+    import torch
+    from mmrec_b200.optim import FusedAdam
+    from mmrec_b200._lib import MMRecError
+    p = torch.nn.Parameter(torch.zeros(4))
+    opt = FusedAdam([p], lr=1e-3)
+    p.grad = torch.ones(4)
+    with pytest.raises(MMRecError):
+        opt.step()
+    assert opt.state_dict()["param_groups"][0]["betas"] == (0.9, 0.999)
+
+
 def test_product_never_imports_the_oracle():
     import subprocess, sys
     out = subprocess.run([sys.executable, "-c",
                           "import sys; sys.path.insert(0, %r); import mmrec_b200.ops, mmrec_b200.graph, "
                           "mmrec_b200.models.freedom, mmrec_b200.models.bm3, mmrec_b200.models.mgcn, "
                           "mmrec_b200.models.lightgcn, mmrec_b200.models.layergcn, mmrec_b200.models.mmgcn, mmrec_b200.sharded, "
-                          "mmrec_b200.common.trainer, mmrec_b200.utils.quick_start; "
+                          "mmrec_b200.common.trainer, mmrec_b200.utils.quick_start, mmrec_b200.optim; "
                           "print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))" % ROOT],
                          capture_output=True, text=True, check=True)
     assert out.stdout.strip() == "False"

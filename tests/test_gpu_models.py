@@ -232,3 +232,35 @@ def test_quick_start_runs_end_to_end(env):
                                                     "eval_batch_size": 128, "train_batch_size": 512}, save_model=False)
     assert len(results) == 1
     assert 0.0 <= results[0][2]["recall@20"] <= 1.0 and results[0][1]["recall@20"] > 0.0
+
+
+@pytest.mark.parametrize("name,file,attrs", [
+    ("FREEDOM", "freedom_tiny.npz", ["mm_adj"]),
+    ("MGCN", "mgcn_tiny.npz", ["image_original_adj", "text_original_adj"]),
+])
+def test_knn_item_graph_on_the_scoring_kernels(env, golden, name, file, attrs):
+    """f4: the item-item graphs the models build at init (`graph._knn`: ops.score + ops.mask_topk) against the matrices the
+    reference built from the same features (src/models/freedom.py:79-100, src/utils/utils.py:165-183): same coordinates,
+    values to 1e-6."""
+    gold = golden(file)
+    config, train, valid, test, model = build(name, env, {})
+    for attr in attrs:
+        gi, gv = gold[attr + "_idx"], gold[attr + "_val"]
+        n = getattr(model, attr).n_rows
+        ref = torch.sparse_coo_tensor(torch.from_numpy(gi), torch.from_numpy(gv), (n, n)).coalesce()
+        r, c, v = getattr(model, attr).coo()
+        ours = torch.sparse_coo_tensor(torch.stack([r, c]).cpu(), v.cpu(), (n, n)).coalesce()
+        assert torch.equal(ours.indices(), ref.indices()), f"{attr}: different neighbour sets"
+        assert rel(ours.values(), ref.values()) < 1e-6
+
+
+def test_mgcn_fused_inference_forward_equals_the_autograd_form(env):
+    """a5b: `MGCN.forward` without autograd (gate / fuse kernels, SpMMs writing into the stacked tables) against the same
+    forward under autograd (torch expressions of src/models/mgcn.py:153-201)."""
+    config, train, valid, test, model = build("MGCN", env, {})
+    model.eval()
+    with torch.no_grad():
+        u0, i0 = model.forward(model.norm_adj)
+    u1, i1 = model.forward(model.norm_adj)                   # grad enabled: the torch route
+    assert u1.requires_grad and not u0.requires_grad
+    assert rel(u0, u1) < 2e-6 and rel(i0, i1) < 2e-6
