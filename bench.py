@@ -414,23 +414,32 @@ def bench_model(wl, model_name, dev, args, flush, sampler=None, full=True):
         # one training step through the plugin calls: calculate_loss + backward + Adam (src/common/trainer.py:147-189)
         try:
             from mmrec_b200.common.trainer import Trainer
-            trainer = Trainer(config, model)
-            model.train(); model.pre_epoch_processing()
-            it = iter(train)
-            ts = []
-            for i in range(8):
-                batch = next(it)
-                e0, e1 = ev(), ev()
-                e0.record()
-                trainer.optimizer.zero_grad()
-                loss = model.calculate_loss(batch)
-                loss = sum(loss) if isinstance(loss, tuple) else loss
-                loss.backward()
-                trainer.optimizer.step()
-                e1.record(); torch.cuda.synchronize()
-                if i >= 3:
-                    ts.append(e0.elapsed_time(e1))
-            res["train_step_ms"] = float(np.median(ts))
+
+            def time_train(trainer):
+                model.train(); model.pre_epoch_processing()
+                it = iter(train)
+                ts = []
+                for i in range(8):
+                    batch = next(it)
+                    e0, e1 = ev(), ev()
+                    e0.record()
+                    trainer.optimizer.zero_grad()
+                    loss = model.calculate_loss(batch)
+                    loss = sum(loss) if isinstance(loss, tuple) else loss
+                    loss.backward()
+                    trainer.optimizer.step()
+                    e1.record(); torch.cuda.synchronize()
+                    if i >= 3:
+                        ts.append(e0.elapsed_time(e1))
+                return float(np.median(ts))
+            # f1: FusedAdam + factored table gradient (csrc/train.cu); then the same step with torch.optim.Adam and the dense
+            # [n_items, F] table gradients for comparison (eager launches on both sides, host overhead included)
+            tr_fused = Trainer(config, model)
+            res["train_step_ms"] = time_train(tr_fused)
+            res["train_optimizer"] = type(tr_fused.optimizer).__name__
+            config["fused_adam"] = False
+            res["train_step_ms_torch_adam"] = time_train(Trainer(config, model))      # (its constructor takes the parameters back)
+            config["fused_adam"] = None
             res["train_batch"] = int(config["train_batch_size"])
             model.eval()
         except Exception as exc:                                     # noqa: BLE001
@@ -486,7 +495,8 @@ def run_ours(args):
                   "scored_items_per_sec_batch4096": r["score_items"] / (ms["c4096"] * 1e-3),
                   "projected_rows_per_sec": (2 * wl.I / (msB * 1e-3)) if msB else None,
                   "edges_per_step": edges, "scored_items_per_step": r["score_items"],
-                  "train_step_ms": r.get("train_step_ms"), "train_batch": r.get("train_batch"),
+                  "train_step_ms": r.get("train_step_ms"), "train_step_ms_torch_adam": r.get("train_step_ms_torch_adam"),
+                  "train_optimizer": r.get("train_optimizer"), "train_batch": r.get("train_batch"),
                   "score_path": os.environ.get("MMREC_SCORE_PATH", "auto"), "torch_gpu_comparator": r.get("torch_gpu_comparator")},
         "roofline": {"kernel": "spmm_vec_kernel<64,16> (the SpMMs of one forward: 3 x A_hat + mm_adj)", "bound": "hbm",
                      "achieved": spmm_bytes / (msA * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -49,12 +49,17 @@ class Trainer(object):
         self.use_fused_topk = config["use_fused_topk"] is not False
 
     def _build_optimizer(self):
-        params, lr, wd = self.model.parameters(), self.learning_rate, self.weight_decay
+        params, lr, wd = list(self.model.parameters()), self.learning_rate, self.weight_decay
         name = self.learner.lower()
+        fused = name == "adam" and self.config["fused_adam"] is not False and len(params) > 0 and params[0].is_cuda
+        if not fused:
+            for p in params:                   # a FusedAdam that owned these parameters before no longer gets factored gradients
+                p._mmrec_defer = None
+                p._mmrec_pending = None
         if name == "adam":
             # f1: the same optimiser on the kernels of csrc/train.cu (Adam step fused with the projection backward of the
             # trainable modality tables); `config["fused_adam"] = False` keeps torch's.
-            if self.config["fused_adam"] is not False and next(self.model.parameters()).is_cuda:
+            if fused:
                 from ..optim import FusedAdam
                 return FusedAdam(params, lr=lr, weight_decay=wd)
             return optim.Adam(params, lr=lr, weight_decay=wd)

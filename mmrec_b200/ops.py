@@ -523,7 +523,8 @@ class _ProjectFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             G = g if idx is None else index_sum_rows(g, idx, table.shape[0])     # d-wide scatter; the table gradient is G @ W
             p = ctx.table_param
-            if p is not None and getattr(p, "_mmrec_defer", False) and getattr(p, "_mmrec_pending", None) is None \
+            owner = getattr(p, "_mmrec_defer", None) if p is not None else None
+            if owner is not None and owner() is not None and getattr(p, "_mmrec_pending", None) is None \
                     and weight.shape[0] <= 128 and weight.shape[1] % 4 == 0:
                 # The optimiser (optim.FusedAdam) asked for the gradient in factored form: it updates the table with G @ W
                 # computed inside its kernel, so the [n_items, F] gradient never exists.  `.grad` stays None for this table.

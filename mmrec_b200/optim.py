@@ -16,6 +16,8 @@ materialise into `.grad` (`materialize_pending`) and the table takes the ordinar
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import ops
@@ -37,8 +39,16 @@ class FusedAdam(torch.optim.Adam):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, foreach=False)
         for group in self.param_groups:
             for p in group["params"]:
-                p._mmrec_defer = True          # ops._ProjectFn.backward may leave this parameter's gradient factored
+                p._mmrec_defer = weakref.ref(self)   # ops._ProjectFn.backward may leave this parameter's gradient factored
+                                                     # for as long as this optimiser lives (`release()` ends it earlier)
                 p._mmrec_pending = None
+
+    def release(self):
+        """Stop asking for factored gradients (call before handing the parameters to another optimiser)."""
+        self.materialize_pending()
+        for group in self.param_groups:
+            for p in group["params"]:
+                p._mmrec_defer = None
 
     # -- factored gradients ------------------------------------------------------------------------
     @staticmethod
