@@ -298,19 +298,21 @@ int mmrec_topk_metrics_f64(int64_t n_users, int K, const int64_t* topk_idx, cons
  * GEMMs dW = g^T X, dX = g W plus a dense [n_items, F] gradient -- and `torch.optim.Adam.step` over it
  * (src/common/trainer.py:117-118,185-189).  IEEE fp32 on CUDA cores, operation order of torch's `_multi_tensor_adam`.
  *
- * mmrec_index_sum_rows_f32     G[i,:] = sum over j ascending with idx[j] == i of g[j,:]    G [n_rows, ldG], g [n_idx, ldg],
- *                              1 <= d <= 256; rows nobody points at become zero; indices outside [0, n_rows) are ignored.
+ * mmrec_index_sum_rows_f32     G[i,:] = sum over j ascending with idx[j] == i of g[j,:]    G [n_rows, ldG], g [n_idx, ldg];
+ *                              rows nobody points at become zero; indices outside [0, n_rows) are ignored.
  *                              The gradient of a gathered projection `Linear(table)[idx]` w.r.t. the table is G W.
  * mmrec_linear_wgrad_f32       dW[k,f] = sum_j g[j,k] table[idx ? idx[j] : j, f]   dW [d, F];   db[k] = sum_j g[j,k]  (db nullable)
- *                              F a multiple of 4, table and dW 16-byte aligned; ws from mmrec_linear_wgrad_workspace_bytes
- *                              (per-CTA partials, reduced in a fixed order: bit-reproducible).
- * mmrec_linear_dgrad_f32       dX = G W   dX [n_rows, F] (leading dimension F), G [n_rows, ldG], W [d, F], d <= 128.
+ *                              ws from mmrec_linear_wgrad_workspace_bytes (per-CTA partials, reduced in a fixed order:
+ *                              bit-reproducible).  16-byte accesses when F % 4 == 0 and table / dW / ws are aligned, else 4-byte.
+ * mmrec_linear_dgrad_f32       dX = G W   dX [n_rows, F] (leading dimension F), G [n_rows, ldG], W [d, F]; any d (128 k at a
+ *                              time), any F.
  * mmrec_linear_dgrad_adam_f32  one Adam step of `param` [n_rows, F] whose gradient is G W, WITHOUT materialising it:
  *                                grad = G W (+ weight_decay * param);  exp_avg += (1 - beta1)(grad - exp_avg);
  *                                exp_avg_sq = beta2 exp_avg_sq + (1 - beta2) grad^2;
  *                                param += step_size * exp_avg / (sqrt(exp_avg_sq) / bc2_sqrt + eps)
  *                              with step_size = -lr / (1 - beta1^t) and bc2_sqrt = sqrt(1 - beta2^t) computed by the caller in
  *                              double, as torch/optim/adam.py does.  W must still hold the values the forward used.
+ *                              d <= 128, F % 4 == 0, 16-byte aligned pointers (else MMREC_EUNSUPPORTED / MMREC_EINVAL).
  * mmrec_adam_f32               the same update for `n_tensors` ordinary (param, grad) pairs, one launch per 24 tensors;
  *                              `tensors` is a HOST array.
  * ------------------------------------------------------------------------------------------- */

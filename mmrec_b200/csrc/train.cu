@@ -20,6 +20,7 @@
 //
 // All arithmetic is IEEE fp32 (fmaf chains, sqrtf, division), in the operation order of torch's `_multi_tensor_adam`.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,52 +34,66 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// index_sum_rows
+// index_sum_rows: CTA = 32 table rows x 64 columns; warp w owns rows 4w .. 4w+3 and scans the index list ONCE (four
+// 32-entry groups per step), a lane owns columns lane and lane + 32 of its warp's four rows -- its accumulators sit in
+// shared memory only because the row of a match is a run-time value; nobody else touches them.
 // ------------------------------------------------------------------------------------------------
 constexpr int ISR_CHUNK = 8192;   // indices staged in shared memory at a time
-constexpr int ISR_ROWS = 64;      // table rows per CTA (8 per warp)
+constexpr int ISR_ROWS = 32;      // table rows per CTA (4 per warp)
+constexpr int ISR_COLS = 64;      // columns per CTA
 
 __global__ void __launch_bounds__(256) index_sum_rows_kernel(int64_t n_idx, const int64_t* __restrict__ idx, const float* __restrict__ g,
                                                              int64_t ldg, int d, int64_t n_rows, float* __restrict__ G, int64_t ldG) {
     __shared__ int s_idx[ISR_CHUNK];
+    __shared__ float s_acc[8][4][ISR_COLS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row_base = (int64_t)blockIdx.x * ISR_ROWS;
-    for (int64_t c0 = 0; c0 < n_idx || c0 == 0; c0 += ISR_CHUNK) {
+    const int cb = blockIdx.y * ISR_COLS;
+    const bool c0_ok = cb + lane < d, c1_ok = cb + lane + 32 < d;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s_acc[warp][q][lane] = 0.f; s_acc[warp][q][lane + 32] = 0.f; }
+    for (int64_t c0 = 0; c0 < n_idx; c0 += ISR_CHUNK) {
         const int len = (int)((n_idx - c0) < ISR_CHUNK ? (n_idx - c0) : ISR_CHUNK);
         __syncthreads();
-        for (int e = threadIdx.x; e < len; e += 256) {
-            const int64_t v = idx[c0 + e];
-            s_idx[e] = (v >= 0 && v < n_rows) ? (int)(v - row_base) : -1;     // row relative to this CTA (others: never matched)
+        for (int e = threadIdx.x; e < ISR_CHUNK; e += 256) {
+            int rel = -1;
+            if (e < len) {
+                const int64_t v = idx[c0 + e];
+                if (v >= row_base && v < row_base + ISR_ROWS && v < n_rows) rel = (int)(v - row_base);   // others: never matched
+            }
+            s_idx[e] = rel;
         }
         __syncthreads();
-        for (int rr = warp; rr < ISR_ROWS; rr += 8) {
-            const int64_t row = row_base + rr;
-            if (row >= n_rows) break;
-            float acc[8];
+        const int lo = warp * 4;
+        for (int it = 0; it < len; it += 128) {                           // (entries beyond len hold -1)
+            int v[4];
+            unsigned m[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-            for (int it = 0; it < len; it += 32) {
-                const int v = (it + lane < len) ? s_idx[it + lane] : -1;
-                unsigned m = __ballot_sync(0xffffffffu, v == rr);
-                while (m) {                                                   // ascending j
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const float* src = g + (c0 + it + b) * ldg;
+            for (int u = 0; u < 4; ++u) v[u] = (it + 32 * u + lane < ISR_CHUNK) ? s_idx[it + 32 * u + lane] - lo : -1;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int c = lane + 32 * q;
-                        if (c < d) acc[q] += __ldg(src + c);
-                    }
+            for (int u = 0; u < 4; ++u) m[u] = __ballot_sync(0xffffffffu, v[u] >= 0 && v[u] < 4);
+            if ((m[0] | m[1] | m[2] | m[3]) == 0u) continue;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                unsigned mm = m[u];
+                while (mm) {                                                 // ascending j: bit-reproducible sums
+                    const int b = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const int q = __shfl_sync(0xffffffffu, v[u], b);
+                    const float* src = g + (c0 + it + 32 * u + b) * ldg + cb;
+                    if (c0_ok) s_acc[warp][q][lane] += __ldg(src + lane);
+                    if (c1_ok) s_acc[warp][q][lane + 32] += __ldg(src + lane + 32);
                 }
             }
-            float* dst = G + row * ldG;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = lane + 32 * q;
-                if (c < d) dst[c] = (c0 == 0) ? acc[q] : dst[c] + acc[q];
-            }
         }
-        if (n_idx == 0) break;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t row = row_base + warp * 4 + q;
+        if (row < n_rows) {
+            if (c0_ok) G[row * ldG + cb + lane] = s_acc[warp][q][lane];
+            if (c1_ok) G[row * ldG + cb + lane + 32] = s_acc[warp][q][lane + 32];
+        }
     }
 }
 
@@ -93,7 +108,7 @@ constexpr size_t WG_SMEM = 2 * WG_RT * WG_SC * sizeof(float) + 2 * WG_RT * WG_KT
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 linear_wgrad_kernel(int64_t n, const int64_t* __restrict__ idx, const float* __restrict__ g, int64_t ldg, int d, int d_pad,
-                    const float* __restrict__ table, int64_t n_table, int64_t F, int64_t rows_per_chunk, float* __restrict__ part,
+                    const float* __restrict__ table, int64_t n_table, int64_t F, int vec, int64_t rows_per_chunk, float* __restrict__ part,
                     float* __restrict__ part_b) {
     extern __shared__ __align__(16) unsigned char wg_smem[];
     float* Xs = reinterpret_cast<float*>(wg_smem);                      // [2][RT][SC]
@@ -129,7 +144,12 @@ linear_wgrad_kernel(int64_t n, const int64_t* __restrict__ idx, const float* __r
             int64_t row = idx ? idx[j] : j;
             row = row < 0 ? 0 : (row >= n_table ? n_table - 1 : row);
             const int64_t col = col0 + 4 * c4;
-            if (col < F) cp_async16(xs + r * WG_SC + 4 * c4, table + row * F + col);
+            if (vec) {                                                   // F % 4 == 0, 16-byte aligned table
+                if (col < F) cp_async16(xs + r * WG_SC + 4 * c4, table + row * F + col);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xs[r * WG_SC + 4 * c4 + q] = (col + q < F) ? __ldg(table + row * F + col + q) : 0.f;
+            }
         }
 #pragma unroll
         for (int i = 0; i < WG_RT * WG_KT / WG_THREADS; ++i) {           // 2 floats per thread
@@ -170,24 +190,42 @@ linear_wgrad_kernel(int64_t n, const int64_t* __restrict__ idx, const float* __r
     float* dst = part + ((int64_t)blockIdx.y * d_pad + k0 + kg * 8) * F;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
-        if (col0 + ca < F) *reinterpret_cast<float4*>(dst + a * F + col0 + ca) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-        if (col0 + cb < F) *reinterpret_cast<float4*>(dst + a * F + col0 + cb) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+        if (vec) {
+            if (col0 + ca < F) *reinterpret_cast<float4*>(dst + a * F + col0 + ca) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+            if (col0 + cb < F) *reinterpret_cast<float4*>(dst + a * F + col0 + cb) = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (col0 + ca + q < F) dst[a * F + col0 + ca + q] = acc[a][q];
+                if (col0 + cb + q < F) dst[a * F + col0 + cb + q] = acc[a][4 + q];
+            }
+        }
     }
     if (want_b) part_b[(int64_t)blockIdx.y * d_pad + k0 + tid] = bacc;
 }
 
 // dW[k][f] = sum_s part[s][k][f] (s ascending), db[k] = sum_s part_b[s][k]
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(int n_chunks, int d, int d_pad, int64_t F, const float* __restrict__ part,
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(int n_chunks, int d, int d_pad, int64_t F, int vec, const float* __restrict__ part,
                                                            const float* __restrict__ part_b, float* __restrict__ dW, float* __restrict__ db) {
-    const int64_t n4 = (int64_t)d * (F / 4);
-    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n4; e += (int64_t)gridDim.x * 256) {
-        const int64_t k = e / (F / 4), c4 = e - k * (F / 4);
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = 0; c < n_chunks; ++c) {
-            const float4 v = ldg4(part + ((int64_t)c * d_pad + k) * F + 4 * c4);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    if (vec) {
+        const int64_t n4 = (int64_t)d * (F / 4);
+        for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n4; e += (int64_t)gridDim.x * 256) {
+            const int64_t k = e / (F / 4), c4 = e - k * (F / 4);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < n_chunks; ++c) {
+                const float4 v = ldg4(part + ((int64_t)c * d_pad + k) * F + 4 * c4);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            *reinterpret_cast<float4*>(dW + k * F + 4 * c4) = s;
         }
-        *reinterpret_cast<float4*>(dW + k * F + 4 * c4) = s;
+    } else {
+        const int64_t n1 = (int64_t)d * F;
+        for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < n1; e += (int64_t)gridDim.x * 256) {
+            const int64_t k = e / F, f = e - k * F;
+            float s = 0.f;
+            for (int c = 0; c < n_chunks; ++c) s += __ldg(part + ((int64_t)c * d_pad + k) * F + f);
+            dW[e] = s;
+        }
     }
     if (db && blockIdx.x == 0) {
         for (int k = threadIdx.x; k < d; k += 256) {
@@ -216,7 +254,7 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     m = fmaf(a.w1, gr - m, m);
     v = fmaf(a.w2 * gr, gr, v * a.beta2);
     const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-    p = fmaf(-a.step_size, m / denom, p);
+    p = fmaf(a.step_size, m / denom, p);          // step_size = -lr / (1 - beta1^t): negative
 }
 
 enum { DG_STORE = 0, DG_ADAM = 1 };
@@ -231,8 +269,8 @@ struct DgradShape {
 
 template <int KT, int SC, int MODE>
 __global__ void __launch_bounds__(256, 1)
-linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, int d, const float* __restrict__ W, int64_t F, float* out,
-                    float* P, float* M, float* V, AdamScalars as) {
+linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, int d, const float* __restrict__ W, int64_t F, int vec, int accum,
+                    int cluster_sync, float* out, float* P, float* M, float* V, AdamScalars as) {
     using S = DgradShape<KT, SC>;
     constexpr int CG = S::CG, RT = S::RT;
     extern __shared__ __align__(16) unsigned char dg_smem[];
@@ -247,7 +285,12 @@ linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, in
     for (int e = tid; e < KT * (SC / 4); e += 256) {                      // this CTA's column strip of W, resident for its lifetime
         const int k = e / (SC / 4), c4 = e - k * (SC / 4);
         const int64_t c = (int64_t)blockIdx.x * SC + 4 * c4;
-        const float4 w = (k < d && c < F) ? ldg4(W + (int64_t)k * F + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < d && c < F) {
+            const float* src = W + (int64_t)k * F + c;
+            if (vec) w = ldg4(src);
+            else { w.x = __ldg(src); if (c + 1 < F) w.y = __ldg(src + 1); if (c + 2 < F) w.z = __ldg(src + 2); if (c + 3 < F) w.w = __ldg(src + 3); }
+        }
         *reinterpret_cast<float4*>(Ws + k * SC + 4 * c4) = w;
     }
     constexpr int GQ = KT * RT / 256;                                     // G tile elements per thread
@@ -310,7 +353,16 @@ linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, in
             const int64_t row = tile * RT + rg * 8 + r;
             if (!(col_ok && row < n_rows)) continue;
             if (MODE == DG_STORE) {
-                *reinterpret_cast<float4*>(out + row * F + col) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                float* o = out + row * F + col;
+                if (vec) {
+                    float4 t = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                    if (accum) { const float4 q = *reinterpret_cast<const float4*>(o); t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w; }
+                    *reinterpret_cast<float4*>(o) = t;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (col + q < F) o[q] = accum ? o[q] + acc[r][q] : acc[r][q];
+                }
             } else {
                 float4 p = pp[r], m = pm[r], v = pv[r];
                 adam_update(p.x, m.x, v.x, acc[r][0], as);
@@ -322,6 +374,9 @@ linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, in
                 *reinterpret_cast<float4*>(V + row * F + col) = v;
             }
         }
+        // Launched as clusters along x (the column strips of the same rows): keep the strips of a row tile in step, so that
+        // their 2 KB requests per row reach the DRAM together as whole rows.  Same tile count in every CTA of a cluster.
+        if (cluster_sync) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         if (next < n_tiles) prefetch(next);                               // in flight during the next tile's k loop
         float* gn = Gs + (buf ^ 1) * KT * RT;
 #pragma unroll
@@ -331,8 +386,8 @@ linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, in
 }
 
 template <int KT, int SC, int MODE>
-static int launch_dgrad(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, float* out, float* P, float* M,
-                        float* V, const AdamScalars& as, cudaStream_t stream) {
+static int launch_dgrad(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, int vec, int accum, float* out, float* P,
+                        float* M, float* V, const AdamScalars& as, cudaStream_t stream) {
     using S = DgradShape<KT, SC>;
     auto kern = linear_dgrad_kernel<KT, SC, MODE>;
     MMREC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));   // per device: set every time
@@ -342,16 +397,33 @@ static int launch_dgrad(int64_t n_rows, const float* G, int64_t ldG, int d, cons
     if (chunks < 1) chunks = 1;
     if (chunks > n_tiles) chunks = n_tiles;
     dim3 grid((unsigned)strips, (unsigned)chunks);
-    kern<<<grid, 256, S::SMEM, stream>>>(n_rows, G, ldG, d, W, F, out, P, M, V, as);
+    // MMREC_DGRAD_CLUSTER=1: the strips of a row tile as one thread-block cluster, synchronised per tile (Adam form only)
+    static int use_cluster = -1;
+    if (use_cluster < 0) { const char* e = getenv("MMREC_DGRAD_CLUSTER"); use_cluster = (e && e[0] == '1') ? 1 : 0; }
+    int cs = 1;
+    if (use_cluster && MODE == DG_ADAM) { cs = 8; while (cs > 1 && (strips % cs) != 0) cs >>= 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = S::SMEM; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MMREC_CUDA(cudaLaunchKernelEx(&cfg, kern, n_rows, G, ldG, d, W, F, vec, accum, (int)(cs > 1), out, P, M, V, as));
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }
 
 template <int MODE>
-static int dispatch_dgrad(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, float* out, float* P, float* M,
-                          float* V, const AdamScalars& as, cudaStream_t stream) {
-    if (d <= 64) return launch_dgrad<64, 512, MODE>(n_rows, G, ldG, d, W, F, out, P, M, V, as, stream);
-    return launch_dgrad<128, 256, MODE>(n_rows, G, ldG, d, W, F, out, P, M, V, as, stream);
+static int dispatch_dgrad(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, int vec, float* out, float* P,
+                          float* M, float* V, const AdamScalars& as, cudaStream_t stream) {
+    if (d <= 64) return launch_dgrad<64, 512, MODE>(n_rows, G, ldG, d, W, F, vec, 0, out, P, M, V, as, stream);
+    // wider layers: 128 k at a time; the store form accumulates over the k chunks (Adam needs the whole sum at once: d <= 128)
+    for (int k0 = 0; k0 < d; k0 += 128) {
+        const int dk = d - k0 < 128 ? d - k0 : 128;
+        const int rc = launch_dgrad<128, 256, MODE>(n_rows, G + k0, ldG, dk, W + (int64_t)k0 * F, F, vec, k0 > 0, out, P, M, V, as, stream);
+        if (rc != MMREC_OK) return rc;
+    }
+    return MMREC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -416,10 +488,11 @@ using namespace mmrec;
 
 extern "C" int mmrec_index_sum_rows_f32(int64_t n_idx, const int64_t* idx, const float* g, int64_t ldg, int d, int64_t n_rows, float* G,
                                         int64_t ldG, void* stream_) {
-    MMREC_CHECK_ARG(n_idx >= 0 && n_rows >= 0 && d >= 1 && d <= 256, "index_sum_rows: bad sizes (1 <= d <= 256)");
+    MMREC_CHECK_ARG(n_idx >= 0 && n_rows >= 0 && d >= 1 && d <= 65535 * ISR_COLS, "index_sum_rows: bad sizes");
     if (n_rows == 0) return MMREC_OK;
     MMREC_CHECK_ARG(G && ldG >= d && (n_idx == 0 || (idx && g && ldg >= d)), "index_sum_rows: null pointer or bad leading dimension");
-    index_sum_rows_kernel<<<(unsigned)((n_rows + ISR_ROWS - 1) / ISR_ROWS), 256, 0, (cudaStream_t)stream_>>>(n_idx, idx, g, ldg, d, n_rows, G, ldG);
+    dim3 grid((unsigned)((n_rows + ISR_ROWS - 1) / ISR_ROWS), (unsigned)((d + ISR_COLS - 1) / ISR_COLS));
+    index_sum_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(n_idx, idx, g, ldg, d, n_rows, G, ldG);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }
@@ -449,9 +522,9 @@ extern "C" size_t mmrec_linear_wgrad_workspace_bytes(int64_t n, int64_t F, int d
 extern "C" int mmrec_linear_wgrad_f32(int64_t n, const int64_t* idx, const float* g, int64_t ldg, int d, const float* table, int64_t n_table,
                                       int64_t F, float* dW, float* db, void* ws, size_t ws_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    MMREC_CHECK_ARG(n >= 0 && d >= 1 && F >= 4 && (F & 3) == 0 && n_table >= 0, "linear_wgrad: bad sizes (F must be a multiple of 4)");
+    MMREC_CHECK_ARG(n >= 0 && d >= 1 && F >= 1 && n_table >= 0, "linear_wgrad: bad sizes");
     MMREC_CHECK_ARG(dW && (n == 0 || (g && table && ldg >= d && n_table >= 1)), "linear_wgrad: null pointer or bad leading dimension");
-    MMREC_CHECK_ARG((((uintptr_t)table | (uintptr_t)dW) & 15) == 0, "linear_wgrad: table and dW must be 16-byte aligned");
+    const int vec = (F & 3) == 0 && (((uintptr_t)table | (uintptr_t)dW | (uintptr_t)ws) & 15) == 0;   // else: 4-byte accesses
     if (n == 0) {
         MMREC_CUDA(cudaMemsetAsync(dW, 0, (size_t)d * F * sizeof(float), stream));
         if (db) MMREC_CUDA(cudaMemsetAsync(db, 0, (size_t)d * sizeof(float), stream));
@@ -470,24 +543,19 @@ extern "C" int mmrec_linear_wgrad_f32(int64_t n, const int64_t* idx, const float
     float* part_b = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + part_bytes);
     MMREC_CUDA(cudaFuncSetAttribute(linear_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
     dim3 grid((unsigned)strips, (unsigned)chunks, (unsigned)kt);
-    linear_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(n, idx, g, ldg, d, d_pad, table, n_table, F, rpc, part, db ? part_b : nullptr);
+    linear_wgrad_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(n, idx, g, ldg, d, d_pad, table, n_table, F, vec, rpc, part, db ? part_b : nullptr);
     MMREC_LAUNCH_CHECK();
-    const int64_t n4 = (int64_t)d * (F / 4);
-    int64_t blocks = (n4 + 255) / 256;
+    const int64_t n_el = vec ? (int64_t)d * (F / 4) : (int64_t)d * F;
+    int64_t blocks = (n_el + 255) / 256;
     if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
-    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>((int)chunks, d, d_pad, F, part, part_b, dW, db);
+    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>((int)chunks, d, d_pad, F, vec, part, part_b, dW, db);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }
 
 static int dgrad_args(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, const char* who) {
-    MMREC_CHECK_ARG(n_rows >= 0 && d >= 1 && F >= 4 && (F & 3) == 0, "%s: bad sizes (F must be a multiple of 4)", who);
-    if (d > 128) {
-        set_error("%s: d = %d > 128 has no kernel", who, d);
-        return MMREC_EUNSUPPORTED;
-    }
+    MMREC_CHECK_ARG(n_rows >= 0 && d >= 1 && F >= 1, "%s: bad sizes", who);
     MMREC_CHECK_ARG(n_rows == 0 || (G && W && ldG >= d), "%s: null pointer or bad leading dimension", who);
-    MMREC_CHECK_ARG(((uintptr_t)W & 15) == 0, "%s: W must be 16-byte aligned", who);
     return MMREC_OK;
 }
 
@@ -495,9 +563,10 @@ extern "C" int mmrec_linear_dgrad_f32(int64_t n_rows, const float* G, int64_t ld
     const int rc = dgrad_args(n_rows, G, ldG, d, W, F, "linear_dgrad");
     if (rc != MMREC_OK) return rc;
     if (n_rows == 0) return MMREC_OK;
-    MMREC_CHECK_ARG(dX && ((uintptr_t)dX & 15) == 0, "linear_dgrad: dX null or not 16-byte aligned");
+    MMREC_CHECK_ARG(dX, "linear_dgrad: dX is null");
+    const int vec = (F & 3) == 0 && (((uintptr_t)W | (uintptr_t)dX) & 15) == 0;       // else: 4-byte accesses
     AdamScalars as{};
-    return dispatch_dgrad<DG_STORE>(n_rows, G, ldG, d, W, F, dX, nullptr, nullptr, nullptr, as, (cudaStream_t)stream_);
+    return dispatch_dgrad<DG_STORE>(n_rows, G, ldG, d, W, F, vec, dX, nullptr, nullptr, nullptr, as, (cudaStream_t)stream_);
 }
 
 extern "C" int mmrec_linear_dgrad_adam_f32(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, float* param,
@@ -505,12 +574,16 @@ extern "C" int mmrec_linear_dgrad_adam_f32(int64_t n_rows, const float* G, int64
                                            double step_size, double bc2_sqrt, void* stream_) {
     const int rc = dgrad_args(n_rows, G, ldG, d, W, F, "linear_dgrad_adam");
     if (rc != MMREC_OK) return rc;
+    if (d > 128 || (F & 3) != 0) {
+        set_error("linear_dgrad_adam: d = %d, F = %lld has no fused kernel (d <= 128, F a multiple of 4)", d, (long long)F);
+        return MMREC_EUNSUPPORTED;
+    }
     if (n_rows == 0) return MMREC_OK;
-    MMREC_CHECK_ARG(param && exp_avg && exp_avg_sq && (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
-                    "linear_dgrad_adam: state pointers null or not 16-byte aligned");
+    MMREC_CHECK_ARG(param && exp_avg && exp_avg_sq && (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)W) & 15) == 0,
+                    "linear_dgrad_adam: pointers null or not 16-byte aligned");
     MMREC_CHECK_ARG(bc2_sqrt > 0.0, "linear_dgrad_adam: bc2_sqrt must be positive");
     const AdamScalars as = adam_scalars(beta1, beta2, eps, weight_decay, step_size, bc2_sqrt);
-    return dispatch_dgrad<DG_ADAM>(n_rows, G, ldG, d, W, F, nullptr, param, exp_avg, exp_avg_sq, as, (cudaStream_t)stream_);
+    return dispatch_dgrad<DG_ADAM>(n_rows, G, ldG, d, W, F, 1, nullptr, param, exp_avg, exp_avg_sq, as, (cudaStream_t)stream_);
 }
 
 extern "C" int mmrec_adam_f32(int n_tensors, const mmrec_adam_tensor* tensors, double beta1, double beta2, double eps, double weight_decay,

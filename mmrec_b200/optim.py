@@ -10,12 +10,17 @@ names (`step`, `exp_avg`, `exp_avg_sq`) and `state_dict` layout -- it IS a `torc
   `grad = G @ W`, and the kernel updates table, exp_avg and exp_avg_sq with that product computed on the fly -- the dense
   [n_items, F] gradient (115 MB per modality at Amazon-baby size) is never written or read.
 
-The factored form is only used where it is exact: a second backward before `step()` (gradient accumulation), a
+Measured on B200 (tools/bench_train.py, 7000 x 4096 table): the factored step takes 342 us (the CTA-per-column-strip
+access pattern moves the six table-sized streams at 2.0 TB/s), the dense route -- `mmrec_linear_dgrad_f32` writing the
+gradient, `mmrec_adam_f32` streaming everything linearly at 6.4 TB/s -- 102 + 125 us; torch/cuBLAS needs 98 + 497 us.
+So `factored` is opt-in (`FusedAdam(..., factored=True)` or env MMREC_FACTORED_TABLE_GRAD=1): it trades time for not
+holding the [n_items, F] gradient.  The factored form is only used where it is exact: a second backward before `step()` (gradient accumulation), a
 gradient from another path, `clip_grad_norm_` or a `weight` that changed since the backward make the pending product
 materialise into `.grad` (`materialize_pending`) and the table takes the ordinary route.  There is no CPU path.
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import torch
@@ -34,12 +39,16 @@ def _bump_version(p):
         p.add_(0)
 
 
+FACTORED_DEFAULT = os.environ.get("MMREC_FACTORED_TABLE_GRAD", "0") == "1"
+
+
 class FusedAdam(torch.optim.Adam):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, factored=None):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, foreach=False)
+        self.factored = FACTORED_DEFAULT if factored is None else bool(factored)
         for group in self.param_groups:
             for p in group["params"]:
-                p._mmrec_defer = weakref.ref(self)   # ops._ProjectFn.backward may leave this parameter's gradient factored
+                p._mmrec_defer = weakref.ref(self) if self.factored else None   # ops._ProjectFn.backward may leave this parameter's gradient factored
                                                      # for as long as this optimiser lives (`release()` ends it earlier)
                 p._mmrec_pending = None
 

@@ -59,10 +59,11 @@ def test_argument_errors_without_a_gpu():
     assert lib.mmrec_catalog_bytes(7000, 64) >= 7000 * 64 * 2 and lib.mmrec_catalog_bytes(7000, 300) == 0
     assert lib.mmrec_launch_count() >= 0
     # f1: projection backward / Adam
-    assert lib.mmrec_index_sum_rows_f32(4, None, None, 64, 300, 10, None, 300, None) == -1          # d > 256
-    assert lib.mmrec_linear_wgrad_f32(8, None, None, 64, 64, None, 8, 4098, None, None, None, 0, None) == -1   # F not a multiple of 4
+    assert lib.mmrec_index_sum_rows_f32(4, None, None, 64, 300, 10, None, 300, None) == -1          # null pointers
+    assert lib.mmrec_linear_wgrad_f32(8, None, None, 64, 64, None, 8, 4098, None, None, None, 0, None) == -1   # null pointers
     assert b"linear_wgrad" in lib.mmrec_last_error()
-    assert lib.mmrec_linear_dgrad_f32(8, None, 200, 200, None, 4096, None, None) == -4             # d > 128: no kernel
+    assert lib.mmrec_linear_dgrad_f32(8, None, 200, 200, None, 4096, None, None) == -1
+    assert lib.mmrec_linear_dgrad_adam_f32(8, 16, 200, 200, 32, 4096, None, None, None, 0.9, 0.999, 1e-8, 0.0, -1e-3, 1.0, None) == -4   # d > 128: no fused kernel
     assert lib.mmrec_linear_dgrad_adam_f32(0, None, 64, 64, None, 4096, None, None, None, 0.9, 0.999, 1e-8, 0.0, -1e-3, 1.0, None) == 0
     assert lib.mmrec_adam_f32(0, None, 0.9, 0.999, 1e-8, 0.0, None) == 0
     bad = (_lib.AdamTensor * 1)()

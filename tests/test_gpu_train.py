@@ -27,7 +27,8 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("n_idx,n_rows,d", [(0, 10, 64), (1, 1, 1), (4096, 7000, 64), (20000, 300, 100), (9000, 70, 256), (500, 100000, 32)])
+@pytest.mark.parametrize("n_idx,n_rows,d", [(0, 10, 64), (1, 1, 1), (4096, 7000, 64), (20000, 300, 100), (9000, 70, 256), (500, 100000, 32),
+                                            (700, 333, 300)])
 def test_index_sum_rows(dev, n_idx, n_rows, d):
     from mmrec_b200 import ops
     g = torch.Generator().manual_seed(n_idx + d)
@@ -47,6 +48,8 @@ def test_index_sum_rows(dev, n_idx, n_rows, d):
     (7000, 7000, 384, 64, False, True),           # text table (one column strip, partly empty)
     (1000, 1000, 516, 128, False, False),         # d = 128: two k tiles; F not a multiple of the strip
     (37, 50, 100, 20, True, True),                # small and ragged
+    (333, 333, 130, 64, False, True),             # F not a multiple of 4: 4-byte accesses
+    (50, 64, 77, 300, True, True),
     (1, 1, 4, 1, False, True),
 ])
 def test_linear_wgrad(dev, n, n_table, F, d, gather, bias):
@@ -74,7 +77,8 @@ def test_linear_wgrad_empty(dev):
     assert float(dW.abs().max()) == 0.0 and float(db.abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("n_rows,F,d", [(7000, 4096, 64), (7000, 384, 64), (333, 1028, 128), (17, 8, 3), (1, 4, 1), (5000, 512, 96)])
+@pytest.mark.parametrize("n_rows,F,d", [(7000, 4096, 64), (7000, 384, 64), (333, 1028, 128), (17, 8, 3), (1, 4, 1), (5000, 512, 96),
+                                        (333, 130, 64), (129, 200, 256), (50, 77, 300)])
 def test_linear_dgrad(dev, n_rows, F, d):
     from mmrec_b200 import ops
     g = torch.Generator().manual_seed(n_rows + F + d)
@@ -153,8 +157,8 @@ def test_project_backward_matches_autograd(dev, gather):
         assert rel(g, w) < TOL
 
 
-@pytest.mark.parametrize("gather,accumulate", [(False, False), (True, False), (True, True)])
-def test_fused_adam_equals_torch_adam_on_a_projection_model(dev, gather, accumulate):
+@pytest.mark.parametrize("gather,accumulate,factored", [(False, False, True), (True, False, True), (True, True, True), (True, False, False)])
+def test_fused_adam_equals_torch_adam_on_a_projection_model(dev, gather, accumulate, factored):
     """FusedAdam (factored table gradient, never materialised) against torch.optim.Adam on the same tiny model: parameters and
     optimiser state after 4 steps.  `accumulate`: two backwards per step -- the factored form must fall back to the dense one."""
     from mmrec_b200 import ops
@@ -178,15 +182,17 @@ def test_fused_adam_equals_torch_adam_on_a_projection_model(dev, gather, accumul
     gen = torch.Generator().manual_seed(12)
     idxs = [torch.randint(0, 500, (700,), generator=gen).to(dev) if gather else None for _ in range(8)]
     a, b = make(), make()
-    opt_a = FusedAdam([a[0], *a[1].parameters(), a[2]], lr=1e-2, weight_decay=0.0)
+    opt_a = FusedAdam([a[0], *a[1].parameters(), a[2]], lr=1e-2, weight_decay=0.0, factored=factored)
     opt_b = torch.optim.Adam([b[0], *b[1].parameters(), b[2]], lr=1e-2, weight_decay=0.0)
     for s in range(4):
         opt_a.zero_grad(); opt_b.zero_grad()
         for r in range(2 if accumulate else 1):
             loss_fn(*a, idxs[2 * s + r], True).backward()
             loss_fn(*b, idxs[2 * s + r], False).backward()
-        if not accumulate:
+        if factored and not accumulate:
             assert a[0].grad is None and a[0]._mmrec_pending is not None       # the dense table gradient was never built
+        if not factored:
+            assert a[0].grad is not None and a[0]._mmrec_pending is None
         v0 = a[0]._version
         opt_a.step(); opt_b.step()
         assert a[0]._version > v0 and a[0]._mmrec_pending is None

@@ -55,6 +55,8 @@ for F in [int(x) for x in a.F.split(",")]:
     opt.step()
     out["torch_adam_us"] = timed(lambda: opt.step())
     out["torch_index_add_us"] = timed(lambda: torch.zeros_like(table).index_add_(0, idx, upb.mm(W)))
-    out["ours_table_step_us"] = out["wgrad_us"] + out["dgrad_adam_us"]
+    out["ours_dense_table_step_us"] = out["wgrad_us"] + out["dgrad_store_us"] + out["adam_plain_us"]      # FusedAdam default
+    out["ours_factored_table_step_us"] = out["wgrad_us"] + out["dgrad_adam_us"]                           # factored=True
+    out["dgrad_cluster"] = os.environ.get("MMREC_DGRAD_CLUSTER", "0")
     out["torch_table_step_us"] = out["torch_wgrad_us"] + out["torch_dgrad_us"] + out["torch_adam_us"]
     print(json.dumps({k: (round(x, 2) if isinstance(x, float) else x) for k, x in out.items()}))
