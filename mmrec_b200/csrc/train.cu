@@ -257,7 +257,7 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     p = fmaf(a.step_size, m / denom, p);          // step_size = -lr / (1 - beta1^t): negative
 }
 
-enum { DG_STORE = 0, DG_ADAM = 1 };
+enum { DG_STORE = 0, DG_ADAM = 1, DG_STORE_ANY = 2 };   // STORE: 16-byte stores, no accumulation; STORE_ANY: run-time vec / accum
 
 template <int KT, int SC>
 struct DgradShape {
@@ -270,7 +270,7 @@ struct DgradShape {
 template <int KT, int SC, int MODE>
 __global__ void __launch_bounds__(256, 1)
 linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, int d, const float* __restrict__ W, int64_t F, int vec, int accum,
-                    int cluster_sync, float* out, float* P, float* M, float* V, AdamScalars as) {
+                    float* out, float* P, float* M, float* V, AdamScalars as) {
     using S = DgradShape<KT, SC>;
     constexpr int CG = S::CG, RT = S::RT;
     extern __shared__ __align__(16) unsigned char dg_smem[];
@@ -353,6 +353,8 @@ linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, in
             const int64_t row = tile * RT + rg * 8 + r;
             if (!(col_ok && row < n_rows)) continue;
             if (MODE == DG_STORE) {
+                *reinterpret_cast<float4*>(out + row * F + col) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            } else if (MODE == DG_STORE_ANY) {
                 float* o = out + row * F + col;
                 if (vec) {
                     float4 t = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
@@ -374,9 +376,6 @@ linear_dgrad_kernel(int64_t n_rows, const float* __restrict__ G, int64_t ldG, in
                 *reinterpret_cast<float4*>(V + row * F + col) = v;
             }
         }
-        // Launched as clusters along x (the column strips of the same rows): keep the strips of a row tile in step, so that
-        // their 2 KB requests per row reach the DRAM together as whole rows.  Same tile count in every CTA of a cluster.
-        if (cluster_sync) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         if (next < n_tiles) prefetch(next);                               // in flight during the next tile's k loop
         float* gn = Gs + (buf ^ 1) * KT * RT;
 #pragma unroll
@@ -397,18 +396,7 @@ static int launch_dgrad(int64_t n_rows, const float* G, int64_t ldG, int d, cons
     if (chunks < 1) chunks = 1;
     if (chunks > n_tiles) chunks = n_tiles;
     dim3 grid((unsigned)strips, (unsigned)chunks);
-    // MMREC_DGRAD_CLUSTER=1: the strips of a row tile as one thread-block cluster, synchronised per tile (Adam form only)
-    static int use_cluster = -1;
-    if (use_cluster < 0) { const char* e = getenv("MMREC_DGRAD_CLUSTER"); use_cluster = (e && e[0] == '1') ? 1 : 0; }
-    int cs = 1;
-    if (use_cluster && MODE == DG_ADAM) { cs = 8; while (cs > 1 && (strips % cs) != 0) cs >>= 1; }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = S::SMEM; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    MMREC_CUDA(cudaLaunchKernelEx(&cfg, kern, n_rows, G, ldG, d, W, F, vec, accum, (int)(cs > 1), out, P, M, V, as));
+    kern<<<grid, 256, S::SMEM, stream>>>(n_rows, G, ldG, d, W, F, vec, accum, out, P, M, V, as);
     MMREC_LAUNCH_CHECK();
     return MMREC_OK;
 }
@@ -566,7 +554,8 @@ extern "C" int mmrec_linear_dgrad_f32(int64_t n_rows, const float* G, int64_t ld
     MMREC_CHECK_ARG(dX, "linear_dgrad: dX is null");
     const int vec = (F & 3) == 0 && (((uintptr_t)W | (uintptr_t)dX) & 15) == 0;       // else: 4-byte accesses
     AdamScalars as{};
-    return dispatch_dgrad<DG_STORE>(n_rows, G, ldG, d, W, F, vec, dX, nullptr, nullptr, nullptr, as, (cudaStream_t)stream_);
+    if (vec && d <= 128) return dispatch_dgrad<DG_STORE>(n_rows, G, ldG, d, W, F, 1, dX, nullptr, nullptr, nullptr, as, (cudaStream_t)stream_);
+    return dispatch_dgrad<DG_STORE_ANY>(n_rows, G, ldG, d, W, F, vec, dX, nullptr, nullptr, nullptr, as, (cudaStream_t)stream_);
 }
 
 extern "C" int mmrec_linear_dgrad_adam_f32(int64_t n_rows, const float* G, int64_t ldG, int d, const float* W, int64_t F, float* param,

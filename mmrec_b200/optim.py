@@ -12,7 +12,8 @@ names (`step`, `exp_avg`, `exp_avg_sq`) and `state_dict` layout -- it IS a `torc
 
 Measured on B200 (tools/bench_train.py, 7000 x 4096 table): the factored step takes 342 us (the CTA-per-column-strip
 access pattern moves the six table-sized streams at 2.0 TB/s), the dense route -- `mmrec_linear_dgrad_f32` writing the
-gradient, `mmrec_adam_f32` streaming everything linearly at 6.4 TB/s -- 102 + 125 us; torch/cuBLAS needs 98 + 497 us.
+gradient, `mmrec_adam_f32` streaming everything linearly at 6.4 TB/s -- 120 + 124 us; torch/cuBLAS needs 101 + 490 us
+(profiles/r02_train.md).
 So `factored` is opt-in (`FusedAdam(..., factored=True)` or env MMREC_FACTORED_TABLE_GRAD=1): it trades time for not
 holding the [n_items, F] gradient.  The factored form is only used where it is exact: a second backward before `step()` (gradient accumulation), a
 gradient from another path, `clip_grad_norm_` or a `weight` that changed since the backward make the pending product

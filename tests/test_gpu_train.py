@@ -112,7 +112,7 @@ def test_linear_dgrad_adam_matches_torch_adam(dev, n_rows, F, d, wd):
     for t, G in enumerate(Gs, 1):
         ops.linear_dgrad_adam(G, W, p, m, v, b1, b2, eps, wd, -lr / (1 - b1 ** t), (1 - b2 ** t) ** 0.5)
     assert rel(m, want_m) < 5e-6 and rel(v, want_v) < 5e-6
-    assert rel(p - p0, want_p - p0) < 2e-5                            # the update itself (3 steps of ~lr each)
+    assert rel(p - p0, want_p - p0) < 1e-4         # the update itself: 3 steps of ~lr on values ~1 (fp32 spacing of p: ~2e-5 of it)
     assert rel(p, want_p) < TOL
 
 
