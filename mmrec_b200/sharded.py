@@ -73,6 +73,22 @@ class ItemShard:
             return PanelCSR.from_coo(rt, ct, vt, self.n_local, n_cols, d, sum_duplicates=True)
         return CSR.from_coo(rt, ct, vt, self.n_local, n_cols, sum_duplicates=True)
 
+    def csrs(self, device, d=64, l2_bytes=1 << 62):
+        """(users x local items, local items x users) as device CSRs; a matrix whose dense operand ([n_cols, d] fp32) is
+        larger than `l2_bytes` comes as a column-panelled `ops.PanelCSR`.  (Off by default: measured on B200 the panels LOSE --
+        1.27 ms -> 2.19 ms per layer at 32M non-zeros, d = 64; 0.35 -> 0.67 ms at the xls shape -- because every panel
+        re-reads and re-writes the whole output for a handful of non-zeros per row; profiles/r02_notes.md.)"""
+        from .ops import CSR, PanelCSR
+        u = torch.from_numpy(self.u).to(device)
+        i = torch.from_numpy(self.i_local).to(device)
+        v = torch.from_numpy(self.val).to(device)
+
+        def build(r, c, n_rows, n_cols):
+            if n_cols * d * 4 > l2_bytes:
+                return PanelCSR.from_coo(r, c, v, n_rows, n_cols, d, sum_duplicates=False)
+            return CSR.from_coo(r, c, v, n_rows, n_cols, sum_duplicates=False)
+        return build(u, i, self.n_users, self.n_local), build(i, u, self.n_local, self.n_users)
+
 
 def _cuda_spmm(A, X, acc_in=None, acc_div=1.0, want_y=True):
     from . import ops

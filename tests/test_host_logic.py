@@ -207,3 +207,22 @@ def test_bm3_objective_is_the_references_op_sequence():
     assert torch.equal(l0, l1)
     for k in names:
         assert torch.allclose(g0[k], g1[k], rtol=1e-6, atol=1e-9), k
+
+
+def test_sharded_driver_only_uses_names_that_exist():
+    """The multi-GPU driver and worker cannot run here (no GPUs); at least every `shard.<name>` / `px.<name>` / `ops.<name>` /
+    `sharded.<name>` they spell must exist (a method lost in a refactor once broke N > 1 without any CPU test noticing)."""
+    import inspect, re
+    from mmrec_b200 import ops, sharded
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = inspect.getsource(sharded) + open(os.path.join(ROOT, "tests", "sharded_gpu_worker.py")).read() + open(os.path.join(ROOT, "bench.py")).read()
+    for name in set(re.findall(r"\bshard\.([a-zA-Z_]\w*)", src)):
+        assert hasattr(sharded.ItemShard, name) or name in ("rank", "world", "n_users", "n_items", "local_items", "n_local", "u", "i_local",
+                                                            "val", "nnz"), f"ItemShard.{name} is used but not defined"
+    px_attrs = set(re.findall(r"self\.([a-zA-Z_]\w*)", inspect.getsource(sharded.PeerExchange.__init__))) | set(dir(sharded.PeerExchange))
+    for name in set(re.findall(r"\bpx\.([a-zA-Z_]\w*)", src)):
+        assert name in px_attrs, f"PeerExchange.{name} is used but not defined"
+    for name in set(re.findall(r"\bops\.([a-zA-Z_]\w*)", src)):
+        assert hasattr(ops, name), f"ops.{name} is used but not defined"
+    for name in set(re.findall(r"\bsharded\.([a-zA-Z_]\w*)", src)):
+        assert hasattr(sharded, name), f"sharded.{name} is used but not defined"
