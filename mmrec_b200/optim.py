@@ -115,8 +115,6 @@ class FusedAdam(torch.optim.Adam):
                     pend = None
                 if pend is None and p.grad is None:
                     continue
-                if not p.is_cuda:
-                    raise MMRecError("FusedAdam steps CUDA parameters only (no CPU path)")
                 if p.dtype != torch.float32 or (p.grad is not None and p.grad.is_sparse):
                     raise MMRecError("FusedAdam: dense float32 parameters only")
                 st = self._state_of(p)

@@ -226,3 +226,63 @@ def test_sharded_driver_only_uses_names_that_exist():
         assert hasattr(ops, name), f"ops.{name} is used but not defined"
     for name in set(re.findall(r"\bsharded\.([a-zA-Z_]\w*)", src)):
         assert hasattr(sharded, name), f"sharded.{name} is used but not defined"
+
+
+def test_fused_adam_host_logic_with_cpu_stand_ins(monkeypatch):
+    """`optim.FusedAdam` + `ops._ProjectFn.backward` host logic (bias corrections, factored table gradients, accumulation
+    fallback, version bumps, state layout) with the five kernels replaced by torch-CPU restatements of their documented
+    formulas (include/mmrec_b200.h, f1) -- against torch.optim.Adam on the same model.  The kernels themselves are checked on
+    the GPU (tests/test_gpu_train.py); this keeps the glue honest on a CPU box."""
+    from mmrec_b200 import ops
+    from mmrec_b200.optim import FusedAdam
+
+    def adam_el(p, g, m, v, b1, b2, eps, wd, step_size, bc2):
+        g = g + wd * p if wd else g
+        m.lerp_(g, 1 - b1); v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        p.add_(m / (v.sqrt() / bc2 + eps), alpha=step_size)
+    monkeypatch.setattr(ops, "project_raw", lambda t, w, b, idx=None, l2=False: torch.nn.functional.linear(t if idx is None else t[idx], w, b))
+    monkeypatch.setattr(ops, "linear_wgrad", lambda g, t, idx=None, want_bias=True: (g.t() @ (t if idx is None else t[idx]), g.sum(0) if want_bias else None))
+    monkeypatch.setattr(ops, "index_sum_rows", lambda g, idx, n: torch.zeros(n, g.shape[1]).index_add_(0, idx, g))
+    monkeypatch.setattr(ops, "linear_dgrad", lambda G, W: G @ W)
+    monkeypatch.setattr(ops, "linear_dgrad_adam", lambda G, W, p, m, v, b1, b2, eps, wd, ss, bc2: adam_el(p, G @ W, m, v, b1, b2, eps, wd, ss, bc2))
+    monkeypatch.setattr(ops, "adam_step", lambda entries, b1, b2, eps, wd: [adam_el(p, g, m, v, b1, b2, eps, wd, ss, bc2) for p, g, m, v, ss, bc2 in entries])
+
+    def make():
+        gen = torch.Generator().manual_seed(7)
+        table = torch.nn.Parameter(torch.randn(60, 24, generator=gen))
+        lin = torch.nn.Linear(24, 8)
+        with torch.no_grad():
+            lin.weight.copy_(0.3 * torch.randn(8, 24, generator=gen)); lin.bias.copy_(0.1 * torch.randn(8, generator=gen))
+        emb = torch.nn.Parameter(torch.randn(60, 8, generator=gen))
+        return table, lin, emb
+
+    def loss(m, idx, ours):
+        table, lin, emb = m
+        proj = ops.project(table, lin.weight, lin.bias, idx=idx) if ours else torch.nn.functional.linear(table, lin.weight, lin.bias)[idx]
+        return (proj * emb[idx]).sum(1).sigmoid().log().neg().mean()
+
+    gen = torch.Generator().manual_seed(8)
+    idxs = [torch.randint(0, 60, (90,), generator=gen) for _ in range(10)]
+    for factored, accumulate, wd in ((True, False, 0.0), (True, True, 0.01), (False, False, 0.01)):
+        a, b = make(), make()
+        pa, pb = [a[0], *a[1].parameters(), a[2]], [b[0], *b[1].parameters(), b[2]]
+        oa = FusedAdam(pa, lr=1e-2, weight_decay=wd, factored=factored)
+        ob = torch.optim.Adam(pb, lr=1e-2, weight_decay=wd)
+        sched_a = torch.optim.lr_scheduler.LambdaLR(oa, lambda e: 0.9 ** e)           # the trainer's scheduler works on the subclass
+        sched_b = torch.optim.lr_scheduler.LambdaLR(ob, lambda e: 0.9 ** e)
+        for s in range(5):
+            oa.zero_grad(); ob.zero_grad()
+            for r in range(2 if accumulate else 1):
+                loss(a, idxs[2 * s + r], True).backward(); loss(b, idxs[2 * s + r], False).backward()
+            if factored and not accumulate:
+                assert a[0].grad is None and a[0]._mmrec_pending is not None
+            v0 = a[0]._version
+            oa.step(); ob.step(); sched_a.step(); sched_b.step()
+            assert a[0]._version > v0 and a[0]._mmrec_pending is None
+        for x, y in zip(pa, pb):
+            np.testing.assert_allclose(x.detach().numpy(), y.detach().numpy(), rtol=2e-5, atol=2e-6)
+            np.testing.assert_allclose(oa.state[x]["exp_avg_sq"].numpy(), ob.state[y]["exp_avg_sq"].numpy(), rtol=2e-5, atol=1e-9)
+            assert float(oa.state[x]["step"]) == 5.0
+        ob.load_state_dict(oa.state_dict())                                          # same layout: loads into torch's Adam
+        oa.release()
+        assert all(getattr(p, "_mmrec_defer", None) is None for p in pa)
