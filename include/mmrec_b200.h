@@ -181,7 +181,8 @@ int mmrec_debug_stream_probe(const float* table, int64_t n_rows, int64_t F, int 
  * mmrec_topk_rows_f32: out_idx/out_val [B, k], descending value, ties -> lower index, index
  *                     reported as column + item_offset.  1 <= k <= 1024, k <= n_items.
  * mmrec_score_topk_f32: all three fused, scores never materialised in HBM (score_cf.cu): the tensor cores compute
- *                     tf32 scores with a proven error bound and only FILTER (per-row certified threshold = the
+ *                     approximate scores (operands rounded to fp16 after a power-of-two scaling: 11 significand bits, as
+ *                     tf32) with a proven error bound and only FILTER (per-row certified threshold = the
  *                     (k + masked)-th largest group maximum minus the bound); every candidate that survives is scored
  *                     again in fp32 (fmaf) from the original tables and ranked on that value, ties -> lower index.
  *                     Nothing depends on timing.  ws from mmrec_score_topk_workspace_bytes.

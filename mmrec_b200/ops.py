@@ -624,8 +624,8 @@ def mask_topk(scores: torch.Tensor, mask: Optional[torch.Tensor], k: int, item_o
 
 
 class Catalog:
-    """The item side of the scoring contraction prepared once per embedding table (`mmrec_catalog_pack_f32`): tf32
-    operand tiles + the maximum row norm of the error bound.  The reference re-reads the same `restore_item_e` for every
+    """The item side of the scoring contraction prepared once per embedding table (`mmrec_catalog_pack_f32`): fp16
+    operand tiles (power-of-two scaled, 11 significand bits) + the maximum row norm of the error bound.  The reference re-reads the same `restore_item_e` for every
     evaluation batch (`src/common/trainer.py:302-310`); a model keeps one Catalog next to its cached evaluation
     embeddings and drops it with them.  Holds a reference to `item_e`: the pair must stay consistent."""
 
