@@ -21,8 +21,9 @@ the oracle is pinned against outputs of the unmodified reference itself, run in 
 build container by `tests/golden/make_golden.py` and committed as
 `tests/golden/*_tiny.npz`; `tests/test_oracle_golden.py` checks every function here
 against those files (bit-exact for indices and for values produced by the same
-torch ops).  MMGCN has no pin (torch_geometric is not installable here): see
-`mmgcn_mean_aggregate`, marked "parity unpinned".
+torch ops).  MMGCN: torch_geometric is not installable here, so its one PyG primitive (`mmgcn_mean_aggregate`) stays
+"parity unpinned"; the model code around it is pinned to the reference run under a shim of that primitive
+(tests/golden/mmgcn_tiny.npz).
 """
 from __future__ import annotations
 
@@ -257,7 +258,9 @@ def mgcn_forward(p, adj, R, image_adj, text_adj, n_ui_layers, n_layers, train=Fa
 
 
 def mmgcn_mean_aggregate(edge_index: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """PARITY UNPINNED (torch_geometric is absent, the reference's MMGCN cannot run here).
+    """PARITY OF THIS PRIMITIVE UNPINNED (torch_geometric is absent here): it restates PyG's documented behaviour, and so
+    does the shim under which the reference's MMGCN is run for the golden file (tests/golden/ref_loader.py) -- everything
+    around it (towers, loss, scoring) IS pinned to the reference's own code through tests/golden/mmgcn_tiny.npz.
     Restates `src/models/mmgcn.py:191-213` + `:40-42`: PyG `MessagePassing(aggr='mean')` with
     `message = x_j` over edge_index = [src; dst] holding both directions: out[dst] = mean_j x[src_j]."""
     src, dst = edge_index[0], edge_index[1]
@@ -267,7 +270,8 @@ def mmgcn_mean_aggregate(edge_index: torch.Tensor, x: torch.Tensor) -> torch.Ten
 
 
 def mmgcn_gcn_forward(p, prefix, edge_index, features, id_embedding, preference, dim_latent, concate=True, has_id=True):
-    """PARITY UNPINNED.  One modality tower, `src/models/mmgcn.py:163-188` (`concate = 'False'` is truthy, `:31`):
+    """One modality tower, `src/models/mmgcn.py:163-188` (`concate = 'False'` is truthy, `:31`); pinned to the reference's
+    model code run under the PyG shim (tests/test_oracle_golden.py::test_mmgcn_matches_reference_model_code):
     `p` maps parameter names (`<prefix>.MLP.weight`, `<prefix>.conv_embed_1.weight`, ...) to tensors."""
     g = lambda name: p[prefix + "." + name]
     lin = lambda x, name: F.linear(x, g(name + ".weight"), g(name + ".bias"))
@@ -278,6 +282,24 @@ def mmgcn_gcn_forward(p, prefix, edge_index, features, id_embedding, preference,
         x_hat = F.leaky_relu(lin(x, f"linear_layer{li}")) + id_embedding if has_id else F.leaky_relu(lin(x, f"linear_layer{li}"))
         x = F.leaky_relu(lin(torch.cat((h, x_hat), dim=1), f"g_layer{li}")) if concate else F.leaky_relu(lin(h, f"g_layer{li}") + x_hat)
     return x
+
+
+def mmgcn_forward(p, edge_index, v_feat, t_feat, id_embedding, v_preference, t_preference, v_dim_latent=256):
+    """`src/models/mmgcn.py:64-77`: mean of the two modality towers (the visual one with a 256-wide latent MLP, `:46-47`)."""
+    rep = mmgcn_gcn_forward(p, "v_gcn", edge_index, v_feat, id_embedding, v_preference, v_dim_latent)
+    rep = rep + mmgcn_gcn_forward(p, "t_gcn", edge_index, t_feat, id_embedding, t_preference, None)
+    return rep / 2
+
+
+def mmgcn_loss(rep, id_embedding, v_preference, batch, n_users, reg_weight):
+    """`src/models/mmgcn.py:79-96`: log-sigmoid of (pos - neg) through the [1, -1] weight, plus the embedding regulariser."""
+    users, pos, neg = batch[0], batch[1] + n_users, batch[2] + n_users
+    user_tensor = users.repeat_interleave(2)
+    item_tensor = torch.stack((pos, neg)).t().contiguous().view(-1)
+    score = torch.sum(rep[user_tensor] * rep[item_tensor], dim=1).view(-1, 2)
+    loss = -torch.mean(torch.log(torch.sigmoid(torch.matmul(score, torch.tensor([[1.0], [-1.0]])))))
+    reg = (id_embedding[user_tensor] ** 2 + id_embedding[item_tensor] ** 2).mean() + (v_preference ** 2).mean()
+    return loss + reg_weight * reg
 
 
 # --------------------------------------------------------------------------------------

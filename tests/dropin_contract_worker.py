@@ -123,5 +123,67 @@ def main():
     print("CONTRACT " + json.dumps(out))
 
 
+def main_mmgcn():
+    """The same for MMGCN: OUR class (no torch_geometric needed) under the reference's harness against
+    tests/golden/mmgcn_tiny.npz, the reference's own model code run under a PyG shim (tests/golden/ref_loader.py)."""
+    import ref_loader
+    from mmrec_b200.utils import synth
+    ref_loader.install()
+    tmp = tempfile.mkdtemp(prefix="mmrec_contract_")
+    data = ref_loader.run_dir(tmp)
+    u, i, e, d, f = synth.SHAPES["tiny"]
+    g = synth.make_graph(u, i, e, seed=0)
+    v, t = synth.make_features(i, f, seed=1)
+    synth.write_dataset(data, "tiny", g, v, t)
+    from utils.configurator import Config
+    from utils.dataset import RecDataset
+    from utils.dataloader import TrainDataLoader, EvalDataLoader
+    from utils.utils import init_seed
+    from common.trainer import Trainer
+    config = Config("MMGCN", "tiny", {"gpu_id": 0, "use_gpu": False, "eval_batch_size": 128, "train_batch_size": 512})
+    config["inter_file_name"] = "tiny.inter"
+    config["USER_ID_FIELD"], config["ITEM_ID_FIELD"] = "userID", "itemID"
+    config["vision_feature_file"], config["text_feature_file"] = "image_feat.npy", "text_feat.npy"
+    for k in config["hyper_parameters"]:
+        if isinstance(config[k], list):
+            config[k] = config[k][0]
+    dataset = RecDataset(config)
+    str(dataset)                                                    # (the reference computes inter_num / user_num in __str__)
+    tr, va, te = dataset.split()
+    str(tr), str(va), str(te)
+    train_data = TrainDataLoader(config, tr, batch_size=config["train_batch_size"], shuffle=True)
+    valid_data = EvalDataLoader(config, va, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    init_seed(config["seed"])
+    train_data.pretrain_setup()
+    install_cpu_ops()
+    from mmrec_b200.models.mmgcn import MMGCN
+    model = MMGCN(config, train_data).to(config["device"])
+    gold = np.load(os.path.join(HERE, "golden", "mmgcn_tiny.npz"), allow_pickle=True)
+    sd = model.state_dict()
+    init_identical = all(np.array_equal(sd[k[len("param0."):]].numpy(), gold[k]) for k in gold.files if k.startswith("param0.")) \
+        and [k for k, _ in model.named_parameters()] == [str(x) for x in gold["param_order"]] \
+        and np.array_equal(model.id_embedding.detach().numpy(), gold["id_embedding"]) \
+        and np.array_equal(model.v_gcn.preference.detach().numpy(), gold["v_preference"]) \
+        and np.array_equal(model.t_gcn.preference.detach().numpy(), gold["t_preference"])
+
+    def rel(a, b):
+        return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / np.linalg.norm(b))
+    model.train()
+    loss = model.calculate_loss(torch.from_numpy(gold["batch"]))
+    loss.backward()
+    grad_rel = max(rel(p.grad.numpy(), gold["grad." + k]) for k, p in model.named_parameters() if "grad." + k in gold.files)
+    model.eval()
+    with torch.no_grad():
+        fwd_rel = rel(model.forward().numpy(), gold["fwd"])
+        sc = model.full_sort_predict([torch.from_numpy(gold["eval_users"]), torch.from_numpy(gold["eval_mask"])])
+        score_err = float(np.abs(sc.numpy() - gold["scores"]).max())
+    valid = Trainer(config, model).evaluate(valid_data)
+    names = [str(x) for x in gold["metric_names"]]
+    out = {"init_identical": bool(init_identical), "fwd_rel": fwd_rel, "loss": float(loss.item()), "want_loss": float(gold["loss"][0]),
+           "grad_rel": grad_rel, "score_err": score_err, "valid": {k: float(v) for k, v in valid.items()},
+           "want_valid": dict(zip(names, [float(x) for x in gold["metric_values"]]))}
+    print("CONTRACT " + json.dumps(out))
+
+
 if __name__ == "__main__":
-    main()
+    main_mmgcn() if len(sys.argv) > 1 and sys.argv[1] == "mmgcn" else main()

@@ -170,6 +170,55 @@ def dump_model(model_name, overrides, out):
     return config, train_data, valid_data, test_data, model
 
 
+def dump_mmgcn(overrides, out):
+    """MMGCN: the reference's own model code under `ref_loader.install_pyg_shim()` (torch_geometric is absent; only its
+    MessagePassing('mean') primitive and `inits.uniform` are restated there).  `id_embedding` / `preference` are plain
+    tensors in the reference (`mmgcn.py:57,125`), recorded beside the state_dict."""
+    from common.trainer import Trainer
+    ref_loader.install_pyg_shim()
+    config, train_data, valid_data, test_data, model = build("MMGCN", overrides)
+    g = {"n_users": np.int64(model.n_users), "n_items": np.int64(model.n_items), "cfg_reg_weight": np.float64(config["reg_weight"]),
+         "cfg_embedding_size": np.float64(config["embedding_size"])}
+    g["edge_index"] = model.edge_index.numpy().copy()
+    for k, v in model.state_dict().items():
+        g["param0." + k] = v.detach().numpy().copy()
+    g["param_order"] = np.array([k for k, _ in model.named_parameters()])
+    g["id_embedding"] = model.id_embedding.detach().numpy().copy()
+    g["v_preference"], g["t_preference"] = model.v_gcn.preference.detach().numpy().copy(), model.t_gcn.preference.detach().numpy().copy()
+    g["v_feat"], g["t_feat"] = model.v_feat.numpy().copy(), model.t_feat.numpy().copy()
+    import random
+    random.seed(7); np.random.seed(7)
+    batch = next(iter(train_data))
+    train_data.pr = 0
+    g["batch"] = batch.numpy().copy()
+    model.train()
+    model.zero_grad()
+    loss = model.calculate_loss(batch)
+    loss.backward()
+    g["loss"] = loss.detach().numpy().reshape(-1).copy()
+    for k, p_ in model.named_parameters():
+        if p_.grad is not None and p_.numel() <= 300 * 64:
+            g["grad." + k] = p_.grad.numpy().copy()
+    g["grad.id_embedding"] = model.id_embedding.grad.numpy().copy()
+    model.eval()
+    with torch.no_grad():
+        rep = model.forward()
+        g["fwd"] = rep.numpy().copy()
+        eb = next(iter(valid_data))
+        valid_data.pr = 0; valid_data.inter_pr = 0
+        scores = model.full_sort_predict(eb)
+        g["eval_users"], g["eval_mask"] = eb[0].numpy().copy(), eb[1].numpy().copy()
+        g["scores"] = scores.numpy().copy()
+        scores[eb[1][0], eb[1][1]] = -1e10
+        tv, ti = torch.topk(scores, max(config["topk"]), dim=-1)
+        g["topk_idx"], g["topk_val"] = ti.numpy().copy(), tv.numpy().copy()
+    res = Trainer(config, model).evaluate(valid_data)
+    g["metric_names"] = np.array(list(res.keys()))
+    g["metric_values"] = np.array([res[k] for k in res], dtype=np.float64)
+    np.savez_compressed(out, **g)
+    print(f"MMGCN: wrote {out} ({os.path.getsize(out)/1024:.0f} KiB), loss {float(g['loss'][0]):.6f}")
+
+
 def dump_trajectory(model_name, overrides, out, epochs=2):
     """Train with the reference's own Trainer; record every batch, every batch loss, per-epoch metrics."""
     from common.trainer import Trainer
@@ -236,6 +285,7 @@ def main():
     dump_model("MGCN", common, os.path.join(HERE, "mgcn_tiny.npz"))
     dump_model("LightGCN", dict(common, n_layers=[3]), os.path.join(HERE, "lightgcn_tiny.npz"))
     dump_model("LayerGCN", dict(common, dropout=[0.1]), os.path.join(HERE, "layergcn_tiny.npz"))
+    dump_mmgcn(common, os.path.join(HERE, "mmgcn_tiny.npz"))
     dump_trajectory("LightGCN", dict(common, n_layers=[2], reg_weight=[1e-4]), os.path.join(HERE, "traj_lightgcn_tiny.npz"))
     dump_trajectory("FREEDOM", dict(common, dropout=[0.0], reg_weight=[1e-3]), os.path.join(HERE, "traj_freedom_tiny.npz"))
 

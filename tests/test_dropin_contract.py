@@ -26,3 +26,20 @@ def test_our_model_class_under_the_reference_trainer():
         assert abs(r["test"][k] - v) < 1e-9, (k, r["test"][k], v)
     assert abs(r["loss"] - r["want_loss"]) <= 1e-5 * abs(r["want_loss"])
     assert r["has_grads"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+def test_our_mmgcn_class_against_the_reference_model_code():
+    """MMGCN (torch_geometric absent): our PyG-free class under the reference's harness reproduces what the reference's own
+    model code produced under the PyG shim -- initial weights bit for bit, forward / loss / gradients / scores to fp32 rounding,
+    and the metrics of the reference's `Trainer.evaluate`."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_contract_worker.py"), "mmgcn"], capture_output=True,
+                         text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("CONTRACT ")]
+    assert out.returncode == 0 and lines, out.stdout[-3000:] + out.stderr[-3000:]
+    r = json.loads(lines[-1][len("CONTRACT "):])
+    assert r["init_identical"]
+    assert r["fwd_rel"] < 1e-6 and r["grad_rel"] < 1e-4 and r["score_err"] < 1e-6
+    assert abs(r["loss"] - r["want_loss"]) <= 1e-6 * abs(r["want_loss"])
+    for k, v in r["want_valid"].items():
+        assert abs(r["valid"][k] - v) < 1e-9, (k, r["valid"][k], v)

@@ -209,3 +209,29 @@ def test_metrics_from_first_batch_only_if_single_batch(golden):
     m = O.topk_metrics(ti.numpy(), list(g["test_pos_items"]))
     got = np.array([m[k] for k in g["metric_names"]])
     np.testing.assert_allclose(got, g["test_metric_values"], atol=1e-12)
+
+
+def test_mmgcn_matches_reference_model_code(golden):
+    """MMGCN's towers, loss, gradients and scoring (`src/models/mmgcn.py:22-188`) against the reference's own model code run
+    under the PyG shim of tests/golden/ref_loader.py (the shim and the oracle restate the same documented primitive,
+    `MessagePassing(aggr='mean')`; that part is not an independent check and says so)."""
+    g = golden("mmgcn_tiny.npz")
+    U = int(g["n_users"])
+    p = params(g)
+    ei, ide = T(g["edge_index"]), T(g["id_embedding"]).requires_grad_()
+    vp, tp = T(g["v_preference"]).requires_grad_(), T(g["t_preference"]).requires_grad_()
+    for v in p.values():
+        v.requires_grad_()
+    rep = O.mmgcn_forward(p, ei, T(g["v_feat"]), T(g["t_feat"]), ide, vp, tp)
+    assert np.array_equal(rep.detach().numpy(), g["fwd"])
+    loss = O.mmgcn_loss(rep, ide, vp, T(g["batch"]), U, float(g["cfg_reg_weight"]))
+    assert np.array_equal(loss.detach().numpy().reshape(-1), g["loss"])
+    loss.backward()
+    np.testing.assert_allclose(ide.grad.numpy(), g["grad.id_embedding"], rtol=1e-5, atol=1e-8)
+    for k in g.files:
+        if k.startswith("grad.") and k != "grad.id_embedding":
+            np.testing.assert_allclose(p[k[5:]].grad.numpy(), g[k], rtol=1e-5, atol=1e-8, err_msg=k)
+    s = O.full_sort_scores(rep.detach()[:U], rep.detach()[U:], T(g["eval_users"]))
+    assert np.array_equal(s.numpy(), g["scores"])
+    _, ti = O.mask_topk(s.clone(), T(g["eval_mask"]), g["topk_idx"].shape[1])
+    assert np.array_equal(ti.numpy(), g["topk_idx"])
