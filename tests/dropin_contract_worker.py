@@ -63,6 +63,41 @@ def install_cpu_ops():
         return O.normalize_adj_m(torch.stack([users, items]), n_users, n_items)
     ops.bipartite_norm = bipartite_norm
 
+    # inference-only entry points (restated from their documented formulas in include/mmrec_b200.h)
+    def spmm_raw(A, X, Y=None, acc_in=None, acc_out=None, acc_div=1.0, gate_ref=None, use_plan=True, y_accumulate=False):
+        y = torch.sparse.mm(A.t_, X)
+        if gate_ref is not None:
+            y = torch.nn.functional.cosine_similarity(y, gate_ref, dim=-1).unsqueeze(1) * y
+        if acc_out is not None:
+            acc_out.copy_(((y if acc_in is None else acc_in + y)) / acc_div)
+        if Y is not None:
+            Y.copy_(Y + y if y_accumulate else y)
+    ops.spmm_raw = spmm_raw
+
+    def gate_rows(x, weight, bias, mul=None, out=None):
+        r = torch.sigmoid(torch.nn.functional.linear(x, weight, bias))
+        r = r if mul is None else mul * r
+        return r if out is None else out.copy_(r)
+    ops.gate_rows = gate_rows
+
+    def mgcn_fuse(img, txt, content, q_w, q_b, q_w2, gi_w, gi_b, gt_w, gt_b, want_side=False):
+        lin = torch.nn.functional.linear
+        att = torch.cat([lin(torch.tanh(lin(img, q_w, q_b)), q_w2), lin(torch.tanh(lin(txt, q_w, q_b)), q_w2)], dim=-1)
+        w = torch.softmax(att, dim=-1)
+        common = w[:, 0].unsqueeze(1) * img + w[:, 1].unsqueeze(1) * txt
+        side = (torch.sigmoid(lin(content, gi_w, gi_b)) * (img - common) + torch.sigmoid(lin(content, gt_w, gt_b)) * (txt - common) + common) / 3
+        return (content + side, side) if want_side else content + side
+    ops.mgcn_fuse = mgcn_fuse
+
+    def propagate_layergcn(A, ego, n_layers):
+        acc, x = torch.zeros_like(ego), ego
+        for _ in range(n_layers):
+            x = torch.sparse.mm(A.t_, x)
+            x = torch.nn.functional.cosine_similarity(x, ego, dim=-1).unsqueeze(1) * x
+            acc = acc + x
+        return acc
+    ops.propagate_layergcn = propagate_layergcn
+
 
 def main():
     import ref_loader
@@ -185,5 +220,90 @@ def main_mmgcn():
     print("CONTRACT " + json.dumps(out))
 
 
+def main_model(name):
+    """BM3 / MGCN / LightGCN / LayerGCN: our class under the reference's harness against the golden file of the reference's
+    own class -- initial weights, `forward`, the loss on the recorded batch WITH the reference's RNG draws (BM3's always-on
+    dropout: same `torch.manual_seed(4321)` stream as tests/golden/make_golden.py), first-batch scores, `Trainer.evaluate`."""
+    import ref_loader
+    from mmrec_b200.utils import synth
+    ref_loader.install()
+    tmp = tempfile.mkdtemp(prefix="mmrec_contract_")
+    data = ref_loader.run_dir(tmp)
+    u, i, e, d, f = synth.SHAPES["tiny"]
+    g = synth.make_graph(u, i, e, seed=0)
+    v, t = synth.make_features(i, f, seed=1)
+    synth.write_dataset(data, "tiny", g, v, t)
+    from utils.configurator import Config
+    from utils.dataset import RecDataset
+    from utils.dataloader import TrainDataLoader, EvalDataLoader
+    from utils.utils import init_seed
+    from common.trainer import Trainer
+    over = {"BM3": {}, "MGCN": {}, "LightGCN": {"n_layers": [3]}, "LayerGCN": {"dropout": [0.1]}}[name]
+    config = Config(name, "tiny", dict({"gpu_id": 0, "use_gpu": False, "eval_batch_size": 128, "train_batch_size": 512}, **over))
+    config["inter_file_name"] = "tiny.inter"
+    config["USER_ID_FIELD"], config["ITEM_ID_FIELD"] = "userID", "itemID"
+    config["vision_feature_file"], config["text_feature_file"] = "image_feat.npy", "text_feat.npy"
+    for k in config["hyper_parameters"]:
+        if isinstance(config[k], list):
+            config[k] = config[k][0]
+    dataset = RecDataset(config)
+    str(dataset)
+    tr, va, te = dataset.split()
+    str(tr), str(va), str(te)
+    train_data = TrainDataLoader(config, tr, batch_size=config["train_batch_size"], shuffle=True)
+    valid_data = EvalDataLoader(config, va, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    test_data = EvalDataLoader(config, te, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    init_seed(config["seed"])
+    train_data.pretrain_setup()
+    install_cpu_ops()
+    import importlib
+    cls = getattr(importlib.import_module("mmrec_b200.models." + name.lower()), name)
+    model = cls(config, train_data).to(config["device"])
+    gold = np.load(os.path.join(HERE, "golden", name.lower() + "_tiny.npz"), allow_pickle=True)
+    sd = model.state_dict()
+    init_identical = all(np.array_equal(sd[k[len("param0."):]].numpy(), gold[k]) for k in gold.files if k.startswith("param0.")) \
+        and [k for k, _ in model.named_parameters()] == [str(x) for x in gold["param_order"]]
+
+    def rel(a, b):
+        return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+    model.eval()
+    with torch.no_grad():
+        if name == "MGCN":
+            fu, fi = model.forward(model.norm_adj)                   # no autograd: the gate / fuse / stacked-table route (a5b)
+        elif name == "LayerGCN":
+            model.forward_adj = model.norm_adj_matrix
+            fu, fi = model.forward()
+        else:
+            fu, fi = model.forward()
+    fwd_rel = max(rel(fu.numpy(), gold["fwd_u"]), rel(fi.numpy(), gold["fwd_i"]))
+    model.train()
+    torch.manual_seed(1234)
+    if name == "LayerGCN":
+        model.masked_adj = model.pruner.adj_from_keep(torch.from_numpy(gold["prune_keep_idx"]))
+    torch.manual_seed(4321)                                          # BM3's F.dropout draws, as in make_golden.py
+    model.zero_grad()
+    loss = model.calculate_loss(torch.from_numpy(gold["batch"]))
+    loss = sum(loss) if isinstance(loss, tuple) else loss
+    loss.backward()
+    named = dict(model.named_parameters())
+    gmax = max(float(np.abs(gold[k]).max()) for k in gold.files if k.startswith("grad."))
+    grad_ok = all(np.linalg.norm(named[k[5:]].grad.numpy().astype(np.float64) - gold[k]) < 1e-4 * np.linalg.norm(gold[k]) + 1e-7 * gmax * np.sqrt(gold[k].size)
+                  for k in gold.files if k.startswith("grad."))
+    model.eval()
+    with torch.no_grad():
+        sc = model.full_sort_predict([torch.from_numpy(gold["eval_users"]), torch.from_numpy(gold["eval_mask"])])
+    score_err = float(np.abs(sc.numpy() - gold["scores"]).max() / np.abs(gold["scores"]).max())
+    trainer = Trainer(config, model)
+    valid = trainer.evaluate(valid_data)
+    test = trainer.evaluate(test_data, is_test=True)
+    names = [str(x) for x in gold["metric_names"]]
+    out = {"model": name, "init_identical": bool(init_identical), "fwd_rel": fwd_rel, "loss": float(loss.item()),
+           "want_loss": float(np.asarray(gold["loss"]).sum()), "grad_ok": bool(grad_ok), "score_err": score_err,
+           "valid": {k: float(v) for k, v in valid.items()}, "want_valid": dict(zip(names, [float(x) for x in gold["metric_values"]])),
+           "test": {k: float(v) for k, v in test.items()}, "want_test": dict(zip(names, [float(x) for x in gold["test_metric_values"]]))}
+    print("CONTRACT " + json.dumps(out))
+
+
 if __name__ == "__main__":
-    main_mmgcn() if len(sys.argv) > 1 and sys.argv[1] == "mmgcn" else main()
+    arg = sys.argv[1] if len(sys.argv) > 1 else ""
+    main_mmgcn() if arg == "mmgcn" else (main_model(arg) if arg else main())

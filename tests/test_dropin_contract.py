@@ -43,3 +43,25 @@ def test_our_mmgcn_class_against_the_reference_model_code():
     assert abs(r["loss"] - r["want_loss"]) <= 1e-6 * abs(r["want_loss"])
     for k, v in r["want_valid"].items():
         assert abs(r["valid"][k] - v) < 1e-9, (k, r["valid"][k], v)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("name", ["BM3", "MGCN", "LightGCN", "LayerGCN"])
+def test_our_model_classes_under_the_reference_harness(name):
+    """The other north-star classes as drop-ins under the reference's Config / RecDataset / loaders / Trainer (kernels replaced by
+    torch-CPU stand-ins): initial weights bit for bit, `forward` (MGCN: the no-autograd gate / fuse / stacked-table route),
+    the loss on the recorded batch under the reference's RNG stream -- BM3's always-on `F.dropout` branch (`bm3.py:110-119`)
+    included, which the device tests can only check with dropout switched off --, gradients, first-batch scores and the
+    reference Trainer's valid / test metrics."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_contract_worker.py"), name], capture_output=True, text=True,
+                         timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("CONTRACT ")]
+    assert out.returncode == 0 and lines, out.stdout[-3000:] + out.stderr[-3000:]
+    r = json.loads(lines[-1][len("CONTRACT "):])
+    assert r["init_identical"] and r["grad_ok"]
+    assert r["fwd_rel"] < 1e-6 and r["score_err"] < 1e-6
+    assert abs(r["loss"] - r["want_loss"]) <= 1e-6 * abs(r["want_loss"])
+    for k, v in r["want_valid"].items():
+        assert abs(r["valid"][k] - v) < 1e-9, (k, r["valid"][k], v)
+    for k, v in r["want_test"].items():
+        assert abs(r["test"][k] - v) < 1e-9, (k, r["test"][k], v)
