@@ -304,6 +304,72 @@ def main_model(name):
     print("CONTRACT " + json.dumps(out))
 
 
+def main_traj(name):
+    """Two epochs of the reference's own training loop (`Trainer._train_epoch`, its Adam, its scheduler, its dataloader's
+    shuffling and negative sampling) driving OUR class, against the trajectory the reference's class produced
+    (tests/golden/traj_*_tiny.npz: every batch, every batch loss, per-epoch metrics)."""
+    import ref_loader
+    from mmrec_b200.utils import synth
+    ref_loader.install()
+    tmp = tempfile.mkdtemp(prefix="mmrec_contract_")
+    data = ref_loader.run_dir(tmp)
+    u, i, e, d, f = synth.SHAPES["tiny"]
+    g = synth.make_graph(u, i, e, seed=0)
+    v, t = synth.make_features(i, f, seed=1)
+    synth.write_dataset(data, "tiny", g, v, t)
+    from utils.configurator import Config
+    from utils.dataset import RecDataset
+    from utils.dataloader import TrainDataLoader, EvalDataLoader
+    from utils.utils import init_seed
+    from common.trainer import Trainer
+    over = {"LightGCN": {"n_layers": [2], "reg_weight": [1e-4]}, "FREEDOM": {"dropout": [0.0], "reg_weight": [1e-3]}}[name]
+    config = Config(name, "tiny", dict({"gpu_id": 0, "use_gpu": False, "eval_batch_size": 128, "train_batch_size": 512}, **over))
+    config["inter_file_name"] = "tiny.inter"
+    config["USER_ID_FIELD"], config["ITEM_ID_FIELD"] = "userID", "itemID"
+    config["vision_feature_file"], config["text_feature_file"] = "image_feat.npy", "text_feat.npy"
+    for k in config["hyper_parameters"]:
+        if isinstance(config[k], list):
+            config[k] = config[k][0]
+    config["epochs"] = 2
+    dataset = RecDataset(config)
+    str(dataset)
+    tr, va, te = dataset.split()
+    str(tr), str(va), str(te)
+    train_data = TrainDataLoader(config, tr, batch_size=config["train_batch_size"], shuffle=True)
+    valid_data = EvalDataLoader(config, va, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    test_data = EvalDataLoader(config, te, additional_dataset=tr, batch_size=config["eval_batch_size"])
+    init_seed(config["seed"])
+    train_data.pretrain_setup()
+    install_cpu_ops()
+    import importlib
+    model = getattr(importlib.import_module("mmrec_b200.models." + name.lower()), name)(config, train_data).to(config["device"])
+    gold = np.load(os.path.join(HERE, "golden", "traj_%s_tiny.npz" % name.lower()), allow_pickle=True)
+    trainer = Trainer(config, model)
+    rec = {"batches": [], "losses": [], "valid": [], "test": []}
+    orig = model.calculate_loss
+
+    def spy(interaction):
+        rec["batches"].append(interaction.numpy().copy())
+        l = orig(interaction)
+        rec["losses"].append(float(sum(l)) if isinstance(l, tuple) else float(l))
+        return l
+    model.calculate_loss = spy
+    for ep in range(2):
+        model.pre_epoch_processing()
+        trainer._train_epoch(train_data, ep)
+        trainer.lr_scheduler.step()
+        rec["valid"].append(list(trainer.evaluate(valid_data).values()))
+        rec["test"].append(list(trainer.evaluate(test_data).values()))
+    batches = np.concatenate(rec["batches"], axis=1)
+    out = {"model": name, "same_batches": bool(batches.shape == gold["batches"].shape and np.array_equal(batches, gold["batches"])),
+           "n_batches": len(rec["losses"]), "loss_max_rel": float(np.max(np.abs(np.array(rec["losses"]) - gold["losses"]) / np.abs(gold["losses"]))),
+           "metric_max_abs": float(max(np.abs(np.array(rec["valid"]) - gold["valid"]).max(), np.abs(np.array(rec["test"]) - gold["test"]).max())),
+           "first_loss": rec["losses"][0], "last_loss": rec["losses"][-1], "want_last_loss": float(gold["losses"][-1])}
+    print("CONTRACT " + json.dumps(out))
+
+
 if __name__ == "__main__":
     arg = sys.argv[1] if len(sys.argv) > 1 else ""
+    if arg.startswith("traj:"):
+        main_traj(arg[5:]); sys.exit(0)
     main_mmgcn() if arg == "mmgcn" else (main_model(arg) if arg else main())

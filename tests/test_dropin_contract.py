@@ -65,3 +65,17 @@ def test_our_model_classes_under_the_reference_harness(name):
         assert abs(r["valid"][k] - v) < 1e-9, (k, r["valid"][k], v)
     for k, v in r["want_test"].items():
         assert abs(r["test"][k] - v) < 1e-9, (k, r["test"][k], v)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("name", ["LightGCN", "FREEDOM"])
+def test_reference_training_loop_drives_our_class(name):
+    """Two epochs of the reference's own `Trainer._train_epoch` (its Adam, scheduler, shuffling, negative sampling) on OUR class:
+    the same batches, every batch loss and the per-epoch valid / test metrics of the trajectory the reference's class recorded."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_contract_worker.py"), "traj:" + name], capture_output=True,
+                         text=True, timeout=900)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("CONTRACT ")]
+    assert out.returncode == 0 and lines, out.stdout[-3000:] + out.stderr[-3000:]
+    r = json.loads(lines[-1][len("CONTRACT "):])
+    assert r["same_batches"] and r["n_batches"] == 8
+    assert r["loss_max_rel"] < 1e-6 and r["metric_max_abs"] < 1e-9
