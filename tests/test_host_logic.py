@@ -299,3 +299,23 @@ def test_unique_sorted_is_np_unique():
     n = 8000
     k = np.unique(np.concatenate([r * n + (c + 5000), (c + 5000) * n + r]))
     assert np.array_equal(rows, k // n) and np.array_equal(cols, k % n) and vals.dtype == np.float32
+
+
+def test_every_ops_and_graph_name_spelled_in_the_package_exists():
+    """No GPU here, so most of `mmrec_b200` cannot be executed: at least every `ops.<name>` / `graph.<name>` / `_lib.<name>` the
+    package, bench.py, the tools and the entry points spell must exist, and every C entry point `ops` calls must be bound."""
+    import re
+    from mmrec_b200 import _lib, graph as G, ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(dp, f) for top in ("mmrec_b200", "tools") for dp, _, fs in os.walk(os.path.join(root, top)) for f in fs if f.endswith(".py")]
+    files += [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    for path in files:
+        src = open(path).read()
+        for name in set(re.findall(r"(?<![\w.])ops\.([a-zA-Z_]\w*)", src)):
+            assert hasattr(ops, name), f"{path}: ops.{name} does not exist"
+        for name in set(re.findall(r"(?<![\w.])graph\.([a-zA-Z_]\w*)", src)):
+            assert hasattr(G, name), f"{path}: graph.{name} does not exist"
+        for name in set(re.findall(r"(?<![\w.])_lib\.([a-zA-Z_]\w*)", src)):
+            assert hasattr(_lib, name), f"{path}: _lib.{name} does not exist"
+        for name in set(re.findall(r"\.(mmrec_[a-z0-9_]+)\(", src)):
+            assert name in _lib.PROTOTYPES, f"{path}: C entry point {name} is called but not bound in _lib.PROTOTYPES"
