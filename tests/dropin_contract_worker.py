@@ -322,7 +322,13 @@ def main_traj(name):
     from utils.dataloader import TrainDataLoader, EvalDataLoader
     from utils.utils import init_seed
     from common.trainer import Trainer
-    over = {"LightGCN": {"n_layers": [2], "reg_weight": [1e-4]}, "FREEDOM": {"dropout": [0.0], "reg_weight": [1e-3]}}[name]
+    # key -> (model class, overrides of make_golden.py's dump_trajectory call, golden file)
+    name, over, gfile = {"LightGCN": ("LightGCN", {"n_layers": [2], "reg_weight": [1e-4]}, "traj_lightgcn_tiny.npz"),
+                         "FREEDOM": ("FREEDOM", {"dropout": [0.0], "reg_weight": [1e-3]}, "traj_freedom_tiny.npz"),
+                         "FREEDOM-prune": ("FREEDOM", {"dropout": [0.8], "reg_weight": [1e-3]}, "traj_freedom_prune_tiny.npz"),
+                         "LayerGCN": ("LayerGCN", {"dropout": [0.1]}, "traj_layergcn_tiny.npz"),
+                         "BM3": ("BM3", {}, "traj_bm3_tiny.npz"),
+                         "MGCN": ("MGCN", {}, "traj_mgcn_tiny.npz")}[name]
     config = Config(name, "tiny", dict({"gpu_id": 0, "use_gpu": False, "eval_batch_size": 128, "train_batch_size": 512}, **over))
     config["inter_file_name"] = "tiny.inter"
     config["USER_ID_FIELD"], config["ITEM_ID_FIELD"] = "userID", "itemID"
@@ -343,7 +349,7 @@ def main_traj(name):
     install_cpu_ops()
     import importlib
     model = getattr(importlib.import_module("mmrec_b200.models." + name.lower()), name)(config, train_data).to(config["device"])
-    gold = np.load(os.path.join(HERE, "golden", "traj_%s_tiny.npz" % name.lower()), allow_pickle=True)
+    gold = np.load(os.path.join(os.environ.get("MMREC_TRAJ_DIR", os.path.join(HERE, "golden")), gfile), allow_pickle=True)
     trainer = Trainer(config, model)
     rec = {"batches": [], "losses": [], "valid": [], "test": []}
     orig = model.calculate_loss

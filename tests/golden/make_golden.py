@@ -219,7 +219,7 @@ def dump_mmgcn(overrides, out):
     print(f"MMGCN: wrote {out} ({os.path.getsize(out)/1024:.0f} KiB), loss {float(g['loss'][0]):.6f}")
 
 
-def dump_trajectory(model_name, overrides, out, epochs=2):
+def dump_trajectory(model_name, overrides, out, epochs=2, slim=False):
     """Train with the reference's own Trainer; record every batch, every batch loss, per-epoch metrics."""
     from common.trainer import Trainer
     config, train_data, valid_data, test_data, model = build(model_name, overrides)
@@ -246,7 +246,7 @@ def dump_trajectory(model_name, overrides, out, epochs=2):
         batch_epoch.append(len(rec["batches"]) - n0)
         rec["valid"].append(list(trainer.evaluate(valid_data).values()))
         rec["test"].append(list(trainer.evaluate(test_data).values()))
-    g = {k: v for k, v in rec.items() if k.startswith("param0.")}
+    g = {} if slim else {k: v for k, v in rec.items() if k.startswith("param0.")}    # slim: batches / losses / metrics only
     g["batch_sizes"] = np.array([b.shape[1] for b in rec["batches"]])
     g["batches"] = np.concatenate(rec["batches"], axis=1)
     g["batches_per_epoch"] = np.array(batch_epoch)
@@ -255,7 +255,7 @@ def dump_trajectory(model_name, overrides, out, epochs=2):
     g["test"] = np.array(rec["test"], dtype=np.float64)
     g["metric_names"] = np.array(list(trainer.evaluate(valid_data).keys()))
     for k, p in model.state_dict().items():
-        if p.numel() <= 300 * 64:
+        if p.numel() <= 300 * 64 and not slim:
             g["paramT." + k] = p.detach().numpy().copy()
     g["learning_rate"] = np.float64(config["learning_rate"])
     np.savez_compressed(out, **g)
@@ -288,6 +288,14 @@ def main():
     dump_mmgcn(common, os.path.join(HERE, "mmgcn_tiny.npz"))
     dump_trajectory("LightGCN", dict(common, n_layers=[2], reg_weight=[1e-4]), os.path.join(HERE, "traj_lightgcn_tiny.npz"))
     dump_trajectory("FREEDOM", dict(common, dropout=[0.0], reg_weight=[1e-3]), os.path.join(HERE, "traj_freedom_tiny.npz"))
+    # CPU contract trajectories (tests/test_dropin_contract.py): per-epoch pruning, dropout and the MGCN route in the loop
+    dump_trajectory("FREEDOM", dict(common, dropout=[0.8], reg_weight=[1e-3]), os.path.join(HERE, "traj_freedom_prune_tiny.npz"), slim=True)
+    for fcache in os.listdir(os.path.join(data_root, DATASET)):
+        if fcache.endswith(".pt"):
+            os.remove(os.path.join(data_root, DATASET, fcache))
+    dump_trajectory("LayerGCN", dict(common, dropout=[0.1]), os.path.join(HERE, "traj_layergcn_tiny.npz"), slim=True)
+    dump_trajectory("BM3", common, os.path.join(HERE, "traj_bm3_tiny.npz"), slim=True)
+    dump_trajectory("MGCN", common, os.path.join(HERE, "traj_mgcn_tiny.npz"), slim=True)
 
 
 if __name__ == "__main__":

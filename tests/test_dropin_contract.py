@@ -79,3 +79,18 @@ def test_reference_training_loop_drives_our_class(name):
     r = json.loads(lines[-1][len("CONTRACT "):])
     assert r["same_batches"] and r["n_batches"] == 8
     assert r["loss_max_rel"] < 1e-6 and r["metric_max_abs"] < 1e-9
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("key", ["FREEDOM-prune", "LayerGCN", "BM3", "MGCN"])
+def test_reference_training_loop_with_pruning_and_dropout(key):
+    """The same two-epoch replay where the model draws random numbers inside the loop: FREEDOM's and LayerGCN's per-epoch
+    degree-sensitive pruning (`freedom.py:128-162`: the `torch.multinomial` stream and the graph rebuilt from it), BM3's dropout,
+    and MGCN (whose evaluations go through the fused inference route).  Same batches, every loss and metric exactly."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_contract_worker.py"), "traj:" + key], capture_output=True,
+                         text=True, timeout=900)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("CONTRACT ")]
+    assert out.returncode == 0 and lines, out.stdout[-3000:] + out.stderr[-3000:]
+    r = json.loads(lines[-1][len("CONTRACT "):])
+    assert r["same_batches"] and r["n_batches"] == 8
+    assert r["loss_max_rel"] < 1e-6 and r["metric_max_abs"] < 1e-9
