@@ -94,3 +94,15 @@ def test_reference_training_loop_with_pruning_and_dropout(key):
     r = json.loads(lines[-1][len("CONTRACT "):])
     assert r["same_batches"] and r["n_batches"] == 8
     assert r["loss_max_rel"] < 1e-6 and r["metric_max_abs"] < 1e-9
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+def test_golden_files_are_what_the_reference_produces():
+    """The pin itself: re-running tests/golden/make_golden.py's recipes against the unmodified reference reproduces committed
+    golden files (a model dump, the MMGCN dump under the PyG shim, a training trajectory) -- every array bit for bit, recorded
+    gradients to 1e-5 (CPU `index_put` backward is not run-to-run deterministic)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "regen_check.py")], capture_output=True, text=True, timeout=900)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("REGEN ")]
+    assert out.returncode == 0 and lines, out.stdout[-3000:] + out.stderr[-3000:]
+    for name, r in json.loads(lines[-1][len("REGEN "):]).items():
+        assert r["same_keys"] and r["reproduced"], (name, r)
